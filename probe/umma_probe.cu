@@ -1,0 +1,564 @@
+// umma_probe.cu -- hardware-behaviour probes for the design questions in DESIGN.md §3:
+//   T1 baseline kind::i8 UMMA (u8 x s8 -> s32) fed by TMA, SW128 / SW64 K-major
+//   T2 A operand start address shifted by whole rows (not a multiple of 8) inside one
+//      swizzled halo buffer, with descriptor base_offset = 0 vs (addr>>7)&7
+//   T3 TMA destination that is 128 B- but not 1024 B-aligned
+//   T4 operands written by ordinary st.shared with the hand-computed swizzle
+//   T5 un-swizzled "chunk-major" layout (LBO/SBO semantics) with 16 B row shifts
+//   T6 4-D NHWC TMA boxes with negative / out-of-bound coordinates (zero-filled halos)
+//   T7 packed f32x2 arithmetic and cvt.pack saturation used by the epilogue
+//   T8 MMA-only speed of light for kind::i8 (the tensor roofline denominator)
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o probe/umma_probe probe/umma_probe.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../deep-fusion_b200/csrc/sm100_ptx.cuh"
+
+using namespace sm100;
+
+#define CK(x)                                                                      \
+  do {                                                                             \
+    cudaError_t e_ = (x);                                                          \
+    if (e_ != cudaSuccess) {                                                       \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                     \
+    }                                                                              \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn) {
+    printf("no cuTensorMapEncodeTiled\n");
+    exit(2);
+  }
+  return (EncodeTiledFn)fn;
+}
+
+static CUtensorMapSwizzle swz_enum(int sw) {
+  return sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                   : sw == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                              : sw == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+
+// ------------------------------------------------------------------ T1..T5 MMA scenarios
+struct MmaCase {
+  int sw;         // 128, 64 or 0 (no swizzle, chunk-major)
+  int src;        // 0 = TMA, 1 = manual st.shared
+  int dst_row0;   // smem row at which A_big row 0 is placed (T3: not multiple of 8)
+  int shift;      // A descriptor starts at A_big row `shift`
+  int bo_mode;    // 0: base_offset = 0; 1: base_offset = (addr >> 7) & 7
+};
+
+constexpr int kArows = 384;  // A_big rows resident in smem
+constexpr int kN = 64;
+
+__global__ void __launch_bounds__(128, 1)
+probe_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const uint8_t* __restrict__ gA, const int8_t* __restrict__ gB, int32_t* __restrict__ gD,
+          MmaCase c) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  const int rowb = c.sw ? c.sw : 128;  // bytes of K per row (K extent of the test)
+  uint8_t* sA = smem;                               // (kArows + 16) rows
+  uint8_t* sB = smem + (kArows + 16) * 128;         // kN rows, 1024 aligned
+  __shared__ __align__(8) uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar_load), 1);
+    mbar_init(smem_u32(&bar_mma), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<64>(smem_u32(&tmem_base_s));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (c.src == 0) {
+    if (tid == 0) {
+      mbar_expect_tx(smem_u32(&bar_load), kArows * rowb + kN * rowb);
+      for (int b = 0; b < kArows / 128; ++b)
+        tma_load_2d(smem_u32(sA + (c.dst_row0 + b * 128) * rowb), &tmA, smem_u32(&bar_load), 0,
+                    b * 128);
+      tma_load_2d(smem_u32(sB), &tmB, smem_u32(&bar_load), 0, 0);
+    }
+    mbar_wait(smem_u32(&bar_load), 0);
+  } else {
+    // manual placement with the swizzle a TMA load would have applied (absolute-address based)
+    for (int idx = tid; idx < kArows * (rowb / 16); idx += 128) {
+      int r = idx / (rowb / 16), ch = idx % (rowb / 16);
+      uint4 v = *reinterpret_cast<const uint4*>(gA + (size_t)r * rowb + ch * 16);
+      uint32_t off;
+      if (c.sw == 0) {
+        off = ch * ((kArows + 16) * 16) + (c.dst_row0 + r) * 16;
+      } else {
+        uint32_t lin = (c.dst_row0 + r) * rowb + ch * 16;
+        // Swizzle<B,4,3>: XOR address bits [4,4+B) with bits [7,7+B)
+        uint32_t bits = c.sw == 128 ? 7u : (c.sw == 64 ? 3u : 1u);
+        off = lin ^ (((lin >> 7) & bits) << 4);
+      }
+      *reinterpret_cast<uint4*>(sA + off) = v;
+    }
+    for (int idx = tid; idx < kN * (rowb / 16); idx += 128) {
+      int r = idx / (rowb / 16), ch = idx % (rowb / 16);
+      uint4 v = *reinterpret_cast<const uint4*>(gB + (size_t)r * rowb + ch * 16);
+      uint32_t off;
+      if (c.sw == 0) {
+        off = ch * (kN * 16) + r * 16;
+      } else {
+        uint32_t lin = r * rowb + ch * 16;
+        uint32_t bits = c.sw == 128 ? 7u : (c.sw == 64 ? 3u : 1u);
+        off = lin ^ (((lin >> 7) & bits) << 4);
+      }
+      *reinterpret_cast<uint4*>(sB + off) = v;
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+  }
+
+  if (tid == 0) {
+    tc_fence_after_sync();
+    const uint32_t idesc = make_idesc_i8(128, kN, 0, 1);
+    const int nk = rowb / 32;
+    for (int k = 0; k < nk; ++k) {
+      uint64_t da, db;
+      if (c.sw == 0) {
+        uint32_t a0 = smem_u32(sA) + (c.dst_row0 + c.shift) * 16 + (k * 2) * ((kArows + 16) * 16);
+        uint32_t b0 = smem_u32(sB) + (k * 2) * (kN * 16);
+        da = make_smem_desc(a0, (kArows + 16) * 16, 128, kLayoutNone);
+        db = make_smem_desc(b0, kN * 16, 128, kLayoutNone);
+      } else {
+        uint32_t layout = c.sw == 128 ? kLayoutSW128 : (c.sw == 64 ? kLayoutSW64 : kLayoutSW32);
+        uint32_t a0 = smem_u32(sA) + (c.dst_row0 + c.shift) * rowb;
+        uint32_t bo = c.bo_mode ? ((a0 >> 7) & 7) : 0;
+        da = make_smem_desc(a0 + k * 32, 16, 8 * rowb, layout, bo);
+        db = make_smem_desc(smem_u32(sB) + k * 32, 16, 8 * rowb, layout, 0);
+      }
+      umma_i8(tmem, da, db, idesc, k > 0);
+    }
+    umma_commit(smem_u32(&bar_mma));
+  }
+  mbar_wait(smem_u32(&bar_mma), 0);
+  tc_fence_after_sync();
+  uint32_t r[32];
+  for (int cb = 0; cb < kN; cb += 32) {
+    tmem_ld_x32(tmem + ((warp * 32u) << 16) + cb, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) gD[(size_t)tid * kN + cb + j] = (int32_t)r[j];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+static int run_mma_cases(EncodeTiledFn enc) {
+  const int Kmax = 128;
+  std::vector<uint8_t> hA(kArows * Kmax);
+  std::vector<int8_t> hB(kN * Kmax);
+  srand(7);
+  for (auto& v : hA) v = rand() & 255;
+  for (auto& v : hB) v = (rand() % 255) - 127;
+  uint8_t* dA;
+  int8_t* dB;
+  int32_t* dD;
+  CK(cudaMalloc(&dA, hA.size()));
+  CK(cudaMalloc(&dB, hB.size()));
+  CK(cudaMalloc(&dD, 128 * kN * 4));
+  const size_t smem_bytes = (kArows + 16) * 128 + kN * 128 + 1024;
+  CK(cudaFuncSetAttribute(probe_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+
+  std::vector<MmaCase> cases;
+  for (int sw : {128, 64}) {
+    cases.push_back({sw, 0, 0, 0, 0});                                  // T1
+    for (int s : {8, 64, 1, 2, 3, 7, 9, 57, 58, 115})                   // T2
+      for (int bo : {0, 1}) cases.push_back({sw, 0, 0, s, bo});
+    for (int d0 : {sw == 128 ? 3 : 2, sw == 128 ? 5 : 6})               // T3 (dst 128 B aligned)
+      for (int s : {0, 1, 29})
+        for (int bo : {0, 1}) cases.push_back({sw, 0, d0, s, bo});
+    for (int s : {0, 1, 9, 58})                                         // T4
+      for (int bo : {0, 1}) cases.push_back({sw, 1, 0, s, bo});
+  }
+  for (int s : {0, 1, 7, 9, 58}) cases.push_back({0, 1, 0, s, 0});      // T5
+
+  int fails = 0;
+  for (const MmaCase& c : cases) {
+    const int rowb = c.sw ? c.sw : 128;
+    // host operands with K = rowb (first rowb bytes of each Kmax row are repacked densely)
+    std::vector<uint8_t> a(kArows * rowb);
+    std::vector<int8_t> b(kN * rowb);
+    for (int r = 0; r < kArows; ++r) memcpy(&a[r * rowb], &hA[r * Kmax], rowb);
+    for (int r = 0; r < kN; ++r) memcpy(&b[r * rowb], &hB[r * Kmax], rowb);
+    CK(cudaMemcpy(dA, a.data(), a.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, b.data(), b.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0xff, 128 * kN * 4));
+    CUtensorMap tmA, tmB;
+    memset(&tmA, 0, sizeof tmA);
+    memset(&tmB, 0, sizeof tmB);
+    if (c.sw) {
+      cuuint64_t gd[2] = {(cuuint64_t)rowb, (cuuint64_t)kArows};
+      cuuint64_t gs[1] = {(cuuint64_t)rowb};
+      cuuint32_t box[2] = {(cuuint32_t)rowb, 128};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r1 = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dA, gd, gs, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(c.sw),
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      cuuint64_t gdb[2] = {(cuuint64_t)rowb, (cuuint64_t)kN};
+      cuuint32_t boxb[2] = {(cuuint32_t)rowb, (cuuint32_t)kN};
+      CUresult r2 = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, dB, gdb, gs, boxb, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(c.sw),
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+        printf("encode failed %d %d\n", (int)r1, (int)r2);
+        return 1;
+      }
+    }
+    probe_mma<<<1, 128, smem_bytes>>>(tmA, tmB, dA, dB, dD, c);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("MMA sw=%d src=%d d0=%d shift=%d bo=%d : LAUNCH ERROR %s\n", c.sw, c.src, c.dst_row0,
+             c.shift, c.bo_mode, cudaGetErrorString(e));
+      return 1;  // context is dead
+    }
+    std::vector<int32_t> d(128 * kN);
+    CK(cudaMemcpy(d.data(), dD, d.size() * 4, cudaMemcpyDeviceToHost));
+    int bad = 0, first = -1;
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < kN; ++n) {
+        int32_t ref = 0;
+        for (int k = 0; k < rowb; ++k)
+          ref += (int)a[(c.shift + m) * rowb + k] * (int)b[n * rowb + k];
+        if (ref != d[m * kN + n]) {
+          if (first < 0) first = m * kN + n;
+          ++bad;
+        }
+      }
+    printf("MMA sw=%3d src=%s d0=%d shift=%3d bo=%d : %s (bad=%d first=%d)\n", c.sw,
+           c.src ? "manual" : "tma", c.dst_row0, c.shift, c.bo_mode, bad ? "FAIL" : "PASS", bad,
+           first);
+    fails += bad != 0;
+  }
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dD);
+  return fails;
+}
+
+// ------------------------------------------------------------------------ T6 halo loads
+// NHWC u8 tensor (N,H,W,C); loads `nrows` boxes {C, W+1, 1, 1} at rows h0.. of image n0
+// (h may be -1 or H -> all zero) and one box {C, W+1, 3, 1} at h0, dumps smem.
+__global__ void __launch_bounds__(128, 1)
+probe_halo(const __grid_constant__ CUtensorMap tmRow, const __grid_constant__ CUtensorMap tmBox3,
+           uint8_t* __restrict__ out, int C, int Wp, int n0, int h0, int nrows) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int rowbytes = Wp * C;
+  const int total = nrows * rowbytes + 3 * rowbytes;
+  for (int i = tid; i < total + 1024; i += 128) smem[i] = 0xAB;
+  __syncthreads();
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+    mbar_expect_tx(smem_u32(&bar), total);
+    for (int r = 0; r < nrows; ++r)
+      tma_load_4d(smem_u32(smem + r * rowbytes), &tmRow, smem_u32(&bar), 0, 0, h0 + r, n0);
+    // second region starts at the next 128 B-aligned (not 1024 B-aligned in general) address
+    tma_load_4d(smem_u32(smem + nrows * rowbytes), &tmBox3, smem_u32(&bar), 0, 0, h0, n0);
+  }
+  __syncthreads();
+  mbar_wait(smem_u32(&bar), 0);
+  for (int i = tid; i < total; i += 128) out[i] = smem[i];
+}
+
+static int run_halo(EncodeTiledFn enc) {
+  const int N = 2, H = 6, W = 5, C = 128, Wp = W + 1;
+  std::vector<uint8_t> h(N * H * W * C);
+  srand(11);
+  for (auto& v : h) v = 1 + rand() % 254;  // never 0 so zero-fill is detectable
+  uint8_t *d, *dout;
+  CK(cudaMalloc(&d, h.size()));
+  CK(cudaMemcpy(d, h.data(), h.size(), cudaMemcpyHostToDevice));
+  const int nrows = 5, h0 = -1, n0 = 1;
+  const int rowbytes = Wp * C, total = (nrows + 3) * rowbytes;
+  CK(cudaMalloc(&dout, total));
+  CUtensorMap tmRow, tmBox3;
+  cuuint64_t gd[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t gs[3] = {(cuuint64_t)C, (cuuint64_t)W * C, (cuuint64_t)H * W * C};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  cuuint32_t box1[4] = {(cuuint32_t)C, (cuuint32_t)Wp, 1, 1};
+  cuuint32_t box3[4] = {(cuuint32_t)C, (cuuint32_t)Wp, 3, 1};
+  CUresult r1 = enc(&tmRow, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, d, gd, gs, box1, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r2 = enc(&tmBox3, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, d, gd, gs, box3, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+    printf("HALO encode failed %d %d\n", (int)r1, (int)r2);
+    return 1;
+  }
+  size_t smem_bytes = total + 2048;
+  CK(cudaFuncSetAttribute(probe_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  probe_halo<<<1, 128, smem_bytes>>>(tmRow, tmBox3, dout, C, Wp, n0, h0, nrows);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("HALO: LAUNCH ERROR %s\n", cudaGetErrorString(e));
+    return 1;
+  }
+  std::vector<uint8_t> o(total);
+  CK(cudaMemcpy(o.data(), dout, total, cudaMemcpyDeviceToHost));
+  // expectation under "absolute smem address" swizzle: pixel p (row-major over the loaded
+  // region, 128 B each), chunk ch lives at p*128 + ((ch ^ (p & 7)) * 16)
+  auto expect = [&](int row, int wq, int c) -> uint8_t {
+    int hh = h0 + row;
+    if (hh < 0 || hh >= H || wq >= W) return 0;
+    return h[(((size_t)n0 * H + hh) * W + wq) * C + c];
+  };
+  int bad_rows = 0, bad_box = 0;
+  for (int r = 0; r < nrows; ++r)
+    for (int wq = 0; wq < Wp; ++wq)
+      for (int c = 0; c < C; ++c) {
+        int p = r * Wp + wq;
+        int off = p * 128 + (((c / 16) ^ (p & 7)) * 16) + c % 16;
+        bad_rows += o[off] != expect(r, wq, c);
+      }
+  for (int r = 0; r < 3; ++r)
+    for (int wq = 0; wq < Wp; ++wq)
+      for (int c = 0; c < C; ++c) {
+        int p = nrows * Wp + r * Wp + wq;  // absolute pixel slot in smem
+        int off = p * 128 + (((c / 16) ^ (p & 7)) * 16) + c % 16;
+        bad_box += o[off] != expect(r, wq, c);
+      }
+  printf("HALO per-row boxes (abs-address swizzle, zero fill): %s (bad=%d)\n",
+         bad_rows ? "FAIL" : "PASS", bad_rows);
+  printf("HALO 3-row box at 128B-aligned dst                  : %s (bad=%d)\n",
+         bad_box ? "FAIL" : "PASS", bad_box);
+  if (bad_box) {
+    // alternative hypothesis: swizzle phase relative to the box start
+    int bad_rel = 0;
+    for (int r = 0; r < 3; ++r)
+      for (int wq = 0; wq < Wp; ++wq)
+        for (int c = 0; c < C; ++c) {
+          int prel = r * Wp + wq;
+          int off = (nrows * Wp + prel) * 128 + (((c / 16) ^ (prel & 7)) * 16) + c % 16;
+          bad_rel += o[off] != expect(r, wq, c);
+        }
+    printf("HALO 3-row box, box-relative swizzle hypothesis      : %s (bad=%d)\n",
+           bad_rel ? "FAIL" : "PASS", bad_rel);
+  }
+  cudaFree(d);
+  cudaFree(dout);
+  return (bad_rows != 0) + (bad_box != 0);
+}
+
+// ------------------------------------------------------------------------ T7 epilogue math
+__global__ void probe_math(const int32_t* acc, const float* bias, const float* scale, int n,
+                           float* out_f, uint32_t* out_pack_rn, uint32_t* out_pack_rd) {
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 >= n + 3 && i >= n) return;
+  float t[4];
+  // packed f32x2: (float(acc) + bias) * scale with two separately rounded operations
+  for (int j = 0; j < 4; j += 2) {
+    float a0 = __int2float_rn(acc[i + j]), a1 = __int2float_rn(acc[i + j + 1]);
+    unsigned long long a, b, s, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(bias[i + j]), "f"(bias[i + j + 1]));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(s) : "f"(scale[i + j]), "f"(scale[i + j + 1]));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(r), "l"(s));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(t[j]), "=f"(t[j + 1]) : "l"(r));
+  }
+  for (int j = 0; j < 4; ++j) out_f[i + j] = t[j];
+  int q[4], f[4];
+  for (int j = 0; j < 4; ++j) {
+    q[j] = __float2int_rn(t[j]);
+    f[j] = __float2int_rd(t[j]);
+  }
+  uint32_t lo, hi;
+  // d = sat(a) << 8 | sat(b) | c << 16  -> pack the high pair first
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(q[3]), "r"(q[2]));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(q[1]), "r"(q[0]), "r"(hi));
+  out_pack_rn[i / 4] = lo;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(f[3]), "r"(f[2]));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(f[1]), "r"(f[0]), "r"(hi));
+  out_pack_rd[i / 4] = lo;
+}
+
+static int run_math() {
+  const int n = 4096;
+  std::vector<int32_t> acc(n);
+  std::vector<float> bias(n), scale(n);
+  srand(5);
+  for (int i = 0; i < n; ++i) {
+    acc[i] = (rand() % 200001) - 100000;
+    if (i % 7 == 0) acc[i] = (rand() % 2 ? 1 : -1) * (16777217 + rand() % 50000000);
+    bias[i] = (float)((rand() % 8193) - 4096);
+    scale[i] = (1.0f + (i % 13) / 32.0f) / 512.0f;
+    if (i % 11 == 0) {  // exact .5 ties after scaling
+      acc[i] = (rand() % 511) * 1 + 0;
+      bias[i] = 0.f;
+      scale[i] = 0.5f;
+    }
+  }
+  int32_t* dacc;
+  float *dbias, *dscale, *dout;
+  uint32_t *dp1, *dp2;
+  CK(cudaMalloc(&dacc, n * 4));
+  CK(cudaMalloc(&dbias, n * 4));
+  CK(cudaMalloc(&dscale, n * 4));
+  CK(cudaMalloc(&dout, n * 4));
+  CK(cudaMalloc(&dp1, n));
+  CK(cudaMalloc(&dp2, n));
+  CK(cudaMemcpy(dacc, acc.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dbias, bias.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dscale, scale.data(), n * 4, cudaMemcpyHostToDevice));
+  probe_math<<<n / 4 / 128, 128>>>(dacc, dbias, dscale, n, dout, dp1, dp2);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("MATH: LAUNCH ERROR %s\n", cudaGetErrorString(e));
+    return 1;
+  }
+  std::vector<float> o(n);
+  std::vector<uint8_t> p1(n), p2(n);
+  CK(cudaMemcpy(o.data(), dout, n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(p1.data(), dp1, n, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(p2.data(), dp2, n, cudaMemcpyDeviceToHost));
+  int badf = 0, badrn = 0, badrd = 0;
+  for (int i = 0; i < n; ++i) {
+    volatile float t = (float)acc[i];
+    t = t + bias[i];
+    t = t * scale[i];
+    float tt = t;
+    badf += memcmp(&tt, &o[i], 4) != 0;
+    float relu = tt < 0 ? 0.f : tt;
+    double rn = __builtin_nearbyint((double)relu);  // default mode = RN-even
+    double rd = __builtin_floor((double)relu);
+    int ern = rn > 255 ? 255 : (int)rn, erd = rd > 255 ? 255 : (int)rd;
+    badrn += ern != p1[i];
+    badrd += erd != p2[i];
+  }
+  printf("MATH f32x2 add/mul bit-exact vs host two-rounding: %s (bad=%d)\n", badf ? "FAIL" : "PASS",
+         badf);
+  printf("MATH cvt.rni + cvt.pack.sat.u8 == relu,rn,usat8    : %s (bad=%d)\n",
+         badrn ? "FAIL" : "PASS", badrn);
+  printf("MATH cvt.rmi + cvt.pack.sat.u8 == relu,floor,usat8 : %s (bad=%d)\n",
+         badrd ? "FAIL" : "PASS", badrd);
+  return badf + badrn + badrd;
+}
+
+// ---------------------------------------------------------------- T8 MMA speed of light
+template <int N>
+__global__ void __launch_bounds__(128, 1) bench_mma(int iters, long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // pseudo-random operand bytes (power draw depends on data toggling)
+  for (int i = tid; i < (128 + N) * 128 / 4; i += 128)
+    reinterpret_cast<uint32_t*>(smem)[i] = (i * 2654435761u) ^ (blockIdx.x * 40503u);
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_base_s));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  long long t0 = 0, t1 = 0;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_i8(128, N, 0, 1);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 128 * 128);
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      uint32_t d = tmem + (it & 1) * N;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint64_t da = make_smem_desc(a0 + k * 32, 16, 1024, kLayoutSW128);
+        uint64_t db = make_smem_desc(b0 + k * 32, 16, 1024, kLayoutSW128);
+        umma_i8(d, da, db, idesc, (it > 1) | k);
+      }
+    }
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    t1 = clock64();
+    cycles_out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+template <int N>
+static void run_bench_one(int nsm) {
+  const int iters = 4000;
+  long long* dcyc;
+  CK(cudaMalloc(&dcyc, nsm * sizeof(long long)));
+  size_t smem_bytes = (128 + N) * 128 + 1024;
+  CK(cudaFuncSetAttribute(bench_mma<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    bench_mma<N><<<nsm, 128, smem_bytes>>>(iters, dcyc);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("BENCH N=%d: LAUNCH ERROR %s\n", N, cudaGetErrorString(e));
+      return;
+    }
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  std::vector<long long> cyc(nsm);
+  CK(cudaMemcpy(cyc.data(), dcyc, nsm * sizeof(long long), cudaMemcpyDeviceToHost));
+  long long cmax = 0;
+  for (auto c : cyc) cmax = c > cmax ? c : cmax;
+  double macs_per_cta = (double)iters * 4 * 128.0 * N * 32.0;
+  double tops = 2.0 * macs_per_cta * nsm / (best * 1e-3) / 1e12;
+  printf("BENCH kind::i8 M=128 N=%3d K=32: %.1f MAC/clk/SM (clock64), %.1f TOPS over %d SMs "
+         "(events, best of 5, %.3f ms)\n",
+         N, macs_per_cta / (double)cmax, tops, nsm, best);
+  cudaFree(dcyc);
+}
+
+int main(int argc, char** argv) {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device: %s sm_%d%d SMs=%d smem/block optin=%zu\n", prop.name, prop.major, prop.minor,
+         prop.multiProcessorCount, (size_t)prop.sharedMemPerBlockOptin);
+  EncodeTiledFn enc = get_encode();
+  int fails = 0;
+  bool all = argc < 2;
+  auto want = [&](const char* s) { return all || strstr(argv[1], s); };
+  if (want("math")) fails += run_math();
+  if (want("halo")) fails += run_halo(enc);
+  if (want("mma")) fails += run_mma_cases(enc);
+  if (want("bench")) {
+    run_bench_one<256>(prop.multiProcessorCount);
+    run_bench_one<128>(prop.multiProcessorCount);
+    run_bench_one<64>(prop.multiProcessorCount);
+  }
+  printf("probe done, failing groups: %d\n", fails);
+  return 0;
+}
