@@ -1,0 +1,147 @@
+// concat.cu -- concat(+ReLU) along channels of NHWC tensors, sm_100a.
+//
+// Replaces op_concat<T>::infer + jit_concat_kernel (reference src/op_concat.cc:22-72,
+// src/jit_concat_kernel.cc:30-128).  The reference makes one JIT call per pixel that copies
+// nb_ic[i] blocks from every input; here the whole op is one grid-stride kernel over the
+// 16-byte vectors of the DESTINATION: consecutive threads write consecutive 16 B of dst (fully
+// coalesced 128-bit stores) and read runs of ic[i]*sizeof(T) contiguous bytes per input that
+// continue into the next pixel of the same input (sector-coalesced 128-bit loads).  HBM-bound:
+// algorithmic bytes = 2 * N*H*W*sum(C)*sizeof(T).
+//
+// ReLU is the reference's literal one (jit_concat_kernel.cc:43-51): vpmaxsb for s8 AND u8,
+// vpmaxsw for s32, vmaxps(0, x) for f32 -- see DESIGN.md (C6/D9).
+#include "df_common.cuh"
+
+namespace {
+
+constexpr int kMaxInputs = 16;  // per launch; longer lists are processed in groups
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+struct ConcatParams {
+  const uint4* src[kMaxInputs];
+  uint32_t vec_begin[kMaxInputs + 1];  // prefix sum of 16 B vectors per pixel, per input
+  uint32_t n_inputs;
+  uint32_t group_vecs;     // vectors per pixel contributed by this group
+  uint32_t dst_pitch;      // vectors per pixel of the whole destination
+  uint32_t dst_off;        // first destination vector of this group inside a pixel
+  uint32_t total;          // n_pixels * group_vecs
+};
+
+enum { kCopy = 0, kReluBytes = 1, kReluHalves = 2, kReluF32 = 3 };
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+template <int kMode>
+__device__ __forceinline__ uint32_t relu_word(uint32_t x) {
+  if (kMode == kReluBytes) return __vmaxs4(x, 0u);   // vpmaxsb
+  if (kMode == kReluHalves) return __vmaxs2(x, 0u);  // vpmaxsw
+  if (kMode == kReluF32) {                           // vmaxps(zero, x): NaN / -0.0 pass
+    float f = __uint_as_float(x);
+    return (0.0f > f) ? 0u : x;
+  }
+  return x;
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kThreads) concat_kernel(const ConcatParams p, uint4* __restrict__ dst) {
+  const uint32_t stride = gridDim.x * kThreads;
+  for (uint32_t base = blockIdx.x * kThreads + threadIdx.x; base < p.total; base += stride * kUnroll) {
+    uint4 val[kUnroll];
+    uint32_t dst_idx[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t v = base + u * stride;
+      if (v < p.total) {
+        const uint32_t pixel = v / p.group_vecs;
+        const uint32_t off = v - pixel * p.group_vecs;
+        uint32_t i = 0;
+        while (i + 1 < p.n_inputs && off >= p.vec_begin[i + 1]) ++i;
+        const uint32_t width = p.vec_begin[i + 1] - p.vec_begin[i];
+        val[u] = ld_stream(p.src[i] + (size_t)pixel * width + (off - p.vec_begin[i]));
+        dst_idx[u] = pixel * p.dst_pitch + p.dst_off + off;  // host guarantees < 2^32
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t v = base + u * stride;
+      if (v < p.total) {
+        uint4 x = val[u];
+        x.x = relu_word<kMode>(x.x);
+        x.y = relu_word<kMode>(x.y);
+        x.z = relu_word<kMode>(x.z);
+        x.w = relu_word<kMode>(x.w);
+        dst[dst_idx[u]] = x;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int df_concat_check(int dtype, int n_inputs, const int* ic) {
+  // jit_concat_kernel::init_conf (reference src/jit_concat_kernel.cc:130-197): 1- or 4-byte
+  // dtype, and the smallest block of the candidate list must divide every input's channels.
+  const int ts = df::dtype_size(dtype);
+  if (!ts) return df::fail(DF_E_INVALID, "concat: unsupported dtype %d", dtype);
+  if (n_inputs <= 0 || !ic) return df::fail(DF_E_INVALID, "concat: no inputs");
+  const int min_block = ts == 1 ? 16 : 4;
+  for (int i = 0; i < n_inputs; ++i)
+    if (ic[i] <= 0 || ic[i] % min_block)
+      return df::fail(DF_E_INVALID, "concat: input %d has %d channels, not a multiple of %d", i, ic[i], min_block);
+  return 0;
+}
+
+extern "C" int df_concat_run(int dtype, int relu, int n_inputs, const void* const* src_dev, const int* ic,
+                             void* dst_dev, long n_pixels, void* stream) {
+  int rc = df_concat_check(dtype, n_inputs, ic);
+  if (rc) return rc;
+  if (!src_dev || !dst_dev) return df::fail(DF_E_INVALID, "concat: null device pointer");
+  if (n_pixels <= 0) return 0;  // empty tensors: nothing to move
+  const int ts = df::dtype_size(dtype);
+  unsigned long long oc_vecs = 0;
+  for (int i = 0; i < n_inputs; ++i) oc_vecs += (unsigned long long)ic[i] * ts / 16;
+  if ((unsigned long long)n_pixels * oc_vecs >= (1ull << 32))
+    return df::fail(DF_E_UNSUPPORTED, "concat: more than 2^32 16-byte vectors in one call");
+  if ((reinterpret_cast<uintptr_t>(dst_dev) & 15))
+    return df::fail(DF_E_INVALID, "concat: dst not 16-byte aligned");
+  const int mode = !relu ? kCopy : (dtype == DF_F32 ? kReluF32 : (dtype == DF_S32 ? kReluHalves : kReluBytes));
+  int sms = 148;
+  df_device_sm_count(&sms);
+  uint32_t done_vecs = 0;
+  for (int g0 = 0; g0 < n_inputs; g0 += kMaxInputs) {
+    ConcatParams p;
+    p.n_inputs = (uint32_t)((n_inputs - g0) < kMaxInputs ? (n_inputs - g0) : kMaxInputs);
+    p.vec_begin[0] = 0;
+    for (uint32_t i = 0; i < p.n_inputs; ++i) {
+      if (reinterpret_cast<uintptr_t>(src_dev[g0 + i]) & 15)
+        return df::fail(DF_E_INVALID, "concat: src %d not 16-byte aligned", g0 + (int)i);
+      p.src[i] = static_cast<const uint4*>(src_dev[g0 + i]);
+      p.vec_begin[i + 1] = p.vec_begin[i] + (uint32_t)(ic[g0 + i] * ts / 16);
+    }
+    p.group_vecs = p.vec_begin[p.n_inputs];
+    p.dst_pitch = (uint32_t)oc_vecs;
+    p.dst_off = done_vecs;
+    p.total = (uint32_t)n_pixels * p.group_vecs;
+    done_vecs += p.group_vecs;
+    const unsigned per_block = kThreads * kUnroll;
+    unsigned blocks = (p.total + per_block - 1) / per_block;
+    const unsigned cap = (unsigned)sms * 8;  // a multiple of the SM count, 8 resident CTAs each
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (mode) {
+      case kCopy: concat_kernel<kCopy><<<blocks, kThreads, 0, st>>>(p, (uint4*)dst_dev); break;
+      case kReluBytes: concat_kernel<kReluBytes><<<blocks, kThreads, 0, st>>>(p, (uint4*)dst_dev); break;
+      case kReluHalves: concat_kernel<kReluHalves><<<blocks, kThreads, 0, st>>>(p, (uint4*)dst_dev); break;
+      default: concat_kernel<kReluF32><<<blocks, kThreads, 0, st>>>(p, (uint4*)dst_dev); break;
+    }
+    DF_CUDA(cudaGetLastError());
+  }
+  return 0;
+}

@@ -1,0 +1,110 @@
+/* dfcuda.h -- C-ABI of the B200 (sm_100a) implementation of deep-fusion's hot path.
+ *
+ * This is the drop-in boundary: plain C, opaque handles, caller-owned device pointers, no torch
+ * or C++ types.  The C++ host layer (deep-fusion_b200/host/deepfusion.cc, which implements the
+ * reference's public API include/deepfusion.h) is its only in-tree caller; INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.  Every entry point names the reference
+ * interface it stands in for (paths relative to the reference repository).
+ *
+ * Conventions: every function returns 0 on success, a positive cudaError_t, or a negative
+ * DF_E_* code; none of them ever exits the process (the reference's error_and_exit behaviour,
+ * util/log.h:38-42, is reproduced by the host layer, not here).  df_last_error() describes the
+ * most recent failure on the calling thread.  There is no CPU fallback: without a CUDA device
+ * the compute entry points fail with the CUDA error.
+ */
+#ifndef DFCUDA_H_
+#define DFCUDA_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* = deepfusion::memory::dtype (include/deepfusion.h:66-72) */
+enum { DF_UNDEF = 0, DF_F32 = 1, DF_S32 = 2, DF_S8 = 3, DF_U8 = 4 };
+/* = deepfusion::round_mode (include/deepfusion.h:46-49) */
+enum { DF_ROUND_NEAREST = 0, DF_ROUND_DOWN = 1 };
+
+enum {
+  DF_E_INVALID = -1,     /* bad argument / rejected by the reference's own init_conf rules   */
+  DF_E_UNSUPPORTED = -2, /* accepted by the reference but outside the B200 path */
+  DF_E_NODRIVER = -3,    /* cuTensorMapEncodeTiled not obtainable                           */
+  DF_E_INTERNAL = -4
+};
+
+const char *df_last_error(void);
+const char *df_version(void);
+
+/* ---- device / memory / stream plumbing (replaces utils::aligned_malloc + implicit host
+ *      residency of memory::data(), util/memory.cc:21-40, src/deepfusion.cc:76-80) ---------- */
+int df_device_count(int *count);
+int df_set_device(int device);
+int df_device_sm_count(int *sms);
+int df_malloc(size_t bytes, void **dev_ptr);
+int df_free(void *dev_ptr);
+int df_memset(void *dev_ptr, int value, size_t bytes, void *stream);
+int df_host_register(void *host_ptr, size_t bytes); /* pin an existing host buffer */
+int df_host_unregister(void *host_ptr);
+int df_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int df_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int df_stream_create(void **stream);
+int df_stream_sync(void *stream);
+int df_stream_destroy(void *stream);
+int df_event_create(void **event);
+int df_event_record(void *event, void *stream);
+int df_event_elapsed_ms(void *start, void *stop, float *ms); /* synchronises on `stop` */
+int df_event_destroy(void *event);
+
+/* ---- concat(+ReLU): replaces op_concat<T>::infer + jit_concat_kernel
+ *      (src/op_concat.cc:22-72, src/jit_concat_kernel.cc:30-197) ---------------------------
+ * NHWC inputs concatenated along channels; `ic[i]` channels each; n_pixels = N*H*W.
+ * Acceptance = jit_concat_kernel::init_conf: every ic[i] a multiple of 16 (1-byte dtypes) or
+ * 4 (4-byte dtypes).  ReLU is the reference's literal one (signed max per byte / 16-bit half,
+ * see DESIGN.md C6).  Device pointers must be 16-byte aligned. */
+int df_concat_check(int dtype, int n_inputs, const int *ic);
+int df_concat_run(int dtype, int relu, int n_inputs, const void *const *src_dev, const int *ic,
+                  void *dst_dev, long n_pixels, void *stream);
+
+/* ---- fused conv3x3+ReLU+conv1x1+ReLU: replaces op_conv<T> (src/op_conv.h:34-96),
+ *      op_conv<T>::init_conf (src/op_conv.cc:262-365), jit_conv_kernel::init_conf
+ *      (src/jit_conv_kernel.cc:512-673) and infer_conv0conv1 (src/op_conv.cc:140-260) -------- */
+typedef struct df_conv_desc {
+  int n, ih, iw;        /* created (maximum) batch, input height / width                    */
+  int ic, oc, oc1;      /* conv0 in / out channels, conv1x1 out channels (0 = conv0 only)   */
+  int kh, kw, sh, sw, ph, pw;
+  int dst_dt;           /* DF_F32 / DF_S32 / DF_S8 / DF_U8                                  */
+  int bia0_dt, bia1_dt; /* DF_UNDEF = no bias                                               */
+  int relu0, relu1;
+  int round0, round1;
+  int nscale0, nscale1; /* 1 or oc / oc1                                                    */
+} df_conv_desc;
+
+typedef struct df_conv df_conv; /* opaque */
+
+typedef struct df_conv_info {
+  int tiles_per_launch;   /* 128-position tiles for the created batch                      */
+  int grid, block;        /* persistent CTAs, threads per CTA                              */
+  int smem_bytes;         /* dynamic shared memory per CTA                                 */
+  int w0_resident, w1_resident, a_stages, b_stages;
+  int padded_w, padded_h; /* Wp, Hp of the linearised padded pixel space                   */
+  double macs_per_image;  /* H*W*(9*IC*OC + OC*OC1)                                        */
+  double mma_efficiency;  /* real pixels / computed tile rows                              */
+} df_conv_info;
+
+/* Validates like the reference (with its defect D1 fixed), re-lays the OIhw4i16o4i weights out
+ * for tcgen05, expands scales, converts biases to f32 exactly as vcvtdq2ps would, uploads to the
+ * current device.  All pointers are HOST pointers and may be freed after the call. */
+int df_conv_create(const df_conv_desc *desc, const int8_t *wei_OIhw4i16o4i,
+                   const int8_t *wei1x1_OIhw4i16o4i, const void *bia0, const void *bia1,
+                   const float *scale0, const float *scale1, df_conv **out);
+/* One forward pass over `n` (<= created n) images; src NHWC u8, dst NHWC dst_dt, both device
+ * pointers, 16-byte aligned.  Asynchronous on `stream`. */
+int df_conv_run(df_conv *op, const uint8_t *src_dev, void *dst_dev, int n, void *stream);
+int df_conv_query(const df_conv *op, df_conv_info *info);
+int df_conv_destroy(df_conv *op);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
