@@ -1,0 +1,420 @@
+// deepfusion.cc -- C++ host layer: the reference's public API (include/deepfusion.h) on top of the
+// CUDA C-ABI (include/dfcuda.h).
+//
+// Mirrors, function by function, the reference's L3/L2 layers:
+//   memory            src/deepfusion.cc:25-88, util/memory.cc
+//   op::submit        src/deepfusion.cc:90-103
+//   concat()/conv()   src/deepfusion.cc:105-185
+//   op_concat<T>      src/op_concat.{h,cc}          -> concat_op
+//   op_conv<T>        src/op_conv.{h,cc}            -> conv_op
+// Differences from the reference are deliberate and listed in DESIGN.md ("Deviations"): weights,
+// biases and scales are captured (copied to the device) at creation; std_dims() is initialised by
+// both constructors; error text is the same, the process still exits on creation failure.
+#include <assert.h>
+#include <string.h>
+#include <sys/time.h>
+
+#include "df_host.h"
+
+namespace deepfusion {
+namespace detail {
+
+size_t dtype_size(memory::dtype dt) {
+  switch (dt) {
+    case memory::dtype::f32:
+    case memory::dtype::s32: return 4;
+    case memory::dtype::s8:
+    case memory::dtype::u8: return 1;
+    default: assert(!"Unkown data type"); return 0;
+  }
+}
+
+int conv_output_size(int image, int kernel, int stride, int padding) {
+  return (image + 2 * padding - kernel) / stride + 1;
+}
+
+bool profiling_enabled() {
+  // the reference reads DEEPFUSION_PROFILE (util/scaffold.cc:56-66) while its README documents
+  // DEEPFUSION_VERBOSE (README.md:26-31); accept either (defect D6)
+  static int cached = -1;
+  if (cached < 0) {
+    const char *a = getenv("DEEPFUSION_VERBOSE"), *b = getenv("DEEPFUSION_PROFILE");
+    cached = ((a && atoi(a) != 0) || (b && atoi(b) != 0)) ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+static double now_ms() {
+  struct timeval t;
+  gettimeofday(&t, NULL);
+  return 1e+3 * t.tv_sec + 1e-3 * t.tv_usec;
+}
+
+static void cuda_or_exit(int rc, const char *what) {
+  if (rc != 0) error_and_exit("%s failed (%d): %s", what, rc, df_last_error());
+}
+
+static void *mirror(memory &m) {
+  memory_state *st = m.state();
+  if (!st->dev) cuda_or_exit(df_malloc(m.buffer_size(), &st->dev), "device allocation");
+  return st->dev;
+}
+
+static int dt_code(memory::dtype dt) { return static_cast<int>(dt); }  // same numbering as DF_*
+
+}  // namespace detail
+
+using detail::cuda_or_exit;
+using detail::mirror;
+
+// ------------------------------------------------------------------------------- memory
+static memory::dims nchw2format(const memory::nchw_dims &dm, const memory::format fmt) {
+  memory::dims out(4);
+  switch (fmt) {
+    case memory::format::nhwc:
+      out[0] = dm[0];
+      out[1] = dm[2];
+      out[2] = dm[3];
+      out[3] = dm[1];
+      break;
+    case memory::format::nchw:
+    case memory::format::OIhw4i16o4i:
+      out[0] = dm[0];
+      out[1] = dm[1];
+      out[2] = dm[2];
+      out[3] = dm[3];
+      break;
+    default: error_and_exit("bad type");
+  }
+  return out;
+}
+
+memory::memory(const nchw_dims &dm, const format fmt, const dtype dt, int alignment)
+    : data_(nullptr), std_dims_(dm), fmt_(fmt), dt_(dt), state_(new detail::memory_state()) {
+  dims_ = nchw2format(dm, fmt);
+  allocate_buffer(alignment);
+}
+
+memory::memory(const dims &dm, const format fmt, const dtype dt, int alignment)
+    : data_(nullptr), dims_(dm), fmt_(fmt), dt_(dt), state_(new detail::memory_state()) {
+  // the reference leaves std_dims_ uninitialised here although op_conv reads it (defect D5)
+  for (size_t i = 0; i < 4; ++i) std_dims_[i] = i < dm.size() ? dm[i] : 1;
+  allocate_buffer(alignment);
+}
+
+memory::~memory() {
+  if (state_) {
+    if (state_->pinned) df_host_unregister(data_);
+    if (state_->dev) df_free(state_->dev);
+    delete state_;
+  }
+  free(data_);
+}
+
+void memory::allocate_buffer(int alignment) {
+  assert(buffer_size() > 0);
+  void *p = nullptr;
+  if (::posix_memalign(&p, alignment, buffer_size()) != 0) p = nullptr;
+  data_ = p;
+  assert(data_ != NULL);
+}
+
+size_t memory::size() {
+  size_t n = 1;
+  for (size_t i = 0; i < dims_.size(); ++i) n *= size_t(dims_[i]);
+  return n;
+}
+
+size_t memory::buffer_size() { return size() * detail::dtype_size(dt_); }
+
+// ----------------------------------------------------------------------------------- op
+void op::submit() {
+  double t0 = 0;
+  const bool prof = detail::profiling_enabled();
+  if (prof) t0 = detail::now_ms();
+  infer();
+  if (prof) info("%s infer %f", this->name(), detail::now_ms() - t0);
+}
+
+// ------------------------------------------------------------------------------- concat
+namespace {
+
+class concat_op : public detail::device_op {
+public:
+  concat_op(const std::vector<std::unique_ptr<memory>> &srcs, std::unique_ptr<memory> &dst, bool post_relu)
+      : relu_(post_relu), dst_(dst.get()) {
+    if (!init_conf(srcs, dst)) error_and_exit("Init Concat op failed!");
+    for (size_t i = 0; i < srcs.size(); ++i) srcs_.push_back(srcs[i].get());
+  }
+
+  void launch(void *stream) override {
+    std::vector<const void *> ptrs(srcs_.size());
+    for (size_t i = 0; i < srcs_.size(); ++i) ptrs[i] = mirror(*srcs_[i]);
+    cuda_or_exit(df_concat_run(detail::dt_code(dst_->data_type()), relu_, (int)srcs_.size(), ptrs.data(), ic_.data(),
+                               mirror(*dst_), n_pixels_, stream),
+                 "concat launch");
+  }
+  int launches() const override { return (int)((srcs_.size() + 15) / 16); }
+
+protected:
+  // jit_concat_kernel::init_conf (src/jit_concat_kernel.cc:130-197)
+  bool init_conf(const std::vector<std::unique_ptr<memory>> &srcs, const std::unique_ptr<memory> &dst) {
+    if (srcs.empty() || !dst) return false;
+    if (dst->dim_format() != memory::format::nhwc) return false;  // only nhwc
+    auto dm = dst->actual_dims();
+    if (dm.size() != 4) return false;
+    long oc = 0;
+    for (size_t i = 0; i < srcs.size(); ++i) {
+      if (srcs[i]->dim_format() != dst->dim_format()) return false;
+      if (srcs[i]->data_type() != dst->data_type()) return false;
+      auto sd = srcs[i]->actual_dims();
+      if (sd.size() != 4 || sd[0] != dm[0] || sd[1] != dm[1] || sd[2] != dm[2]) {
+        info("Concat input %zu spatial dims do not match", i);
+        return false;
+      }
+      ic_.push_back(sd[3]);
+      oc += sd[3];
+    }
+    if (oc != dm[3]) {
+      info("Concat output channels do not match the inputs");
+      return false;
+    }
+    if (df_concat_check(detail::dt_code(dst->data_type()), (int)ic_.size(), ic_.data()) != 0) {
+      info("%s", df_last_error());
+      return false;
+    }
+    n_pixels_ = (long)dm[0] * dm[1] * dm[2];
+    return true;
+  }
+
+  void infer() override {
+    for (memory *s : srcs_) cuda_or_exit(df_h2d(mirror(*s), s->data(), s->buffer_size(), nullptr), "concat H2D");
+    launch(nullptr);
+    cuda_or_exit(df_d2h(dst_->data(), mirror(*dst_), dst_->buffer_size(), nullptr), "concat D2H");
+    cuda_or_exit(df_stream_sync(nullptr), "concat sync");
+  }
+  const char *name() override { return "concat"; }
+
+private:
+  bool relu_;
+  memory *dst_;
+  std::vector<memory *> srcs_;
+  std::vector<int> ic_;
+  long n_pixels_ = 0;
+};
+
+// --------------------------------------------------------------------------------- conv
+class conv_op : public detail::device_op {
+public:
+  conv_op(const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei, const std::unique_ptr<memory> &bia,
+          std::array<int, 2> sz_stride, std::array<int, 2> sz_padding, std::unique_ptr<memory> &dst,
+          const std::vector<float> &conv0_scales, const std::vector<float> &conv1_scales,
+          const std::unique_ptr<memory> &wei1x1, const std::unique_ptr<memory> &bia1x1, bool conv0_relu,
+          bool conv1_relu, round_mode conv0_round_mode, round_mode conv1_round_mode)
+      : src_(src.get()), dst_(dst.get()) {
+    memset(&desc_, 0, sizeof desc_);
+    if (!init_conf(src, wei, bia, sz_stride, sz_padding, dst, conv0_scales, conv1_scales, wei1x1, bia1x1, conv0_relu,
+                   conv1_relu, conv0_round_mode, conv1_round_mode))
+      error_and_exit("Init Conv op failed!");
+    // parameters are captured now (the reference keeps raw pointers and a dangling scales
+    // pointer, defect D7); the activations stay borrowed
+    int rc = df_conv_create(&desc_, static_cast<const int8_t *>(wei->data()),
+                            wei1x1 ? static_cast<const int8_t *>(wei1x1->data()) : nullptr,
+                            bia ? bia->data() : nullptr, bia1x1 ? bia1x1->data() : nullptr, conv0_scales.data(),
+                            conv1_scales.data(), &handle_);
+    if (rc == DF_E_UNSUPPORTED) error_and_exit("unsupported on B200 path: %s", df_last_error());
+    if (rc != 0) {
+      info("%s", df_last_error());
+      error_and_exit("Init Conv op failed!");
+    }
+  }
+  ~conv_op() override { df_conv_destroy(handle_); }
+
+  void launch(void *stream) override {
+    cuda_or_exit(df_conv_run(handle_, static_cast<const uint8_t *>(mirror(*src_)), mirror(*dst_), desc_.n, stream),
+                 "conv launch");
+  }
+  int launches() const override { return 1; }
+
+protected:
+  // op_conv<T>::init_conf (src/op_conv.cc:262-365) + the format gate of
+  // jit_conv_kernel::init_conf (src/jit_conv_kernel.cc:531-564); the numeric rules are
+  // re-checked by df_conv_create.
+  bool init_conf(const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei,
+                 const std::unique_ptr<memory> &bia, std::array<int, 2> sz_stride, std::array<int, 2> sz_padding,
+                 std::unique_ptr<memory> &dst, const std::vector<float> &conv0_scales,
+                 const std::vector<float> &conv1_scales, const std::unique_ptr<memory> &wei1x1,
+                 const std::unique_ptr<memory> &bia1x1, bool conv0_relu, bool conv1_relu, round_mode r0,
+                 round_mode r1) {
+    if (!src || !wei || !dst) return false;
+    using dt = memory::dtype;
+    using fm = memory::format;
+    if (src->data_type() != dt::u8 || wei->data_type() != dt::s8 || (wei1x1 && wei1x1->data_type() != dt::s8)) {
+      info("Conv needs u8 src and s8 weights");
+      return false;
+    }
+    auto blocked = [](const std::unique_ptr<memory> &w) {
+      return w->dim_format() == fm::OIhw4i16o4i || w->dim_format() == fm::gOIhw4i16o4i;
+    };
+    if (src->dim_format() != fm::nhwc || dst->dim_format() != fm::nhwc || !blocked(wei) ||
+        (wei1x1 && !blocked(wei1x1)) || (bia && bia->dim_format() != fm::x) ||
+        (bia1x1 && bia1x1->dim_format() != fm::x)) {
+      info("Conv formats must be nhwc / OIhw4i16o4i / x");
+      return false;
+    }
+    constexpr int C = 1, H = 2, W = 3;
+    auto src_dims = src->std_dims(), wei_dims = wei->std_dims(), dst_dims = dst->std_dims();
+    for (size_t i = 0; i < 2; ++i)
+      if (dst_dims[i + 2] != detail::conv_output_size(src_dims[i + 2], wei_dims[i + 2], sz_stride[i], sz_padding[i])) {
+        info("Output image size do not match: %zu", i);
+        return false;
+      }
+    if (src_dims[0] != dst_dims[0]) {
+      info("Batch size do not equal");
+      return false;
+    }
+    if (src_dims[C] != wei_dims[C]) {
+      info("Input channel do not match");
+      return false;
+    }
+    if (!wei1x1) {
+      if (dst_dims[C] != wei_dims[0]) {
+        info("Output channel do not match");
+        return false;
+      }
+      if (bia && bia->std_dims()[0] != wei_dims[0]) {
+        info("Bias channel do not match");
+        return false;
+      }
+      if (conv0_scales.size() != 1 && conv0_scales.size() != size_t(dst_dims[C])) return false;
+    } else {
+      auto w1 = wei1x1->std_dims();
+      if (w1[C] != wei_dims[0]) {
+        info("Conv0 output channel do not match");
+        return false;
+      }
+      if (dst_dims[C] != w1[0]) {
+        info("Conv1x1 output channel do not match");
+        return false;
+      }
+      if (w1[H] != 1 || w1[W] != 1) {
+        info("Fused conv must be 1x1 kernel");
+        return false;
+      }
+      if (bia && bia->std_dims()[0] != wei_dims[0]) {
+        info("Bias channel do not match");
+        return false;
+      }
+      if (bia1x1 && bia1x1->std_dims()[0] != dst_dims[C]) {
+        info("Bias channel do not match");
+        return false;
+      }
+      if ((conv0_scales.size() != 1 && conv0_scales.size() != size_t(w1[1])) ||
+          (conv1_scales.size() != 1 && conv1_scales.size() != size_t(w1[0])))
+        return false;
+    }
+    desc_.n = src_dims[0];
+    desc_.ih = src_dims[H];
+    desc_.iw = src_dims[W];
+    desc_.ic = src_dims[C];
+    desc_.oc = wei_dims[0];  // defect D1: the reference takes this from dst
+    desc_.oc1 = wei1x1 ? wei1x1->std_dims()[0] : 0;
+    desc_.kh = wei_dims[H];
+    desc_.kw = wei_dims[W];
+    desc_.sh = sz_stride[0];
+    desc_.sw = sz_stride[1];
+    desc_.ph = sz_padding[0];
+    desc_.pw = sz_padding[1];
+    desc_.dst_dt = detail::dt_code(dst->data_type());
+    desc_.bia0_dt = bia ? detail::dt_code(bia->data_type()) : DF_UNDEF;
+    desc_.bia1_dt = bia1x1 ? detail::dt_code(bia1x1->data_type()) : DF_UNDEF;
+    desc_.relu0 = conv0_relu;
+    desc_.relu1 = conv1_relu;
+    desc_.round0 = r0 == round_mode::down ? DF_ROUND_DOWN : DF_ROUND_NEAREST;
+    desc_.round1 = r1 == round_mode::down ? DF_ROUND_DOWN : DF_ROUND_NEAREST;
+    desc_.nscale0 = (int)conv0_scales.size();
+    desc_.nscale1 = (int)conv1_scales.size();
+    return true;
+  }
+
+  void infer() override {
+    cuda_or_exit(df_h2d(mirror(*src_), src_->data(), src_->buffer_size(), nullptr), "conv H2D");
+    launch(nullptr);
+    cuda_or_exit(df_d2h(dst_->data(), mirror(*dst_), dst_->buffer_size(), nullptr), "conv D2H");
+    cuda_or_exit(df_stream_sync(nullptr), "conv sync");
+  }
+  const char *name() override { return "conv"; }
+
+private:
+  memory *src_, *dst_;
+  df_conv_desc desc_;
+  df_conv *handle_ = nullptr;
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------- factories
+std::unique_ptr<op> concat(const std::vector<std::unique_ptr<memory>> &srcs, std::unique_ptr<memory> &dst,
+                           bool post_relu) {
+  switch (dst->data_type()) {
+    case memory::dtype::f32:
+    case memory::dtype::s32:
+    case memory::dtype::s8:
+    case memory::dtype::u8: return std::unique_ptr<op>(new concat_op(srcs, dst, post_relu));
+    default: assert(!"bad data_type");
+  }
+  return nullptr;
+}
+
+std::unique_ptr<op> conv(const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei,
+                         const std::unique_ptr<memory> &bia, std::array<int, 2> sz_stride,
+                         std::array<int, 2> sz_padding, const std::unique_ptr<memory> &wei1x1,
+                         const std::unique_ptr<memory> &bia1x1, std::unique_ptr<memory> &dst, bool conv0_relu,
+                         std::vector<float> conv0_scales, round_mode conv0_round_mode, bool conv1_relu,
+                         std::vector<float> conv1_scales, round_mode conv1_round_mode) {
+  switch (dst->data_type()) {
+    case memory::dtype::f32:
+    case memory::dtype::s32:
+    case memory::dtype::s8:
+    case memory::dtype::u8:
+      return std::unique_ptr<op>(new conv_op(src, wei, bia, sz_stride, sz_padding, dst, conv0_scales, conv1_scales,
+                                             wei1x1, bia1x1, conv0_relu, conv1_relu, conv0_round_mode,
+                                             conv1_round_mode));
+    default: assert(!"bad data_type");
+  }
+  return nullptr;
+}
+
+std::unique_ptr<op> conv(const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei,
+                         const std::unique_ptr<memory> &bia, std::array<int, 2> sz_stride,
+                         std::array<int, 2> sz_padding, std::unique_ptr<memory> &dst, bool conv0_relu,
+                         std::vector<float> conv0_scales, round_mode conv0_round_mode) {
+  return conv(src, wei, bia, sz_stride, sz_padding, nullptr, nullptr, dst, conv0_relu, conv0_scales,
+              conv0_round_mode);
+}
+
+// ------------------------------------------------------------------------------ ext API
+namespace ext {
+
+void *device_data(memory &m) { return mirror(m); }
+void to_device(memory &m, void *stream) {
+  cuda_or_exit(df_h2d(mirror(m), m.data(), m.buffer_size(), stream), "to_device");
+}
+void to_host(memory &m, void *stream) { cuda_or_exit(df_d2h(m.data(), mirror(m), m.buffer_size(), stream), "to_host"); }
+void submit_device(op &o, void *stream) {
+  detail::device_op *d = dynamic_cast<detail::device_op *>(&o);
+  if (!d) error_and_exit("submit_device: not a B200 op");
+  d->launch(stream);
+}
+void sync(void *stream) { cuda_or_exit(df_stream_sync(stream), "sync"); }
+int launches_per_submit(op &o) {
+  detail::device_op *d = dynamic_cast<detail::device_op *>(&o);
+  return d ? d->launches() : 0;
+}
+void pin(memory &m) {
+  detail::memory_state *st = m.state();
+  if (!st->pinned && df_host_register(m.data(), m.buffer_size()) == 0) st->pinned = true;
+}
+
+}  // namespace ext
+}  // namespace deepfusion

@@ -1,0 +1,101 @@
+"""GPU tests (-m gpu) through the reference-facing C++ API (memory / concat() / conv() / submit()),
+written like the reference's own test/test_concat.cc: build memories, fill them, create the op,
+submit(), compare the destination's HOST buffer with the oracle."""
+import numpy as np
+import pytest
+
+import cases
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def H():
+    import dfb200
+    assert dfb200.device_count() >= 1
+    from dfb200 import hostapi
+    return hostapi
+
+
+@pytest.mark.parametrize("dt", ["u8", "s8", "s32", "f32"])
+def test_concat_submit_like_reference_test(H, dt):
+    shapes = cases.CONCAT_BASIC + (cases.CONCAT_32BIT_EXTRA if dt in ("f32", "s32") else [])
+    for srcs_dims, dst_dims in shapes:
+        ins = cases.concat_inputs(dt, srcs_dims, "reference-range")
+        srcs = [H.Memory(d, "nhwc", dt) for d in srcs_dims]
+        for m, a in zip(srcs, ins):
+            m.set(a)
+        dst = H.Memory(dst_dims, "nhwc", dt)
+        for post_relu in (True, False):  # same order as test/test_concat.cc:103-107
+            c = H.concat(srcs, dst, post_relu)
+            c.submit()
+            want = O.concat(cases.DT[dt], post_relu, ins)
+            assert np.array_equal(dst.array().view(np.uint8), want.view(np.uint8))
+
+
+@pytest.mark.parametrize("name", ["cfg1_crop", "cfg3_crop", "cfg4_f32", "s8_relu_down", "single_scale"])
+def test_conv_submit(H, name):
+    c = {x.name: x for x in cases.SMALL_CONV}[name]
+    src_a, w0, w1, b0, b1, s0, s1 = c.tensors()
+    wb, w1b = c.blocked(w0, w1)
+    src = H.Memory((c.n, c.ic, c.h, c.w), "nhwc", "u8")
+    src.set(src_a)
+    wei = H.Memory((c.oc, c.ic, 3, 3), "OIhw4i16o4i", "s8")
+    wei.array().reshape(-1)[...] = wb
+    wei1 = H.Memory((c.oc1, c.oc, 1, 1), "OIhw4i16o4i", "s8")
+    wei1.array().reshape(-1)[...] = w1b
+    bia = bia1 = None
+    if c.b0:
+        bia = H.Memory((c.oc,), "x", c.b0, nchw=False)
+        bia.set(b0)
+    if c.b1:
+        bia1 = H.Memory((c.oc1,), "x", c.b1, nchw=False)
+        bia1.set(b1)
+    dst = H.Memory((c.n, c.oc1, c.h, c.w), "nhwc", c.dst)
+    op = H.conv(src, wei, bia, (1, 1), (1, 1), dst, wei1x1=wei1, bia1x1=bia1, conv0_relu=bool(c.relu0),
+                conv0_scales=s0, conv0_round_mode=c.r0, conv1_relu=bool(c.relu1), conv1_scales=s1,
+                conv1_round_mode=c.r1)
+    op.submit()
+    d = O.make_desc(c.n, c.h, c.w, c.ic, c.oc, c.oc1, cases.DT[c.dst], cases.DT[c.b0], cases.DT[c.b1], relu0=c.relu0,
+                    relu1=c.relu1, round0=c.r0, round1=c.r1, nscale0=s0.size, nscale1=s1.size)
+    want = O.conv(d, src_a, wb, b0, s0, w1b, b1, s1)
+    assert np.array_equal(dst.array().view(np.uint8), want.view(np.uint8))
+    # a second submit with new source data through the same op (handles are not re-bound)
+    src.set(255 - src_a)
+    op.submit()
+    want2 = O.conv(d, 255 - src_a, wb, b0, s0, w1b, b1, s1)
+    assert np.array_equal(dst.array().view(np.uint8), want2.view(np.uint8))
+    assert op.launches() == 1
+
+
+def test_concat_feeds_conv_on_device(H):
+    """concat+ReLU output consumed by the fused conv without leaving HBM (ext API)."""
+    from dfb200 import synth
+    n, h, w = 2, 14, 14
+    ics = (64, 128, 32, 32)
+    ins = [synth.src_u8(20 + i, (n, h, w, c), 0, 127) for i, c in enumerate(ics)]
+    srcs = [H.Memory((n, c, h, w), "nhwc", "u8") for c in ics]
+    for m, a in zip(srcs, ins):
+        m.set(a)
+        m.to_device()
+    cat = H.Memory((n, 256, h, w), "nhwc", "u8")
+    c = cases.ConvCase("chain", n, h, w, 256, 128, 256, "u8", "s32", "s32")
+    _, w0, w1, b0, b1, s0, s1 = c.tensors()
+    wb, w1b = c.blocked(w0, w1)
+    wei = H.Memory((128, 256, 3, 3), "OIhw4i16o4i", "s8"); wei.array().reshape(-1)[...] = wb
+    wei1 = H.Memory((256, 128, 1, 1), "OIhw4i16o4i", "s8"); wei1.array().reshape(-1)[...] = w1b
+    bia = H.Memory((128,), "x", "s32", nchw=False); bia.set(b0)
+    bia1 = H.Memory((256,), "x", "s32", nchw=False); bia1.set(b1)
+    dst = H.Memory((n, 256, h, w), "nhwc", "u8")
+    op_cat = H.concat(srcs, cat, True)
+    op_conv = H.conv(cat, wei, bia, (1, 1), (1, 1), dst, wei1x1=wei1, bia1x1=bia1, conv0_scales=s0, conv1_scales=s1)
+    op_cat.submit_device()
+    op_conv.submit_device()
+    H.sync()
+    dst.to_host()
+    H.sync()
+    cat_ref = O.concat(O.U8, True, ins)
+    d = O.make_desc(n, h, w, 256, 128, 256, O.U8, O.S32, O.S32, nscale0=128, nscale1=256)
+    want = O.conv(d, cat_ref, wb, b0, s0, w1b, b1, s1)
+    assert np.array_equal(dst.array(), want)
