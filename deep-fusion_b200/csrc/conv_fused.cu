@@ -62,6 +62,21 @@ struct Params {
   int relu1, round0, round1, nan_safe;
   const float *bias0, *scale0, *bias1, *scale1;
   void* dst;
+  unsigned long long* trace;  // optional timeline buffer (df_conv_debug_trace), normally null
+  int trace_cap;
+};
+
+// Diagnostic timeline: role r of CTA b appends (tag << 48 | clock) words to its own lane of the
+// buffer.  One predictable branch per event when disabled.
+struct Tracer {
+  unsigned long long* base;
+  int cap, n;
+  __device__ Tracer(const Params& p, int role) : base(nullptr), cap(p.trace_cap), n(0) {
+    if (p.trace) base = p.trace + ((size_t)blockIdx.x * 4 + role) * p.trace_cap;
+  }
+  __device__ __forceinline__ void ev(unsigned tag) {
+    if (base && n < cap) base[n++] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+  }
 };
 
 struct Barriers {
@@ -183,7 +198,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
                   const __grid_constant__ CUtensorMap tmW1, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align in the shared address space (keeps LDS/STS instead of generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Barriers* bar = reinterpret_cast<Barriers*>(smem);
   const uint32_t sbase = smem_u32(smem);
 
@@ -238,72 +254,92 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int q_first = 2 * p.Wp;  // linear index of image 0, row 0, column 0
 
+  // The three single-thread roles each run their whole loop inside ONE elect.sync region and advance
+  // shared-memory descriptors by ADDITION: that keeps descriptor math in the uniform datapath.  Both
+  // alternatives measured slow (probe/mma_contention.cu, profiles/r01_mma_issue_probe.log): a
+  // per-tap elect/__syncwarp costs ~370 cycles per iteration, and rebuilding descriptors from
+  // vector registers (R2UR) ~140 cycles per tap -- more than the 96..256 cycles of MMA work in a tap.
   if (warp == 0) {
     // =============================== TMA producer: halo rows ===============================
-    if (lane == 0) {
+    if (elect_one()) {
+      Tracer tr(p, 0);
       for (int it = 0; it < n_local; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int s = it % p.SA;
         mbar_wait(smem_u32(&bar->a_empty[s]), ((it / p.SA) & 1) ^ 1);
+        tr.ev(1);
         const int q0 = q_first + tile * kTileM;
         const int g_lo = (q0 - p.Wp - 1) / p.Wp;
         const int g_hi = (q0 + kTileM + p.Wp) / p.Wp;
         const int nrows = g_hi - g_lo + 1;
         const uint32_t full = smem_u32(&bar->a_full[s]);
-        mbar_expect_tx(full, (uint32_t)(nrows * p.nkb * p.Wp * p.swb));
         const uint32_t stage = sbase + p.off_a + s * p.a_stage_bytes;
-        for (int r = 0; r < nrows; ++r) {
-          const int g = g_lo + r;
-          int n = 0, h = -1;  // g == 0: the all-zero row above everything
-          if (g > 0) {
-            n = (g - 1) / p.Hp;
-            h = (g - 1) - n * p.Hp - 1;  // -1 = shared zero row between images
+        mbar_expect_tx(full, (uint32_t)(nrows * p.nkb * p.Wp * p.swb));
+        int n = (g_lo > 0) ? (g_lo - 1) / p.Hp : 0;
+        int h = (g_lo > 0) ? (g_lo - 1) - n * p.Hp - 1 : -2;  // -2: the all-zero row above everything
+        uint32_t dst = stage;
+        const uint32_t row_bytes = p.Wp * p.swb;
+        for (int r = 0; r < nrows; ++r, dst += row_bytes) {
+          for (int kb = 0; kb < p.nkb; ++kb) tma_load_4d(dst + kb * p.a_kb_stride, &tmA, full, kb * p.swb, 0, h, n);
+          if (h == -2) {
+            h = -1;  // g = 1: the zero row above image 0
+          } else if (++h == p.H) {
+            h = -1;  // shared zero row between images
+            ++n;
           }
-          for (int kb = 0; kb < p.nkb; ++kb)
-            tma_load_4d(stage + kb * p.a_kb_stride + r * p.Wp * p.swb, &tmA, full, kb * p.swb, 0, h, n);
         }
       }
     }
   } else if (warp == 2) {
     // =============================== TMA producer: weights =================================
-    if (lane == 0) {
+    if (elect_one()) {
       const int n_w0 = 9 * p.nkb, n_w1 = p.n_chunks * p.nkb1;
       if (p.w0_res || p.w1_res) {
         const uint32_t full = smem_u32(&bar->res_full);
         mbar_expect_tx(full, (p.w0_res ? n_w0 * p.w0_block_bytes : 0) + (p.w1_res ? n_w1 * p.w1_block_bytes : 0));
         if (p.w0_res)
-          for (int b = 0; b < n_w0; ++b)
-            tma_load_2d(sbase + p.off_w0 + b * p.w0_block_bytes, &tmW0, full, 0, b * p.OC);
+          for (int b = 0; b < n_w0; ++b) tma_load_2d(sbase + p.off_w0 + b * p.w0_block_bytes, &tmW0, full, 0, b * p.OC);
         if (p.w1_res)
-          for (int b = 0; b < n_w1; ++b)
-            tma_load_2d(sbase + p.off_w1 + b * p.w1_block_bytes, &tmW1, full, 0, b * p.nc1);
+          for (int b = 0; b < n_w1; ++b) tma_load_2d(sbase + p.off_w1 + b * p.w1_block_bytes, &tmW1, full, 0, b * p.nc1);
       }
-      uint32_t bcount = 0;
-      for (int it = 0; it <= n_local; ++it) {  // same interleaving as the MMA thread below
-        if (it < n_local && !p.w0_res)
-          for (int b = 0; b < n_w0; ++b, ++bcount) {
-            const int s = bcount % p.SB;
-            mbar_wait(smem_u32(&bar->b_empty[s]), ((bcount / p.SB) & 1) ^ 1);
-            mbar_expect_tx(smem_u32(&bar->b_full[s]), p.w0_block_bytes);
-            tma_load_2d(sbase + p.off_b + s * p.b_stage_bytes, &tmW0, smem_u32(&bar->b_full[s]), 0, b * p.OC);
-          }
-        if (it >= 1 && !p.w1_res)
-          for (int b = 0; b < n_w1; ++b, ++bcount) {
-            const int s = bcount % p.SB;
-            mbar_wait(smem_u32(&bar->b_empty[s]), ((bcount / p.SB) & 1) ^ 1);
-            mbar_expect_tx(smem_u32(&bar->b_full[s]), p.w1_block_bytes);
-            tma_load_2d(sbase + p.off_b + s * p.b_stage_bytes, &tmW1, smem_u32(&bar->b_full[s]), 0, b * p.nc1);
-          }
+      if (!p.w0_res || !p.w1_res) {
+        uint32_t s = 0, ph = 1;  // stage cursor and the parity to wait for on b_empty
+        for (int it = 0; it <= n_local; ++it) {  // same interleaving as the MMA thread below
+          if (it < n_local && !p.w0_res)
+            for (int b = 0; b < n_w0; ++b) {
+              mbar_wait(smem_u32(&bar->b_empty[s]), ph);
+              mbar_expect_tx(smem_u32(&bar->b_full[s]), p.w0_block_bytes);
+              tma_load_2d(sbase + p.off_b + s * p.b_stage_bytes, &tmW0, smem_u32(&bar->b_full[s]), 0, b * p.OC);
+              if (++s == (uint32_t)p.SB) { s = 0; ph ^= 1; }
+            }
+          if (it >= 1 && !p.w1_res)
+            for (int b = 0; b < n_w1; ++b) {
+              mbar_wait(smem_u32(&bar->b_empty[s]), ph);
+              mbar_expect_tx(smem_u32(&bar->b_full[s]), p.w1_block_bytes);
+              tma_load_2d(sbase + p.off_b + s * p.b_stage_bytes, &tmW1, smem_u32(&bar->b_full[s]), 0, b * p.nc1);
+              if (++s == (uint32_t)p.SB) { s = 0; ph ^= 1; }
+            }
+        }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ======================================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc0 = make_idesc_i8(kTileM, p.OC, 0, 1);
       const uint32_t idesc1 = make_idesc_i8(kTileM, p.nc1, 0, 1);
-      const uint32_t lay0 = layout_of(p.swb), lay1 = layout_of(p.swb1);
+      // descriptors differ only in their 14-bit start-address field (16 B units): constant part + adds
+      const uint64_t desc0_hi = make_smem_desc(0, 16, 8 * p.swb, layout_of(p.swb));
+      const uint64_t desc1_hi = make_smem_desc(0, 16, 8 * p.swb1, layout_of(p.swb1));
+      const uint32_t a_step_kw = p.swb >> 4, a_step_kh = (p.Wp * p.swb) >> 4, a_step_kb = p.a_kb_stride >> 4;
+      const uint32_t w0_step = p.w0_block_bytes >> 4, w1_step = p.w1_block_bytes >> 4;
+      const uint32_t mid_step_kb = p.mid_kb_stride >> 4, b_stage_step = p.b_stage_bytes >> 4;
+      const uint64_t b_stage0 = (sbase + p.off_b) >> 4;
+      const int nks_full = p.swb >> 5, nks1_full = p.swb1 >> 5;
       if (p.w0_res || p.w1_res) mbar_wait(smem_u32(&bar->res_full), 0);
-      uint32_t bcount = 0, c1count = 0;
+      uint32_t bs = 0, bph = 0;  // weight stage cursor / parity to wait for on b_full
+      uint32_t c1count = 0;
+      Tracer tr(p, 1);
+      tr.ev(9);
       for (int it = 0; it <= n_local; ++it) {
         if (it < n_local) {
           // ---- GEMM1(it): acc0 = sum over 9 taps, K-blocks of halo(tile) x W0
@@ -313,77 +349,83 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / p.n_acc0) & 1) ^ 1);
           mbar_wait(smem_u32(&bar->a_full[sa]), (it / p.SA) & 1);
           tc_fence_after_sync();
+          tr.ev(10);
           const int q0 = q_first + tile * kTileM;
           const int g_lo = (q0 - p.Wp - 1) / p.Wp;
           const int a_off_px = (q0 - p.Wp - 1) - g_lo * p.Wp;
-          const uint32_t a_stage = sbase + p.off_a + sa * p.a_stage_bytes;
           const uint32_t d_tmem = tmem + ab * p.OC;
+          uint64_t a_row = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * p.swb) >> 4);
+          uint64_t b_res = desc0_hi | ((sbase + p.off_w0) >> 4);
           uint32_t accumulate = 0;
-          for (int tap = 0; tap < 9; ++tap) {
-            const int kh = tap / 3, kw = tap - kh * 3;
-            for (int kb = 0; kb < p.nkb; ++kb) {
-              uint32_t b_base;
-              int s = 0;
-              if (p.w0_res) {
-                b_base = sbase + p.off_w0 + (tap * p.nkb + kb) * p.w0_block_bytes;
-              } else {
-                s = bcount % p.SB;
-                mbar_wait(smem_u32(&bar->b_full[s]), (bcount / p.SB) & 1);
-                tc_fence_after_sync();
-                b_base = sbase + p.off_b + s * p.b_stage_bytes;
-              }
-              const uint32_t a_base = a_stage + kb * p.a_kb_stride + (a_off_px + kh * p.Wp + kw) * p.swb;
-              const int nks = (kb == p.nkb - 1) ? p.ks_last : (p.swb >> 5);
-              for (int ks = 0; ks < nks; ++ks) {
-                umma_i8(d_tmem, make_smem_desc(a_base + ks * 32, 16, 8 * p.swb, lay0),
-                        make_smem_desc(b_base + ks * 32, 16, 8 * p.swb, lay0), idesc0, accumulate);
-                accumulate = 1;
-              }
-              if (!p.w0_res) {
-                umma_commit(smem_u32(&bar->b_empty[s]));
-                ++bcount;
+          for (int kh = 0; kh < 3; ++kh, a_row += a_step_kh) {
+            uint64_t a_tap = a_row;
+            for (int kw = 0; kw < 3; ++kw, a_tap += a_step_kw) {
+              uint64_t a_kb = a_tap;
+              for (int kb = 0; kb < p.nkb; ++kb, a_kb += a_step_kb) {
+                uint64_t b_desc;
+                if (p.w0_res) {
+                  b_desc = b_res;
+                  b_res += w0_step;
+                } else {
+                  mbar_wait(smem_u32(&bar->b_full[bs]), bph);
+                  tc_fence_after_sync();
+                  b_desc = desc0_hi | (b_stage0 + bs * b_stage_step);
+                }
+                const int nks = (kb == p.nkb - 1) ? p.ks_last : nks_full;
+                uint64_t a_ks = a_kb;
+                for (int ks = 0; ks < nks; ++ks, a_ks += 2, b_desc += 2) {
+                  umma_i8(d_tmem, a_ks, b_desc, idesc0, accumulate);
+                  accumulate = 1;
+                }
+                if (!p.w0_res) {
+                  umma_commit(smem_u32(&bar->b_empty[bs]));
+                  if (++bs == (uint32_t)p.SB) { bs = 0; bph ^= 1; }
+                }
               }
             }
           }
           umma_commit(smem_u32(&bar->a_empty[sa]));
           umma_commit(smem_u32(&bar->acc0_full[ab]));
+          tr.ev(11);
         }
         if (it >= 1) {
           // ---- GEMM2(it-1): acc1[chunk] = mid x W1[chunk]
           const int jt = it - 1, mb = jt % p.NM;
           mbar_wait(smem_u32(&bar->mid_full[mb]), (jt / p.NM) & 1);
           tc_fence_after_sync();
-          const uint32_t mid = sbase + p.off_mid + mb * p.mid_bytes;
+          tr.ev(12);
+          const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid + mb * p.mid_bytes) >> 4);
+          uint64_t b_res = desc1_hi | ((sbase + p.off_w1) >> 4);
           for (int j = 0; j < p.n_chunks; ++j, ++c1count) {
             const int cb = c1count & 1;
             mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ 1);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
+            uint64_t a_kb = mid_desc;
             uint32_t accumulate = 0;
-            for (int kb = 0; kb < p.nkb1; ++kb) {
-              uint32_t b_base;
-              int s = 0;
+            for (int kb = 0; kb < p.nkb1; ++kb, a_kb += mid_step_kb) {
+              uint64_t b_desc;
               if (p.w1_res) {
-                b_base = sbase + p.off_w1 + (j * p.nkb1 + kb) * p.w1_block_bytes;
+                b_desc = b_res;
+                b_res += w1_step;
               } else {
-                s = bcount % p.SB;
-                mbar_wait(smem_u32(&bar->b_full[s]), (bcount / p.SB) & 1);
+                mbar_wait(smem_u32(&bar->b_full[bs]), bph);
                 tc_fence_after_sync();
-                b_base = sbase + p.off_b + s * p.b_stage_bytes;
+                b_desc = desc1_hi | (b_stage0 + bs * b_stage_step);
               }
-              const uint32_t a_base = mid + kb * p.mid_kb_stride;
-              const int nks = (kb == p.nkb1 - 1) ? p.ks1_last : (p.swb1 >> 5);
-              for (int ks = 0; ks < nks; ++ks) {
-                umma_i8(d_tmem, make_smem_desc(a_base + ks * 32, 16, 8 * p.swb1, lay1),
-                        make_smem_desc(b_base + ks * 32, 16, 8 * p.swb1, lay1), idesc1, accumulate);
+              const int nks = (kb == p.nkb1 - 1) ? p.ks1_last : nks1_full;
+              uint64_t a_ks = a_kb;
+              for (int ks = 0; ks < nks; ++ks, a_ks += 2, b_desc += 2) {
+                umma_i8(d_tmem, a_ks, b_desc, idesc1, accumulate);
                 accumulate = 1;
               }
               if (!p.w1_res) {
-                umma_commit(smem_u32(&bar->b_empty[s]));
-                ++bcount;
+                umma_commit(smem_u32(&bar->b_empty[bs]));
+                if (++bs == (uint32_t)p.SB) { bs = 0; bph ^= 1; }
               }
             }
             umma_commit(smem_u32(&bar->acc1_full[cb]));
+            tr.ev(13);
           }
           umma_commit(smem_u32(&bar->mid_empty[mb]));
         }
@@ -402,6 +444,8 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ts = (kDst == DF_F32 || kDst == DF_S32) ? 4 : 1;
     const uint32_t swz_mask1 = (uint32_t)(p.swb1 / 16 - 1);
     uint32_t c1count = 0;
+    Tracer tr(p, 3);
+    if (threadIdx.x != kEpiWarp0 * 32) tr.base = nullptr;
     for (int it = 0; it < n_local; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       // where does this row go?
@@ -413,25 +457,41 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       // ---- conv0 epilogue: acc0 -> u8 intermediate in smem (K-major, swizzled)
       const int ab = it % p.n_acc0, mb = it % p.NM;
-      mbar_wait(smem_u32(&bar->mid_empty[mb]), ((it / p.NM) & 1) ^ 1);
-      mbar_wait(smem_u32(&bar->acc0_full[ab]), (it / p.n_acc0) & 1);
+      mbar_wait_warp(smem_u32(&bar->mid_empty[mb]), ((it / p.NM) & 1) ^ 1);
+      mbar_wait_warp(smem_u32(&bar->acc0_full[ab]), (it / p.n_acc0) & 1);
       tc_fence_after_sync();
+      tr.ev(30);
       uint8_t* mid = smem + p.off_mid + mb * p.mid_bytes;
-      for (int c = half; c < (p.OC >> 4); c += 2) {
-        uint32_t acc[16];
-        tmem_ld_x16(lane_addr + ab * p.OC + c * 16, acc);
-        tmem_ld_wait();
-        const float4* b4 = reinterpret_cast<const float4*>(sb0 + c * 16);
-        const float4* s4 = reinterpret_cast<const float4*>(ss0 + c * 16);
-        uint4 v;
-        v.x = requant_u8x4<kDown0, kNanSafe>(acc + 0, b4[0], s4[0]);
-        v.y = requant_u8x4<kDown0, kNanSafe>(acc + 4, b4[1], s4[1]);
-        v.z = requant_u8x4<kDown0, kNanSafe>(acc + 8, b4[2], s4[2]);
-        v.w = requant_u8x4<kDown0, kNanSafe>(acc + 12, b4[3], s4[3]);
-        const int kb = (c * 16) / p.swb1;
-        uint32_t off = (uint32_t)m * p.swb1 + (uint32_t)(c * 16 - kb * p.swb1);
-        off ^= ((off >> 7) & swz_mask1) << 4;  // Swizzle<B,4,3> on the (1024 B aligned) block offset
-        *reinterpret_cast<uint4*>(mid + kb * p.mid_kb_stride + off) = v;
+      {
+        // two statically indexed register buffers: the TMEM load of group c+2 is in flight while
+        // group c is converted (a runtime-indexed acc[buf][] would live in local memory)
+        const int nch = p.OC >> 4;
+        const uint32_t t_base = lane_addr + ab * p.OC;
+        uint32_t acc_a[16], acc_b[16];
+        auto emit = [&](const uint32_t* acc, int c) {
+          const float4* b4 = reinterpret_cast<const float4*>(sb0 + c * 16);
+          const float4* s4 = reinterpret_cast<const float4*>(ss0 + c * 16);
+          uint4 v;
+          v.x = requant_u8x4<kDown0, kNanSafe>(acc + 0, b4[0], s4[0]);
+          v.y = requant_u8x4<kDown0, kNanSafe>(acc + 4, b4[1], s4[1]);
+          v.z = requant_u8x4<kDown0, kNanSafe>(acc + 8, b4[2], s4[2]);
+          v.w = requant_u8x4<kDown0, kNanSafe>(acc + 12, b4[3], s4[3]);
+          const int kb = (c * 16) / p.swb1;
+          uint32_t off = (uint32_t)m * p.swb1 + (uint32_t)(c * 16 - kb * p.swb1);
+          off ^= ((off >> 7) & swz_mask1) << 4;  // Swizzle<B,4,3> on the (1024 B aligned) block offset
+          *reinterpret_cast<uint4*>(mid + kb * p.mid_kb_stride + off) = v;
+        };
+        if (half < nch) tmem_ld_x16(t_base + half * 16, acc_a);
+        for (int c = half; c < nch; c += 4) {
+          tmem_ld_wait();
+          if (c + 2 < nch) tmem_ld_x16(t_base + (c + 2) * 16, acc_b);
+          emit(acc_a, c);
+          if (c + 2 < nch) {
+            tmem_ld_wait();
+            if (c + 4 < nch) tmem_ld_x16(t_base + (c + 4) * 16, acc_a);
+            emit(acc_b, c + 2);
+          }
+        }
       }
       tc_fence_before_sync();
       fence_proxy_async_smem();
@@ -440,28 +500,41 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_arrive(smem_u32(&bar->acc0_empty[ab]));
         mbar_arrive(smem_u32(&bar->mid_full[mb]));
       }
+      tr.ev(31);
 
       // ---- conv1 epilogue: acc1 chunks -> global
       for (int j = 0; j < p.n_chunks; ++j, ++c1count) {
         const int cb = c1count & 1;
-        mbar_wait(smem_u32(&bar->acc1_full[cb]), (c1count >> 1) & 1);
+        mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c1count >> 1) & 1);
         tc_fence_after_sync();
-        for (int c = half; c < (p.nc1 >> 4); c += 2) {
+        tr.ev(32);
+        int nch = (p.OC1 - j * p.nc1) >> 4;  // real 16-column groups in this chunk
+        if (nch > (p.nc1 >> 4)) nch = p.nc1 >> 4;
+        const uint32_t t_base = lane_addr + kAcc1Col + cb * kAcc1Stride;
+        uint32_t acc_a[16], acc_b[16];
+        auto emit = [&](const uint32_t* acc, int c) {
           const int col = j * p.nc1 + c * 16;
-          if (col >= p.OC1) break;
-          uint32_t acc[16];
-          tmem_ld_x16(lane_addr + kAcc1Col + cb * kAcc1Stride + c * 16, acc);
-          tmem_ld_wait();
           if (valid)
             store16<kDst, kDown1, kNanSafe>(acc, sb1 + col, ss1 + col, p.relu1 != 0, out_row + (size_t)col * ts);
+        };
+        if (half < nch) tmem_ld_x16(t_base + half * 16, acc_a);
+        for (int c = half; c < nch; c += 4) {
+          tmem_ld_wait();
+          if (c + 2 < nch) tmem_ld_x16(t_base + (c + 2) * 16, acc_b);
+          emit(acc_a, c);
+          if (c + 2 < nch) {
+            tmem_ld_wait();
+            if (c + 4 < nch) tmem_ld_x16(t_base + (c + 4) * 16, acc_a);
+            emit(acc_b, c + 2);
+          }
         }
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bar->acc1_empty[cb]));
+        tr.ev(33);
       }
     }
   }
-
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 3) tmem_dealloc<512>(tmem);
@@ -524,6 +597,8 @@ struct df_conv {
   CUtensorMap tmA;
   const void* tmA_src;
   int tmA_n;
+  unsigned long long* trace;
+  int trace_cap;
 };
 
 namespace {
@@ -812,9 +887,20 @@ extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, vo
   p.N = n;
   p.n_tiles = tiles_for(p, n);
   p.dst = dst;
+  p.trace = op->trace;
+  p.trace_cap = op->trace_cap;
   const int grid = p.n_tiles < op->sms ? p.n_tiles : op->sms;
   op->kernel<<<grid, kThreads, op->smem_bytes, (cudaStream_t)stream>>>(op->tmA, op->tmW0, op->tmW1, p);
   DF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Diagnostic: record a per-role clock64 timeline into `dev_buf` (grid * 4 * cap u64 words) on the
+// following launches; pass null to switch it off.  Not part of the reference-facing surface.
+extern "C" int df_conv_debug_trace(df_conv* op, void* dev_buf, int cap) {
+  if (!op) return df::fail(DF_E_INVALID, "trace: null op");
+  op->trace = static_cast<unsigned long long*>(dev_buf);
+  op->trace_cap = dev_buf ? cap : 0;
   return 0;
 }
 

@@ -61,6 +61,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Warp-collective wait: ONE lane polls, the rest park at the warp barrier.  Hundreds of threads
+// spinning on try_wait saturate the SM's MIO/sync pipeline and slow down every other warp
+// (measured: 3-5x on both MMA issue and epilogue math, profiles/r01_trace_*.log).
+// kBackoffNs > 0 adds a sleep between polls for waits that are expected to be long.
+template <int kBackoffNs = 0>
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+      if (kBackoffNs > 0) __nanosleep(kBackoffNs);
+      if (++spins > DF_MBAR_SPIN_LIMIT) {
+        printf("mbar_wait timeout: block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar,
+               parity);
+        __trap();
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------- fences
 // generic-proxy writes to smem -> visible to the async proxy (TMA / tcgen05.mma reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "df_free", "df_memset", "df_host_register", "df_host_unregister", "df_h2d", "df_d2h", "df_stream_create",
     "df_stream_sync", "df_stream_destroy", "df_event_create", "df_event_record", "df_event_elapsed_ms",
     "df_event_destroy", "df_concat_check", "df_concat_run", "df_conv_create", "df_conv_run", "df_conv_query",
-    "df_conv_destroy",
+    "df_conv_destroy", "df_conv_debug_trace",
 ]
 
 
@@ -85,6 +85,7 @@ def lib():
         l.df_conv_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         l.df_conv_query.argtypes = [C.c_void_p, C.POINTER(ConvInfo)]
         l.df_conv_destroy.argtypes = [C.c_void_p]
+        l.df_conv_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _lib = l
     return _lib
 

@@ -103,6 +103,9 @@ int df_conv_create(const df_conv_desc *desc, const int8_t *wei_OIhw4i16o4i,
 int df_conv_run(df_conv *op, const uint8_t *src_dev, void *dst_dev, int n, void *stream);
 int df_conv_query(const df_conv *op, df_conv_info *info);
 int df_conv_destroy(df_conv *op);
+/* Diagnostic only (no reference counterpart): per-role clock64 timeline of the next launches
+ * into dev_buf[grid * 4 * cap] (u64 words: tag << 48 | clock); NULL switches it off. */
+int df_conv_debug_trace(df_conv *op, void *dev_buf, int cap);
 
 #ifdef __cplusplus
 }

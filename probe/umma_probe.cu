@@ -462,7 +462,7 @@ static int run_math() {
 
 // ---------------------------------------------------------------- T8 MMA speed of light
 template <int N>
-__global__ void __launch_bounds__(128, 1) bench_mma(int iters, long long* cycles_out) {
+__global__ void __launch_bounds__(128, 1) bench_mma(int iters, long long* cycles_out, int a_row_shift, int swb) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(128, 1) bench_mma(int iters, long long* cycles
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   // pseudo-random operand bytes (power draw depends on data toggling)
-  for (int i = tid; i < (128 + N) * 128 / 4; i += 128)
+  for (int i = tid; i < (256 + N) * 128 / 4; i += 128)
     reinterpret_cast<uint32_t*>(smem)[i] = (i * 2654435761u) ^ (blockIdx.x * 40503u);
   fence_proxy_async_smem();
   if (tid == 0) {
@@ -485,14 +485,15 @@ __global__ void __launch_bounds__(128, 1) bench_mma(int iters, long long* cycles
   long long t0 = 0, t1 = 0;
   if (tid == 0) {
     const uint32_t idesc = make_idesc_i8(128, N, 0, 1);
-    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 128 * 128);
+    const uint32_t a0 = smem_u32(smem) + a_row_shift * swb, b0 = smem_u32(smem + 256 * 128);
+    const uint32_t lay = swb == 128 ? kLayoutSW128 : kLayoutSW64;
+    const int nk = swb / 32;
     t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       uint32_t d = tmem + (it & 1) * N;
-#pragma unroll
       for (int k = 0; k < 4; ++k) {
-        uint64_t da = make_smem_desc(a0 + k * 32, 16, 1024, kLayoutSW128);
-        uint64_t db = make_smem_desc(b0 + k * 32, 16, 1024, kLayoutSW128);
+        uint64_t da = make_smem_desc(a0 + (k % nk) * 32, 16, 8 * swb, lay);
+        uint64_t db = make_smem_desc(b0 + (k % nk) * 32, 16, 8 * swb, lay);
         umma_i8(d, da, db, idesc, (it > 1) | k);
       }
     }
@@ -507,11 +508,11 @@ __global__ void __launch_bounds__(128, 1) bench_mma(int iters, long long* cycles
 }
 
 template <int N>
-static void run_bench_one(int nsm) {
+static void run_bench_one(int nsm, int a_row_shift = 0, int swb = 128) {
   const int iters = 4000;
   long long* dcyc;
   CK(cudaMalloc(&dcyc, nsm * sizeof(long long)));
-  size_t smem_bytes = (128 + N) * 128 + 1024;
+  size_t smem_bytes = (256 + N) * 128 + 1024;
   CK(cudaFuncSetAttribute(bench_mma<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
@@ -519,7 +520,7 @@ static void run_bench_one(int nsm) {
   float best = 1e30f;
   for (int rep = 0; rep < 5; ++rep) {
     cudaEventRecord(e0);
-    bench_mma<N><<<nsm, 128, smem_bytes>>>(iters, dcyc);
+    bench_mma<N><<<nsm, 128, smem_bytes>>>(iters, dcyc, a_row_shift, swb);
     cudaEventRecord(e1);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -536,9 +537,9 @@ static void run_bench_one(int nsm) {
   for (auto c : cyc) cmax = c > cmax ? c : cmax;
   double macs_per_cta = (double)iters * 4 * 128.0 * N * 32.0;
   double tops = 2.0 * macs_per_cta * nsm / (best * 1e-3) / 1e12;
-  printf("BENCH kind::i8 M=128 N=%3d K=32: %.1f MAC/clk/SM (clock64), %.1f TOPS over %d SMs "
+  printf("BENCH kind::i8 M=128 N=%3d K=32 sw=%d a_row_shift=%2d: %.1f MAC/clk/SM (clock64), %.1f TOPS over %d SMs "
          "(events, best of 5, %.3f ms)\n",
-         N, macs_per_cta / (double)cmax, tops, nsm, best);
+         N, swb, a_row_shift, macs_per_cta / (double)cmax, tops, nsm, best);
   cudaFree(dcyc);
 }
 
@@ -558,6 +559,9 @@ int main(int argc, char** argv) {
     run_bench_one<256>(prop.multiProcessorCount);
     run_bench_one<128>(prop.multiProcessorCount);
     run_bench_one<64>(prop.multiProcessorCount);
+    for (int sh : {1, 4, 8, 9, 30, 59}) run_bench_one<128>(prop.multiProcessorCount, sh, 128);
+    for (int sh : {0, 1, 2, 9, 58}) run_bench_one<64>(prop.multiProcessorCount, sh, 64);
+    for (int sh : {1, 9}) run_bench_one<256>(prop.multiProcessorCount, sh, 128);
   }
   printf("probe done, failing groups: %d\n", fails);
   return 0;
