@@ -25,6 +25,7 @@
 //  * weights live in shared memory for the whole (persistent) kernel when they fit; otherwise
 //    they stream through a ring of stages in exactly the order the MMA thread consumes them.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -54,6 +55,7 @@ struct Params {
   int swb1, nkb1, ks1_last;  // conv1
   int nc1, n_chunks, n_acc0;
   int SA, SB, NM, w0_res, w1_res;  // halo stages, weight stages, intermediate buffers
+  int tile_step_mod;               // (128 * gridDim.x) mod Wp: halo-window offset step per tile
   uint32_t off_bias0, off_scale0, off_bias1, off_scale1;
   uint32_t off_a, a_stage_bytes, a_kb_stride;
   uint32_t off_mid, mid_bytes, mid_kb_stride;
@@ -93,11 +95,64 @@ __device__ __forceinline__ uint32_t layout_of(int swb) {
   return swb == 128 ? kLayoutSW128 : (swb == 64 ? kLayoutSW64 : kLayoutSW32);
 }
 
+// ------------------------------------------------------------------------ geometry policies
+// The BASELINE.json shapes get their channel geometry at compile time: the MMA issue loop then
+// unrolls completely (9 taps x K-blocks x K-steps), weight-stage indices become constants and all
+// descriptor arithmetic is immediate adds in the uniform datapath.  Every other accepted shape runs
+// the same code through the run-time policy (loops stay loops; slower issue, same results).
+template <int kIC, int kOC, int kOC1, int kW0Res, int kW1Res, int kSB>
+struct StaticGeom {
+  static constexpr bool is_static = true;
+  static constexpr int IC = kIC, OC = kOC, OC1 = kOC1, w0_res = kW0Res, w1_res = kW1Res, SB = kSB;
+  static constexpr int swb = kIC > 64 ? 128 : (kIC > 32 ? 64 : 32);
+  static constexpr int nkb = (kIC + swb - 1) / swb;
+  static constexpr int ks_last = (kIC - (nkb - 1) * swb + 31) / 32;
+  static constexpr int swb1 = kOC > 64 ? 128 : (kOC > 32 ? 64 : 32);
+  static constexpr int nkb1 = (kOC + swb1 - 1) / swb1;
+  static constexpr int ks1_last = (kOC - (nkb1 - 1) * swb1 + 31) / 32;
+  static constexpr int nc1 = kOC1 < 128 ? kOC1 : 128;
+  static constexpr int n_chunks = (kOC1 + nc1 - 1) / nc1;
+  static constexpr int n_acc0 = kOC <= 128 ? 2 : 1;
+};
+struct DynGeom {
+  static constexpr bool is_static = false;
+};
+
+#define DF_GEO(name)                                  \
+  __device__ __forceinline__ int name() const {       \
+    if constexpr (G::is_static) return G::name;       \
+    else return p.name;                               \
+  }
+template <class G>
+struct Geo {
+  const Params& p;
+  DF_GEO(IC) DF_GEO(OC) DF_GEO(OC1) DF_GEO(w0_res) DF_GEO(w1_res) DF_GEO(SB)
+  DF_GEO(swb) DF_GEO(nkb) DF_GEO(ks_last) DF_GEO(swb1) DF_GEO(nkb1) DF_GEO(ks1_last)
+  DF_GEO(nc1) DF_GEO(n_chunks) DF_GEO(n_acc0)
+  __device__ __forceinline__ uint32_t w0_block_bytes() const { return (uint32_t)(OC() * swb()); }
+  __device__ __forceinline__ uint32_t w1_block_bytes() const { return (uint32_t)(nc1() * swb1()); }
+  __device__ __forceinline__ uint32_t mid_kb_stride() const { return (uint32_t)(kTileM * swb1()); }
+};
+#undef DF_GEO
+
 // ---------------------------------------------------------------------------- epilogue math
-// (float(acc) + bias) * scale as three separately rounded f32 operations -- vcvtdq2ps, vaddps,
-// vmulps (jit_conv_kernel.cc:96-100, :259-263).  Never an FMA.
-__device__ __forceinline__ float scale_acc(uint32_t acc, float bias, float scale) {
-  return __fmul_rn(__fadd_rn(__int2float_rn((int)acc), bias), scale);
+// t = (float(acc) + bias) * scale as separately rounded f32 operations -- vcvtdq2ps, vaddps, vmulps
+// (jit_conv_kernel.cc:96-100, :259-263), two lanes at a time on the packed f32x2 pipe (add.rn /
+// mul.rn keep IEEE rounding per lane; verified bit-exact in probe/umma_probe.cu).  Never an FMA.
+__device__ __forceinline__ void scale_pair(uint32_t a0, uint32_t a1, float b0, float b1, float s0, float s1, float& t0,
+                                           float& t1) {
+  const float f0 = __int2float_rn((int)a0), f1 = __int2float_rn((int)a1);
+  unsigned long long f, b, s;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(f) : "f"(f0), "f"(f1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(s) : "f"(s0), "f"(s1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(f), "l"(b));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(f), "l"(s));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(f));
+}
+__device__ __forceinline__ void scale4(const uint32_t* acc, const float4 b, const float4 s, float* t) {
+  scale_pair(acc[0], acc[1], b.x, b.y, s.x, s.y, t[0], t[1]);
+  scale_pair(acc[2], acc[3], b.z, b.w, s.z, s.w, t[2], t[3]);
 }
 // vmaxps(zero, t): second source when NaN or both zero
 __device__ __forceinline__ float relu_x86(float t) { return (0.0f > t) ? 0.0f : t; }
@@ -114,28 +169,24 @@ __device__ __forceinline__ int cvt_x86(float t) {
 // through non-finite scales / biases) is patched to 255 when kNanSafe.
 template <bool kDown, bool kNanSafe>
 __device__ __forceinline__ uint32_t requant_u8x4(const uint32_t* acc, const float4 b, const float4 s) {
-  float t0 = scale_acc(acc[0], b.x, s.x), t1 = scale_acc(acc[1], b.y, s.y);
-  float t2 = scale_acc(acc[2], b.z, s.z), t3 = scale_acc(acc[3], b.w, s.w);
-  int q0 = kDown ? __float2int_rd(t0) : __float2int_rn(t0);
-  int q1 = kDown ? __float2int_rd(t1) : __float2int_rn(t1);
-  int q2 = kDown ? __float2int_rd(t2) : __float2int_rn(t2);
-  int q3 = kDown ? __float2int_rd(t3) : __float2int_rn(t3);
-  if (kNanSafe) {
-    if (t0 != t0) q0 = 255;
-    if (t1 != t1) q1 = 255;
-    if (t2 != t2) q2 = 255;
-    if (t3 != t3) q3 = 255;
+  float t[4];
+  scale4(acc, b, s, t);
+  int q[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    q[i] = kDown ? __float2int_rd(t[i]) : __float2int_rn(t[i]);
+    if (kNanSafe && t[i] != t[i]) q[i] = 255;
   }
   uint32_t hi, lo;
-  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(q3), "r"(q2));
-  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(q1), "r"(q0), "r"(hi));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(q[3]), "r"(q[2]));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(q[1]), "r"(q[0]), "r"(hi));
   return lo;
 }
 
 template <bool kDown>
 __device__ __forceinline__ uint32_t requant_s8x4(const uint32_t* acc, const float4 b, const float4 s, bool relu) {
-  float t[4] = {scale_acc(acc[0], b.x, s.x), scale_acc(acc[1], b.y, s.y), scale_acc(acc[2], b.z, s.z),
-                scale_acc(acc[3], b.w, s.w)};
+  float t[4];
+  scale4(acc, b, s, t);
   int q[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -171,29 +222,32 @@ __device__ __forceinline__ void store16(const uint32_t* acc, const float* bias, 
   } else {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const float4 b = b4[g], s = s4[g];
-      float t0 = scale_acc(acc[4 * g + 0], b.x, s.x), t1 = scale_acc(acc[4 * g + 1], b.y, s.y);
-      float t2 = scale_acc(acc[4 * g + 2], b.z, s.z), t3 = scale_acc(acc[4 * g + 3], b.w, s.w);
+      float t[4];
+      scale4(acc + 4 * g, b4[g], s4[g], t);
       if (relu) {
-        t0 = relu_x86(t0);
-        t1 = relu_x86(t1);
-        t2 = relu_x86(t2);
-        t3 = relu_x86(t3);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = relu_x86(t[i]);
       }
       uint4 v;
       if (kDst == DF_F32) {
-        v = make_uint4(__float_as_uint(t0), __float_as_uint(t1), __float_as_uint(t2), __float_as_uint(t3));
+        v = make_uint4(__float_as_uint(t[0]), __float_as_uint(t[1]), __float_as_uint(t[2]), __float_as_uint(t[3]));
       } else {
-        v = make_uint4((uint32_t)cvt_x86<kDown>(t0), (uint32_t)cvt_x86<kDown>(t1), (uint32_t)cvt_x86<kDown>(t2),
-                       (uint32_t)cvt_x86<kDown>(t3));
+        v = make_uint4((uint32_t)cvt_x86<kDown>(t[0]), (uint32_t)cvt_x86<kDown>(t[1]), (uint32_t)cvt_x86<kDown>(t[2]),
+                       (uint32_t)cvt_x86<kDown>(t[3]));
       }
       reinterpret_cast<uint4*>(out)[g] = v;
     }
   }
 }
 
+template <int kCols>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
+  if constexpr (kCols == 32) tmem_ld_x32(taddr, r);
+  else tmem_ld_x16(taddr, r);
+}
+
 // ------------------------------------------------------------------------------- the kernel
-template <int kDst, bool kDown0, bool kDown1, bool kNanSafe>
+template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
                   const __grid_constant__ CUtensorMap tmW1, const Params p) {
@@ -202,6 +256,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Barriers* bar = reinterpret_cast<Barriers*>(smem);
   const uint32_t sbase = smem_u32(smem);
+  const Geo<G> g{p};
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_local = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -237,14 +292,14 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     float* ss0 = reinterpret_cast<float*>(smem + p.off_scale0);
     float* sb1 = reinterpret_cast<float*>(smem + p.off_bias1);
     float* ss1 = reinterpret_cast<float*>(smem + p.off_scale1);
-    for (int i = threadIdx.x; i < p.OC; i += kThreads) {
+    for (int i = threadIdx.x; i < g.OC(); i += kThreads) {
       sb0[i] = p.bias0[i];
       ss0[i] = p.scale0[i];
     }
-    const int oc1_pad = p.n_chunks * p.nc1;
+    const int oc1_pad = g.n_chunks() * g.nc1();
     for (int i = threadIdx.x; i < oc1_pad; i += kThreads) {
-      sb1[i] = i < p.OC1 ? p.bias1[i] : 0.f;
-      ss1[i] = i < p.OC1 ? p.scale1[i] : 0.f;
+      sb1[i] = i < g.OC1() ? p.bias1[i] : 0.f;
+      ss1[i] = i < g.OC1() ? p.scale1[i] : 0.f;
     }
   }
   tc_fence_before_sync();
@@ -274,13 +329,14 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int nrows = g_hi - g_lo + 1;
         const uint32_t full = smem_u32(&bar->a_full[s]);
         const uint32_t stage = sbase + p.off_a + s * p.a_stage_bytes;
-        mbar_expect_tx(full, (uint32_t)(nrows * p.nkb * p.Wp * p.swb));
+        mbar_expect_tx(full, (uint32_t)(nrows * g.nkb() * p.Wp * g.swb()));
         int n = (g_lo > 0) ? (g_lo - 1) / p.Hp : 0;
         int h = (g_lo > 0) ? (g_lo - 1) - n * p.Hp - 1 : -2;  // -2: the all-zero row above everything
         uint32_t dst = stage;
-        const uint32_t row_bytes = p.Wp * p.swb;
+        const uint32_t row_bytes = p.Wp * g.swb();
         for (int r = 0; r < nrows; ++r, dst += row_bytes) {
-          for (int kb = 0; kb < p.nkb; ++kb) tma_load_4d(dst + kb * p.a_kb_stride, &tmA, full, kb * p.swb, 0, h, n);
+#pragma unroll
+          for (int kb = 0; kb < g.nkb(); ++kb) tma_load_4d(dst + kb * p.a_kb_stride, &tmA, full, kb * g.swb(), 0, h, n);
           if (h == -2) {
             h = -1;  // g = 1: the zero row above image 0
           } else if (++h == p.H) {
@@ -293,31 +349,31 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 2) {
     // =============================== TMA producer: weights =================================
     if (elect_one()) {
-      const int n_w0 = 9 * p.nkb, n_w1 = p.n_chunks * p.nkb1;
-      if (p.w0_res || p.w1_res) {
+      const int n_w0 = 9 * g.nkb(), n_w1 = g.n_chunks() * g.nkb1();
+      if (g.w0_res() || g.w1_res()) {
         const uint32_t full = smem_u32(&bar->res_full);
-        mbar_expect_tx(full, (p.w0_res ? n_w0 * p.w0_block_bytes : 0) + (p.w1_res ? n_w1 * p.w1_block_bytes : 0));
-        if (p.w0_res)
-          for (int b = 0; b < n_w0; ++b) tma_load_2d(sbase + p.off_w0 + b * p.w0_block_bytes, &tmW0, full, 0, b * p.OC);
-        if (p.w1_res)
-          for (int b = 0; b < n_w1; ++b) tma_load_2d(sbase + p.off_w1 + b * p.w1_block_bytes, &tmW1, full, 0, b * p.nc1);
+        mbar_expect_tx(full, (g.w0_res() ? n_w0 * g.w0_block_bytes() : 0) + (g.w1_res() ? n_w1 * g.w1_block_bytes() : 0));
+        if (g.w0_res())
+          for (int b = 0; b < n_w0; ++b) tma_load_2d(sbase + p.off_w0 + b * g.w0_block_bytes(), &tmW0, full, 0, b * g.OC());
+        if (g.w1_res())
+          for (int b = 0; b < n_w1; ++b) tma_load_2d(sbase + p.off_w1 + b * g.w1_block_bytes(), &tmW1, full, 0, b * g.nc1());
       }
-      if (!p.w0_res || !p.w1_res) {
+      if (!g.w0_res() || !g.w1_res()) {
         uint32_t s = 0, ph = 1;  // stage cursor and the parity to wait for on b_empty
         for (int it = 0; it <= n_local; ++it) {  // same interleaving as the MMA thread below
-          if (it < n_local && !p.w0_res)
+          if (it < n_local && !g.w0_res())
             for (int b = 0; b < n_w0; ++b) {
               mbar_wait(smem_u32(&bar->b_empty[s]), ph);
-              mbar_expect_tx(smem_u32(&bar->b_full[s]), p.w0_block_bytes);
-              tma_load_2d(sbase + p.off_b + s * p.b_stage_bytes, &tmW0, smem_u32(&bar->b_full[s]), 0, b * p.OC);
-              if (++s == (uint32_t)p.SB) { s = 0; ph ^= 1; }
+              mbar_expect_tx(smem_u32(&bar->b_full[s]), g.w0_block_bytes());
+              tma_load_2d(sbase + p.off_b + s * p.b_stage_bytes, &tmW0, smem_u32(&bar->b_full[s]), 0, b * g.OC());
+              if (++s == (uint32_t)g.SB()) { s = 0; ph ^= 1; }
             }
-          if (it >= 1 && !p.w1_res)
+          if (it >= 1 && !g.w1_res())
             for (int b = 0; b < n_w1; ++b) {
               mbar_wait(smem_u32(&bar->b_empty[s]), ph);
-              mbar_expect_tx(smem_u32(&bar->b_full[s]), p.w1_block_bytes);
-              tma_load_2d(sbase + p.off_b + s * p.b_stage_bytes, &tmW1, smem_u32(&bar->b_full[s]), 0, b * p.nc1);
-              if (++s == (uint32_t)p.SB) { s = 0; ph ^= 1; }
+              mbar_expect_tx(smem_u32(&bar->b_full[s]), g.w1_block_bytes());
+              tma_load_2d(sbase + p.off_b + s * p.b_stage_bytes, &tmW1, smem_u32(&bar->b_full[s]), 0, b * g.nc1());
+              if (++s == (uint32_t)g.SB()) { s = 0; ph ^= 1; }
             }
         }
       }
@@ -325,68 +381,73 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ===================================== MMA issuer ======================================
     if (elect_one()) {
-      const uint32_t idesc0 = make_idesc_i8(kTileM, p.OC, 0, 1);
-      const uint32_t idesc1 = make_idesc_i8(kTileM, p.nc1, 0, 1);
+      const uint32_t idesc0 = make_idesc_i8(kTileM, g.OC(), 0, 1);
+      const uint32_t idesc1 = make_idesc_i8(kTileM, g.nc1(), 0, 1);
       // descriptors differ only in their 14-bit start-address field (16 B units): constant part + adds
-      const uint64_t desc0_hi = make_smem_desc(0, 16, 8 * p.swb, layout_of(p.swb));
-      const uint64_t desc1_hi = make_smem_desc(0, 16, 8 * p.swb1, layout_of(p.swb1));
-      const uint32_t a_step_kw = p.swb >> 4, a_step_kh = (p.Wp * p.swb) >> 4, a_step_kb = p.a_kb_stride >> 4;
-      const uint32_t w0_step = p.w0_block_bytes >> 4, w1_step = p.w1_block_bytes >> 4;
-      const uint32_t mid_step_kb = p.mid_kb_stride >> 4, b_stage_step = p.b_stage_bytes >> 4;
-      const uint64_t b_stage0 = (sbase + p.off_b) >> 4;
-      const int nks_full = p.swb >> 5, nks1_full = p.swb1 >> 5;
-      if (p.w0_res || p.w1_res) mbar_wait(smem_u32(&bar->res_full), 0);
-      uint32_t bs = 0, bph = 0;  // weight stage cursor / parity to wait for on b_full
+      const uint64_t desc0_hi = make_smem_desc(0, 16, 8 * g.swb(), layout_of(g.swb()));
+      const uint64_t desc1_hi = make_smem_desc(0, 16, 8 * g.swb1(), layout_of(g.swb1()));
+      const uint32_t a_step_kw = g.swb() >> 4, a_step_kh = (p.Wp * g.swb()) >> 4, a_step_kb = p.a_kb_stride >> 4;
+      const uint32_t w0_step = g.w0_block_bytes() >> 4, w1_step = g.w1_block_bytes() >> 4;
+      const uint32_t mid_step_kb = g.mid_kb_stride() >> 4, b_stage_step = p.b_stage_bytes >> 4;
+      const uint64_t w0_desc = desc0_hi | ((sbase + p.off_w0) >> 4), w1_desc = desc1_hi | ((sbase + p.off_w1) >> 4);
+      const uint64_t bst0_desc = desc0_hi | ((sbase + p.off_b) >> 4), bst1_desc = desc1_hi | ((sbase + p.off_b) >> 4);
+      const int nks_full = g.swb() >> 5, nks1_full = g.swb1() >> 5;
+      if (g.w0_res() || g.w1_res()) mbar_wait(smem_u32(&bar->res_full), 0);
+      // weight-stage cursor.  Static geometry: every GEMM starts at stage 0 (SB divides the number of
+      // streamed blocks of each GEMM), so block i sits in stage i % SB -- a compile-time constant.
+      uint32_t bs = 0, bph = 0;
       uint32_t c1count = 0;
+      // position of the tile inside its halo window, advanced without divisions
+      int a_off_px = (q_first - p.Wp - 1 + (int)blockIdx.x * kTileM) % p.Wp;
+      uint32_t sa = 0, a_par = 0;
       Tracer tr(p, 1);
       tr.ev(9);
       for (int it = 0; it <= n_local; ++it) {
         if (it < n_local) {
           // ---- GEMM1(it): acc0 = sum over 9 taps, K-blocks of halo(tile) x W0
-          const int tile = blockIdx.x + it * gridDim.x;
-          const int sa = it % p.SA;
-          const int ab = it % p.n_acc0;
-          mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / p.n_acc0) & 1) ^ 1);
-          mbar_wait(smem_u32(&bar->a_full[sa]), (it / p.SA) & 1);
+          const int ab = it % g.n_acc0();
+          mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / g.n_acc0()) & 1) ^ 1);
+          mbar_wait(smem_u32(&bar->a_full[sa]), a_par);
           tc_fence_after_sync();
           tr.ev(10);
-          const int q0 = q_first + tile * kTileM;
-          const int g_lo = (q0 - p.Wp - 1) / p.Wp;
-          const int a_off_px = (q0 - p.Wp - 1) - g_lo * p.Wp;
-          const uint32_t d_tmem = tmem + ab * p.OC;
-          uint64_t a_row = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * p.swb) >> 4);
-          uint64_t b_res = desc0_hi | ((sbase + p.off_w0) >> 4);
-          uint32_t accumulate = 0;
-          for (int kh = 0; kh < 3; ++kh, a_row += a_step_kh) {
-            uint64_t a_tap = a_row;
-            for (int kw = 0; kw < 3; ++kw, a_tap += a_step_kw) {
-              uint64_t a_kb = a_tap;
-              for (int kb = 0; kb < p.nkb; ++kb, a_kb += a_step_kb) {
+          const uint32_t d_tmem = tmem + ab * g.OC();
+          const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swb()) >> 4);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int kb = 0; kb < g.nkb(); ++kb) {
+                const int blk = (kh * 3 + kw) * g.nkb() + kb;
                 uint64_t b_desc;
-                if (p.w0_res) {
-                  b_desc = b_res;
-                  b_res += w0_step;
+                uint32_t st = 0;
+                if (g.w0_res()) {
+                  b_desc = w0_desc + blk * w0_step;
                 } else {
-                  mbar_wait(smem_u32(&bar->b_full[bs]), bph);
+                  st = G::is_static ? (uint32_t)(blk % g.SB()) : bs;
+                  const uint32_t par = G::is_static ? (bph ^ ((blk / g.SB()) & 1)) : bph;
+                  mbar_wait(smem_u32(&bar->b_full[st]), par);
                   tc_fence_after_sync();
-                  b_desc = desc0_hi | (b_stage0 + bs * b_stage_step);
+                  b_desc = bst0_desc + st * b_stage_step;
                 }
-                const int nks = (kb == p.nkb - 1) ? p.ks_last : nks_full;
-                uint64_t a_ks = a_kb;
-                for (int ks = 0; ks < nks; ++ks, a_ks += 2, b_desc += 2) {
-                  umma_i8(d_tmem, a_ks, b_desc, idesc0, accumulate);
-                  accumulate = 1;
-                }
-                if (!p.w0_res) {
-                  umma_commit(smem_u32(&bar->b_empty[bs]));
-                  if (++bs == (uint32_t)p.SB) { bs = 0; bph ^= 1; }
+                const uint64_t a_desc = a_tile + kh * a_step_kh + kw * a_step_kw + kb * a_step_kb;
+                const int nks = (kb == g.nkb() - 1) ? g.ks_last() : nks_full;
+#pragma unroll
+                for (int ks = 0; ks < nks; ++ks) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+                if (!g.w0_res()) {
+                  umma_commit(smem_u32(&bar->b_empty[st]));
+                  if (!G::is_static && ++bs == (uint32_t)g.SB()) { bs = 0; bph ^= 1; }
                 }
               }
             }
           }
+          if (G::is_static && !g.w0_res()) bph ^= ((9 * g.nkb() / g.SB()) & 1);
           umma_commit(smem_u32(&bar->a_empty[sa]));
           umma_commit(smem_u32(&bar->acc0_full[ab]));
           tr.ev(11);
+          if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
+          a_off_px += p.tile_step_mod;
+          if (a_off_px >= p.Wp) a_off_px -= p.Wp;
         }
         if (it >= 1) {
           // ---- GEMM2(it-1): acc1[chunk] = mid x W1[chunk]
@@ -395,54 +456,60 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after_sync();
           tr.ev(12);
           const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid + mb * p.mid_bytes) >> 4);
-          uint64_t b_res = desc1_hi | ((sbase + p.off_w1) >> 4);
-          for (int j = 0; j < p.n_chunks; ++j, ++c1count) {
+#pragma unroll
+          for (int j = 0; j < g.n_chunks(); ++j, ++c1count) {
             const int cb = c1count & 1;
             mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ 1);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
-            uint64_t a_kb = mid_desc;
-            uint32_t accumulate = 0;
-            for (int kb = 0; kb < p.nkb1; ++kb, a_kb += mid_step_kb) {
+#pragma unroll
+            for (int kb = 0; kb < g.nkb1(); ++kb) {
+              const int blk = j * g.nkb1() + kb;
               uint64_t b_desc;
-              if (p.w1_res) {
-                b_desc = b_res;
-                b_res += w1_step;
+              uint32_t st = 0;
+              if (g.w1_res()) {
+                b_desc = w1_desc + blk * w1_step;
               } else {
-                mbar_wait(smem_u32(&bar->b_full[bs]), bph);
+                st = G::is_static ? (uint32_t)(blk % g.SB()) : bs;
+                const uint32_t par = G::is_static ? (bph ^ ((blk / g.SB()) & 1)) : bph;
+                mbar_wait(smem_u32(&bar->b_full[st]), par);
                 tc_fence_after_sync();
-                b_desc = desc1_hi | (b_stage0 + bs * b_stage_step);
+                b_desc = bst1_desc + st * b_stage_step;
               }
-              const int nks = (kb == p.nkb1 - 1) ? p.ks1_last : nks1_full;
-              uint64_t a_ks = a_kb;
-              for (int ks = 0; ks < nks; ++ks, a_ks += 2, b_desc += 2) {
-                umma_i8(d_tmem, a_ks, b_desc, idesc1, accumulate);
-                accumulate = 1;
-              }
-              if (!p.w1_res) {
-                umma_commit(smem_u32(&bar->b_empty[bs]));
-                if (++bs == (uint32_t)p.SB) { bs = 0; bph ^= 1; }
+              const uint64_t a_desc = mid_desc + kb * mid_step_kb;
+              const int nks = (kb == g.nkb1() - 1) ? g.ks1_last() : nks1_full;
+#pragma unroll
+              for (int ks = 0; ks < nks; ++ks) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, (kb | ks) != 0);
+              if (!g.w1_res()) {
+                umma_commit(smem_u32(&bar->b_empty[st]));
+                if (!G::is_static && ++bs == (uint32_t)g.SB()) { bs = 0; bph ^= 1; }
               }
             }
             umma_commit(smem_u32(&bar->acc1_full[cb]));
             tr.ev(13);
           }
+          if (G::is_static && !g.w1_res()) bph ^= ((g.n_chunks() * g.nkb1() / g.SB()) & 1);
           umma_commit(smem_u32(&bar->mid_empty[mb]));
         }
       }
     }
   } else if (warp >= kEpiWarp0) {
     // ====================================== epilogue =======================================
-    const int quarter = warp & 3;             // TMEM lane quarter this warp may read
-    const int half = (warp - kEpiWarp0) >> 2;  // which half of the 16-column groups
+    // Column groups of GC = 32 (or 16 when the channel counts are not multiples of 64); each of
+    // the two warps sharing a TMEM lane quarter takes every other group.
+    constexpr bool kWide = G::is_static;  // static shapes have OC % 64 == 0 and nc1 % 64 == 0
+    constexpr int GC = kWide ? 32 : 16;
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may read
+    const int half = (warp - kEpiWarp0) >> 2;  // which half of the column groups
     const int m = quarter * 32 + lane;         // tile row = TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     const float* sb0 = reinterpret_cast<const float*>(smem + p.off_bias0);
     const float* ss0 = reinterpret_cast<const float*>(smem + p.off_scale0);
     const float* sb1 = reinterpret_cast<const float*>(smem + p.off_bias1);
     const float* ss1 = reinterpret_cast<const float*>(smem + p.off_scale1);
-    const int ts = (kDst == DF_F32 || kDst == DF_S32) ? 4 : 1;
-    const uint32_t swz_mask1 = (uint32_t)(p.swb1 / 16 - 1);
+    constexpr int ts = (kDst == DF_F32 || kDst == DF_S32) ? 4 : 1;
+    const uint32_t swz_mask1 = (uint32_t)(g.swb1() / 16 - 1);
+    const bool relu1 = p.relu1 != 0;
     uint32_t c1count = 0;
     Tracer tr(p, 3);
     if (threadIdx.x != kEpiWarp0 * 32) tr.base = nullptr;
@@ -450,46 +517,51 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int tile = blockIdx.x + it * gridDim.x;
       // where does this row go?
       const int q = q_first + tile * kTileM + m;
-      const int g = q / p.Wp, wq = q - g * p.Wp;
-      const int n = (g - 1) / p.Hp, hp = (g - 1) - n * p.Hp;
+      const int gq = q / p.Wp, wq = q - gq * p.Wp;
+      const int n = (gq - 1) / p.Hp, hp = (gq - 1) - n * p.Hp;
       const bool valid = (wq < p.W) && (hp >= 1) && (n < p.N);
-      uint8_t* out_row = static_cast<uint8_t*>(p.dst) + ((size_t)(n * p.H + hp - 1) * p.W + wq) * p.OC1 * ts;
+      uint8_t* out_row = static_cast<uint8_t*>(p.dst) + ((size_t)(n * p.H + hp - 1) * p.W + wq) * g.OC1() * ts;
 
       // ---- conv0 epilogue: acc0 -> u8 intermediate in smem (K-major, swizzled)
-      const int ab = it % p.n_acc0, mb = it % p.NM;
+      const int ab = it % g.n_acc0(), mb = it % p.NM;
       mbar_wait_warp(smem_u32(&bar->mid_empty[mb]), ((it / p.NM) & 1) ^ 1);
-      mbar_wait_warp(smem_u32(&bar->acc0_full[ab]), (it / p.n_acc0) & 1);
+      mbar_wait_warp(smem_u32(&bar->acc0_full[ab]), (it / g.n_acc0()) & 1);
       tc_fence_after_sync();
       tr.ev(30);
       uint8_t* mid = smem + p.off_mid + mb * p.mid_bytes;
       {
-        // two statically indexed register buffers: the TMEM load of group c+2 is in flight while
-        // group c is converted (a runtime-indexed acc[buf][] would live in local memory)
-        const int nch = p.OC >> 4;
-        const uint32_t t_base = lane_addr + ab * p.OC;
-        uint32_t acc_a[16], acc_b[16];
-        auto emit = [&](const uint32_t* acc, int c) {
-          const float4* b4 = reinterpret_cast<const float4*>(sb0 + c * 16);
-          const float4* s4 = reinterpret_cast<const float4*>(ss0 + c * 16);
-          uint4 v;
-          v.x = requant_u8x4<kDown0, kNanSafe>(acc + 0, b4[0], s4[0]);
-          v.y = requant_u8x4<kDown0, kNanSafe>(acc + 4, b4[1], s4[1]);
-          v.z = requant_u8x4<kDown0, kNanSafe>(acc + 8, b4[2], s4[2]);
-          v.w = requant_u8x4<kDown0, kNanSafe>(acc + 12, b4[3], s4[3]);
-          const int kb = (c * 16) / p.swb1;
-          uint32_t off = (uint32_t)m * p.swb1 + (uint32_t)(c * 16 - kb * p.swb1);
-          off ^= ((off >> 7) & swz_mask1) << 4;  // Swizzle<B,4,3> on the (1024 B aligned) block offset
-          *reinterpret_cast<uint4*>(mid + kb * p.mid_kb_stride + off) = v;
+        // two statically indexed register buffers: the TMEM load of the next group is in flight
+        // while this one is converted (a runtime-indexed acc[buf][] would live in local memory)
+        const int ngr = g.OC() / GC;
+        const uint32_t t_base = lane_addr + ab * g.OC();
+        uint32_t acc_a[GC], acc_b[GC];
+        auto emit = [&](const uint32_t* acc, int gr) {
+#pragma unroll
+          for (int sub = 0; sub < GC / 16; ++sub) {
+            const int c16 = gr * (GC / 16) + sub;  // 16-column (= 16-byte) unit
+            const float4* b4 = reinterpret_cast<const float4*>(sb0 + c16 * 16);
+            const float4* s4 = reinterpret_cast<const float4*>(ss0 + c16 * 16);
+            uint4 v;
+            v.x = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 0, b4[0], s4[0]);
+            v.y = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 4, b4[1], s4[1]);
+            v.z = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 8, b4[2], s4[2]);
+            v.w = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 12, b4[3], s4[3]);
+            const int kb = (c16 * 16) / g.swb1();
+            uint32_t off = (uint32_t)m * g.swb1() + (uint32_t)(c16 * 16 - kb * g.swb1());
+            off ^= ((off >> 7) & swz_mask1) << 4;  // Swizzle<B,4,3> on the (1024 B aligned) block offset
+            *reinterpret_cast<uint4*>(mid + kb * g.mid_kb_stride() + off) = v;
+          }
         };
-        if (half < nch) tmem_ld_x16(t_base + half * 16, acc_a);
-        for (int c = half; c < nch; c += 4) {
+        if (half < ngr) tmem_ld_cols<GC>(t_base + half * GC, acc_a);
+#pragma unroll
+        for (int gr = half; gr < ngr; gr += 4) {
           tmem_ld_wait();
-          if (c + 2 < nch) tmem_ld_x16(t_base + (c + 2) * 16, acc_b);
-          emit(acc_a, c);
-          if (c + 2 < nch) {
+          if (gr + 2 < ngr) tmem_ld_cols<GC>(t_base + (gr + 2) * GC, acc_b);
+          emit(acc_a, gr);
+          if (gr + 2 < ngr) {
             tmem_ld_wait();
-            if (c + 4 < nch) tmem_ld_x16(t_base + (c + 4) * 16, acc_a);
-            emit(acc_b, c + 2);
+            if (gr + 4 < ngr) tmem_ld_cols<GC>(t_base + (gr + 4) * GC, acc_a);
+            emit(acc_b, gr + 2);
           }
         }
       }
@@ -503,29 +575,35 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tr.ev(31);
 
       // ---- conv1 epilogue: acc1 chunks -> global
-      for (int j = 0; j < p.n_chunks; ++j, ++c1count) {
+      for (int j = 0; j < g.n_chunks(); ++j, ++c1count) {
         const int cb = c1count & 1;
         mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c1count >> 1) & 1);
         tc_fence_after_sync();
         tr.ev(32);
-        int nch = (p.OC1 - j * p.nc1) >> 4;  // real 16-column groups in this chunk
-        if (nch > (p.nc1 >> 4)) nch = p.nc1 >> 4;
+        int ncols = g.OC1() - j * g.nc1();  // real columns in this chunk
+        if (ncols > g.nc1()) ncols = g.nc1();
+        const int ngr = ncols / GC;
         const uint32_t t_base = lane_addr + kAcc1Col + cb * kAcc1Stride;
-        uint32_t acc_a[16], acc_b[16];
-        auto emit = [&](const uint32_t* acc, int c) {
-          const int col = j * p.nc1 + c * 16;
-          if (valid)
-            store16<kDst, kDown1, kNanSafe>(acc, sb1 + col, ss1 + col, p.relu1 != 0, out_row + (size_t)col * ts);
+        uint32_t acc_a[GC], acc_b[GC];
+        auto emit = [&](const uint32_t* acc, int gr) {
+          if (valid) {
+#pragma unroll
+            for (int sub = 0; sub < GC / 16; ++sub) {
+              const int col = j * g.nc1() + gr * GC + sub * 16;
+              store16<kDst, kDown1, kNanSafe>(acc + sub * 16, sb1 + col, ss1 + col, relu1, out_row + (size_t)col * ts);
+            }
+          }
         };
-        if (half < nch) tmem_ld_x16(t_base + half * 16, acc_a);
-        for (int c = half; c < nch; c += 4) {
+        if (half < ngr) tmem_ld_cols<GC>(t_base + half * GC, acc_a);
+#pragma unroll
+        for (int gr = half; gr < ngr; gr += 4) {
           tmem_ld_wait();
-          if (c + 2 < nch) tmem_ld_x16(t_base + (c + 2) * 16, acc_b);
-          emit(acc_a, c);
-          if (c + 2 < nch) {
+          if (gr + 2 < ngr) tmem_ld_cols<GC>(t_base + (gr + 2) * GC, acc_b);
+          emit(acc_a, gr);
+          if (gr + 2 < ngr) {
             tmem_ld_wait();
-            if (c + 4 < nch) tmem_ld_x16(t_base + (c + 4) * 16, acc_a);
-            emit(acc_b, c + 2);
+            if (gr + 4 < ngr) tmem_ld_cols<GC>(t_base + (gr + 4) * GC, acc_a);
+            emit(acc_b, gr + 2);
           }
         }
         tc_fence_before_sync();
@@ -535,6 +613,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   }
+
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 3) tmem_dealloc<512>(tmem);
@@ -564,15 +643,38 @@ inline int pick_swb(int k) { return k > 64 ? 128 : (k > 32 ? 64 : 32); }
 
 typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
 
-KernelFn pick_kernel(int dst_dt, bool down0, bool down1, bool nan_safe) {
-#define DF_PICK(DT)                                                                                     \
-  if (dst_dt == DT) {                                                                                   \
-    if (nan_safe) {                                                                                     \
-      if (down0) return down1 ? conv_fused_kernel<DT, true, true, true> : conv_fused_kernel<DT, true, false, true>; \
-      return down1 ? conv_fused_kernel<DT, false, true, true> : conv_fused_kernel<DT, false, false, true>;          \
-    }                                                                                                   \
-    if (down0) return down1 ? conv_fused_kernel<DT, true, true, false> : conv_fused_kernel<DT, true, false, false>; \
-    return down1 ? conv_fused_kernel<DT, false, true, false> : conv_fused_kernel<DT, false, false, false>;          \
+// Static geometries = the BASELINE.json conv shapes together with the shared-memory plan
+// df_conv_create derives for them (weights resident? how many weight stages).
+using GeoCfg1 = StaticGeom<64, 64, 256, 1, 1, 1>;      // 56x56  64->64->256 : everything resident
+using GeoCfg3 = StaticGeom<128, 128, 512, 0, 1, 3>;    // 28x28 128->128->512: W1 resident, W0 through 3 stages
+using GeoCfg4 = StaticGeom<256, 256, 1024, 0, 0, 2>;   // 14x14 256->256->1024: all weights through 2 stages
+
+template <class G>
+KernelFn pick_static(int dst_dt) {
+  switch (dst_dt) {
+    case DF_U8: return conv_fused_kernel<G, DF_U8, false, false, false>;
+    case DF_S8: return conv_fused_kernel<G, DF_S8, false, false, false>;
+    case DF_S32: return conv_fused_kernel<G, DF_S32, false, false, false>;
+    case DF_F32: return conv_fused_kernel<G, DF_F32, false, false, false>;
+  }
+  return nullptr;
+}
+
+// geom_id: 0 = run-time geometry, 1 / 3 / 4 = GeoCfg1 / GeoCfg3 / GeoCfg4
+KernelFn pick_kernel(int geom_id, int dst_dt, bool down0, bool down1, bool nan_safe) {
+  if (geom_id && !down0 && !down1 && !nan_safe) {
+    if (geom_id == 1) return pick_static<GeoCfg1>(dst_dt);
+    if (geom_id == 3) return pick_static<GeoCfg3>(dst_dt);
+    if (geom_id == 4) return pick_static<GeoCfg4>(dst_dt);
+  }
+#define DF_PICK(DT)                                                                                                   \
+  if (dst_dt == DT) {                                                                                                 \
+    if (nan_safe) {                                                                                                   \
+      if (down0) return down1 ? conv_fused_kernel<DynGeom, DT, true, true, true> : conv_fused_kernel<DynGeom, DT, true, false, true>;   \
+      return down1 ? conv_fused_kernel<DynGeom, DT, false, true, true> : conv_fused_kernel<DynGeom, DT, false, false, true>;            \
+    }                                                                                                                 \
+    if (down0) return down1 ? conv_fused_kernel<DynGeom, DT, true, true, false> : conv_fused_kernel<DynGeom, DT, true, false, false>;   \
+    return down1 ? conv_fused_kernel<DynGeom, DT, false, true, false> : conv_fused_kernel<DynGeom, DT, false, false, false>;            \
   }
   DF_PICK(DF_U8)
   DF_PICK(DF_S8)
@@ -582,12 +684,20 @@ KernelFn pick_kernel(int dst_dt, bool down0, bool down1, bool nan_safe) {
   return nullptr;
 }
 
+template <class G>
+bool geom_matches(const Params& p) {
+  return p.IC == G::IC && p.OC == G::OC && p.OC1 == G::OC1 && p.w0_res == G::w0_res && p.w1_res == G::w1_res &&
+         p.SB >= G::SB && p.swb == G::swb && p.nkb == G::nkb && p.swb1 == G::swb1 && p.nkb1 == G::nkb1 &&
+         p.nc1 == G::nc1 && p.n_chunks == G::n_chunks && p.n_acc0 == G::n_acc0;
+}
+
 }  // namespace
 
 struct df_conv {
   df_conv_desc desc;
   Params prm;        // everything except n-dependent fields and dst
   KernelFn kernel;
+  int geom_id;
   uint32_t smem_bytes;
   int device, sms;
   int8_t *d_w0, *d_w1;
@@ -781,6 +891,12 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
     int sb = (int)((avail - p.off_b) / p.b_stage_bytes);
     p.SB = sb > kMaxBStages ? kMaxBStages : sb;
   }
+  // compile-time geometry when the shape and the plan are one of the BASELINE configurations
+  op->geom_id = 0;
+  if (geom_matches<GeoCfg1>(p)) { op->geom_id = 1; p.SB = GeoCfg1::SB; }
+  else if (geom_matches<GeoCfg3>(p)) { op->geom_id = 3; p.SB = GeoCfg3::SB; }
+  else if (geom_matches<GeoCfg4>(p)) { op->geom_id = 4; p.SB = GeoCfg4::SB; }
+  if (getenv("DF_FORCE_DYNAMIC_GEOMETRY")) op->geom_id = 0;  // test hook: exercise the generic path
   op->smem_bytes = p.off_b + p.SB * p.b_stage_bytes + 1024;
 
   // ---- parameters: weights re-laid out K-major per (tap, K-block); bias -> f32; scales expanded
@@ -850,7 +966,7 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   DF_TRY(encode_2d(&op->tmW0, op->d_w0, p.swb, (long)9 * p.nkb * p.OC, p.OC));
   DF_TRY(encode_2d(&op->tmW1, op->d_w1, p.swb1, (long)p.n_chunks * p.nkb1 * p.nc1, p.nc1));
 
-  op->kernel = pick_kernel(d->dst_dt, d->round0 == DF_ROUND_DOWN, d->round1 == DF_ROUND_DOWN, p.nan_safe != 0);
+  op->kernel = pick_kernel(op->geom_id, d->dst_dt, d->round0 == DF_ROUND_DOWN, d->round1 == DF_ROUND_DOWN, p.nan_safe != 0);
   DF_TRY_CUDA(cudaFuncSetAttribute((const void*)op->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->smem_bytes));
   *out = op;
   return 0;
@@ -890,6 +1006,7 @@ extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, vo
   p.trace = op->trace;
   p.trace_cap = op->trace_cap;
   const int grid = p.n_tiles < op->sms ? p.n_tiles : op->sms;
+  p.tile_step_mod = (kTileM * grid) % p.Wp;
   op->kernel<<<grid, kThreads, op->smem_bytes, (cudaStream_t)stream>>>(op->tmA, op->tmW0, op->tmW1, p);
   DF_CUDA(cudaGetLastError());
   return 0;
