@@ -28,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "df_common.cuh"
@@ -37,9 +38,10 @@ using namespace sm100;
 
 namespace {
 
-constexpr int kThreads = 384;
-constexpr int kEpiWarp0 = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarp0 = 4;    // warps 0..3: TMA(A) | MMA | TMA(W) | TMEM alloc
+constexpr int kEpiWarps = 8;    // warps per epilogue group (two per TMEM lane quarter)
+constexpr int kEpiGroups = 2;   // groups take alternate work units (conv0 tile / conv1 chunk)
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiGroups * kEpiWarps);  // 640
 constexpr int kTileM = 128;
 constexpr int kMaxAStages = 4;
 constexpr int kMaxBStages = 8;
@@ -56,13 +58,16 @@ struct Params {
   int nc1, n_chunks, n_acc0;
   int SA, SB, NM, w0_res, w1_res;  // halo stages, weight stages, intermediate buffers
   int tile_step_mod;               // (128 * gridDim.x) mod Wp: halo-window offset step per tile
-  uint32_t off_bias0, off_scale0, off_bias1, off_scale1;
+  uint32_t off_bias0, off_scale0, off_bias1, off_scale1, off_k1;
+  int fast1;      // conv1 int->float by exact offset-magic conversion (k1 / bias1 hold K[q] / C[q])
+  int epi_ahead;  // epilogue does conv0 of tile i+1 before the conv1 chunks of tile i
   uint32_t off_a, a_stage_bytes, a_kb_stride;
   uint32_t off_mid, mid_bytes, mid_kb_stride;
   uint32_t off_w0, w0_block_bytes, off_w1, w1_block_bytes;
   uint32_t off_b, b_stage_bytes;
   int relu1, round0, round1, nan_safe;
   const float *bias0, *scale0, *bias1, *scale1;
+  const int* k1;
   void* dst;
   unsigned long long* trace;  // optional timeline buffer (df_conv_debug_trace), normally null
   int trace_cap;
@@ -113,9 +118,15 @@ struct StaticGeom {
   static constexpr int nc1 = kOC1 < 128 ? kOC1 : 128;
   static constexpr int n_chunks = (kOC1 + nc1 - 1) / nc1;
   static constexpr int n_acc0 = kOC <= 128 ? 2 : 1;
+  // Epilogue constants as immediate constant-bank operands need the column loops fully unrolled
+  // (per chunk and per column half); beyond two chunks that code no longer fits the instruction
+  // caches (measured: 35 % no_instruction stalls at 110 KB of SASS), so larger shapes read the
+  // constants from shared memory instead.
+  static constexpr bool imm_consts = n_chunks <= 2;
 };
 struct DynGeom {
   static constexpr bool is_static = false;
+  static constexpr bool imm_consts = false;
 };
 
 #define DF_GEO(name)                                  \
@@ -154,6 +165,29 @@ __device__ __forceinline__ void scale4(const uint32_t* acc, const float4 b, cons
   scale_pair(acc[0], acc[1], b.x, b.y, s.x, s.y, t[0], t[1]);
   scale_pair(acc[2], acc[3], b.z, b.w, s.z, s.w, t[2], t[3]);
 }
+// conv1 fast path.  acc1 = sum of u8 * s8 over OC <= 256 terms lies in [lo[q], lo[q] + 2^23) with
+// lo[q] = 255 * (sum of the negative weights of channel q), so with K[q] = 0x4B000000 - lo[q]
+//   __int_as_float(acc + K[q]) == 2^23 + (acc - lo[q])      exactly (ulp is 1 in [2^23, 2^24)),
+// and adding C[q] = bias[q] + lo[q] - 2^23 (exactly representable, checked at create time) rounds
+// the real number acc + bias ONCE -- bit-identical to vcvtdq2ps ; vaddps, because float(acc) is
+// exact below 2^24.  This moves the conversion off the quarter-rate I2F pipe (probe/epi_pipes.cu).
+__device__ __forceinline__ void scale4_fast(const uint32_t* acc, const int4 k, const float4 c, const float4 s, float* t) {
+  const float f0 = __int_as_float((int)acc[0] + k.x), f1 = __int_as_float((int)acc[1] + k.y);
+  const float f2 = __int_as_float((int)acc[2] + k.z), f3 = __int_as_float((int)acc[3] + k.w);
+  unsigned long long a, b, cc, dd, s0, s1;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(f0), "f"(f1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(f2), "f"(f3));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c.x), "f"(c.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(dd) : "f"(c.z), "f"(c.w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(s0) : "f"(s.x), "f"(s.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(s1) : "f"(s.z), "f"(s.w));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(a), "l"(cc));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(b) : "l"(b), "l"(dd));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(a), "l"(s0));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(b) : "l"(b), "l"(s1));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(t[0]), "=f"(t[1]) : "l"(a));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(t[2]), "=f"(t[3]) : "l"(b));
+}
 // vmaxps(zero, t): second source when NaN or both zero
 __device__ __forceinline__ float relu_x86(float t) { return (0.0f > t) ? 0.0f : t; }
 
@@ -168,9 +202,7 @@ __device__ __forceinline__ int cvt_x86(float t) {
 // [0,255] equals ReLU followed by unsigned saturation for every finite t; NaN (only reachable
 // through non-finite scales / biases) is patched to 255 when kNanSafe.
 template <bool kDown, bool kNanSafe>
-__device__ __forceinline__ uint32_t requant_u8x4(const uint32_t* acc, const float4 b, const float4 s) {
-  float t[4];
-  scale4(acc, b, s, t);
+__device__ __forceinline__ uint32_t pack_u8x4(const float* t) {
   int q[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -182,11 +214,15 @@ __device__ __forceinline__ uint32_t requant_u8x4(const uint32_t* acc, const floa
   asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(q[1]), "r"(q[0]), "r"(hi));
   return lo;
 }
-
-template <bool kDown>
-__device__ __forceinline__ uint32_t requant_s8x4(const uint32_t* acc, const float4 b, const float4 s, bool relu) {
+template <bool kDown, bool kNanSafe>
+__device__ __forceinline__ uint32_t requant_u8x4(const uint32_t* acc, const float4 b, const float4 s) {
   float t[4];
   scale4(acc, b, s, t);
+  return pack_u8x4<kDown, kNanSafe>(t);
+}
+
+template <bool kDown>
+__device__ __forceinline__ uint32_t pack_s8x4(float* t, bool relu) {
   int q[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -199,31 +235,25 @@ __device__ __forceinline__ uint32_t requant_s8x4(const uint32_t* acc, const floa
   return lo;
 }
 
-// 16 accumulator columns of one row -> destination (conv1 epilogue, jit_conv_kernel.cc:89-130)
-template <int kDst, bool kDown, bool kNanSafe>
-__device__ __forceinline__ void store16(const uint32_t* acc, const float* bias, const float* scale, bool relu,
-                                        uint8_t* out) {
+// 16 accumulator columns of one row -> destination (conv1 epilogue, jit_conv_kernel.cc:89-130).
+// kFast selects the offset-magic conversion (bias holds C[q], k the integer offsets K[q]).
+template <int kDst, bool kDown, bool kNanSafe, bool kFast>
+__device__ __forceinline__ void store16(const uint32_t* acc, const float* bias, const int* k, const float* scale,
+                                        bool relu, uint8_t* out) {
   const float4* b4 = reinterpret_cast<const float4*>(bias);
   const float4* s4 = reinterpret_cast<const float4*>(scale);
-  if (kDst == DF_U8) {
-    uint4 v;
-    v.x = requant_u8x4<kDown, kNanSafe>(acc + 0, b4[0], s4[0]);
-    v.y = requant_u8x4<kDown, kNanSafe>(acc + 4, b4[1], s4[1]);
-    v.z = requant_u8x4<kDown, kNanSafe>(acc + 8, b4[2], s4[2]);
-    v.w = requant_u8x4<kDown, kNanSafe>(acc + 12, b4[3], s4[3]);
-    *reinterpret_cast<uint4*>(out) = v;
-  } else if (kDst == DF_S8) {
-    uint4 v;
-    v.x = requant_s8x4<kDown>(acc + 0, b4[0], s4[0], relu);
-    v.y = requant_s8x4<kDown>(acc + 4, b4[1], s4[1], relu);
-    v.z = requant_s8x4<kDown>(acc + 8, b4[2], s4[2], relu);
-    v.w = requant_s8x4<kDown>(acc + 12, b4[3], s4[3], relu);
-    *reinterpret_cast<uint4*>(out) = v;
-  } else {
+  const int4* k4 = reinterpret_cast<const int4*>(k);
+  uint32_t packed[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float t[4];
-      scale4(acc + 4 * g, b4[g], s4[g], t);
+  for (int g = 0; g < 4; ++g) {
+    float t[4];
+    if (kFast) scale4_fast(acc + 4 * g, k4[g], b4[g], s4[g], t);
+    else scale4(acc + 4 * g, b4[g], s4[g], t);
+    if (kDst == DF_U8) {
+      packed[g] = pack_u8x4<kDown, kNanSafe>(t);
+    } else if (kDst == DF_S8) {
+      packed[g] = pack_s8x4<kDown>(t, relu);
+    } else {
       if (relu) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) t[i] = relu_x86(t[i]);
@@ -238,6 +268,92 @@ __device__ __forceinline__ void store16(const uint32_t* acc, const float* bias, 
       reinterpret_cast<uint4*>(out)[g] = v;
     }
   }
+  if (kDst == DF_U8 || kDst == DF_S8) *reinterpret_cast<uint4*>(out) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
+// Per-channel epilogue constants of the static geometries travel as a by-value kernel parameter, i.e.
+// they sit in the constant bank.  With compile-time column indices (the static epilogue is fully
+// unrolled) every FADD / FMUL / IADD takes its constant as an immediate c[0][off] operand and no load
+// instruction is issued at all.  Broadcast LDS of the same values tops out at ~1.8 constants/clk/SM
+// (probe/lds_bcast.cu, profiles/r01_lds_broadcast_vs_constbank.log), which capped the epilogue at
+// ~19 elements/clk/SM -- below what the tensor pipe produces.
+template <class G>
+struct EpiConsts {
+  float bias0[G::OC], scale0[G::OC];
+  int k1[G::n_chunks * G::nc1];
+  float c1[G::n_chunks * G::nc1], scale1[G::n_chunks * G::nc1];
+};
+struct EpiConstsNone {
+  int unused;
+};
+template <class G, bool kStatic = G::is_static>
+struct EpiConstsOf {
+  using type = EpiConstsNone;
+};
+template <class G>
+struct EpiConstsOf<G, true> {
+  using type = EpiConsts<G>;
+};
+
+template <int N, class F, int I = 0>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<N, F, I + 1>(static_cast<F&&>(f));
+  }
+}
+
+// conv0, static geometry: 16 columns starting at compile-time column kCol0 -> 16 bytes of u8
+template <class G>
+__device__ __forceinline__ uint4 requant16_static0(const uint32_t* acc, const EpiConsts<G>& ec, int kCol0) {
+  uint32_t w[4];
+#pragma unroll
+  for (int g4 = 0; g4 < 4; ++g4) {
+    float t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = kCol0 + g4 * 4 + i;
+      t[i] = __fmul_rn(__fadd_rn(__int2float_rn((int)acc[g4 * 4 + i]), ec.bias0[col]), ec.scale0[col]);
+    }
+    w[g4] = pack_u8x4<false, false>(t);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// conv1, static geometry, offset-magic conversion: 16 columns from compile-time column kCol0
+template <class G, int kDst>
+__device__ __forceinline__ void store16_static1(const uint32_t* acc, const EpiConsts<G>& ec, int kCol0, bool relu,
+                                                uint8_t* out) {
+  uint32_t packed[4];
+#pragma unroll
+  for (int g4 = 0; g4 < 4; ++g4) {
+    float t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = kCol0 + g4 * 4 + i;
+      const float f = __int_as_float((int)acc[g4 * 4 + i] + ec.k1[col]);   // == 2^23 + (acc - lo[col]) exactly
+      t[i] = __fmul_rn(__fadd_rn(f, ec.c1[col]), ec.scale1[col]);
+    }
+    if (kDst == DF_U8) {
+      packed[g4] = pack_u8x4<false, false>(t);
+    } else if (kDst == DF_S8) {
+      packed[g4] = pack_s8x4<false>(t, relu);
+    } else {
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = relu_x86(t[i]);
+      }
+      uint4 v;
+      if (kDst == DF_F32) {
+        v = make_uint4(__float_as_uint(t[0]), __float_as_uint(t[1]), __float_as_uint(t[2]), __float_as_uint(t[3]));
+      } else {
+        v = make_uint4((uint32_t)cvt_x86<false>(t[0]), (uint32_t)cvt_x86<false>(t[1]), (uint32_t)cvt_x86<false>(t[2]),
+                       (uint32_t)cvt_x86<false>(t[3]));
+      }
+      reinterpret_cast<uint4*>(out)[g4] = v;
+    }
+  }
+  if (kDst == DF_U8 || kDst == DF_S8) *reinterpret_cast<uint4*>(out) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
 
 template <int kCols>
@@ -250,7 +366,8 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
 template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
-                  const __grid_constant__ CUtensorMap tmW1, const Params p) {
+                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ Params p,
+                  const __grid_constant__ typename EpiConstsOf<G>::type ec) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // align in the shared address space (keeps LDS/STS instead of generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -258,7 +375,9 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t sbase = smem_u32(smem);
   const Geo<G> g{p};
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shfl from lane 0 tells ptxas the warp index is warp-uniform (values derived from it can then
+  // live in uniform registers, e.g. the column base of the epilogue's constant-bank loads)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n_local = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   // ---- one-time setup
@@ -286,7 +405,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmW1);
   }
   if (warp == 3) tmem_alloc<512>(smem_u32(&bar->tmem_base));
-  {
+  if constexpr (!G::imm_consts) {
     // per-channel f32 bias / scale vectors -> smem (read by every epilogue thread)
     float* sb0 = reinterpret_cast<float*>(smem + p.off_bias0);
     float* ss0 = reinterpret_cast<float*>(smem + p.off_scale0);
@@ -297,9 +416,11 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ss0[i] = p.scale0[i];
     }
     const int oc1_pad = g.n_chunks() * g.nc1();
+    int* sk1 = reinterpret_cast<int*>(smem + p.off_k1);
     for (int i = threadIdx.x; i < oc1_pad; i += kThreads) {
       sb1[i] = i < g.OC1() ? p.bias1[i] : 0.f;
       ss1[i] = i < g.OC1() ? p.scale1[i] : 0.f;
+      sk1[i] = i < g.OC1() ? p.k1[i] : 0;
     }
   }
   tc_fence_before_sync();
@@ -495,74 +616,83 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= kEpiWarp0) {
     // ====================================== epilogue =======================================
-    // Column groups of GC = 32 (or 16 when the channel counts are not multiples of 64); each of
-    // the two warps sharing a TMEM lane quarter takes every other group.
+    // Work units: E0(t) = conv0 epilogue of tile t (TMEM acc0 -> u8 tile in smem) and C_j(t) = conv1
+    // chunk j of tile t (TMEM acc1 -> global).  The kEpiGroups groups of 8 warps take alternate
+    // units of one common stream, so two units are in flight at any time; with epi_ahead the stream
+    // runs E0(t+1) before C_*(t) so that GEMM2(t) is never waiting for the epilogue it feeds.
+    // Inside a unit the two warps sharing a TMEM lane quarter take alternate column groups of
+    // GC = 32 (16 when the channel counts are not multiples of 64).
     constexpr bool kWide = G::is_static;  // static shapes have OC % 64 == 0 and nc1 % 64 == 0
     constexpr int GC = kWide ? 32 : 16;
-    const int quarter = warp & 3;              // TMEM lane quarter this warp may read
-    const int half = (warp - kEpiWarp0) >> 2;  // which half of the column groups
-    const int m = quarter * 32 + lane;         // tile row = TMEM lane
+    const int ew = warp - kEpiWarp0;
+    const int group = ew / kEpiWarps;
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may read
+    const int half = (ew % kEpiWarps) >> 2;     // which half of the column groups
+    const int m = quarter * 32 + lane;          // tile row = TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
     const float* sb0 = reinterpret_cast<const float*>(smem + p.off_bias0);
     const float* ss0 = reinterpret_cast<const float*>(smem + p.off_scale0);
     const float* sb1 = reinterpret_cast<const float*>(smem + p.off_bias1);
     const float* ss1 = reinterpret_cast<const float*>(smem + p.off_scale1);
+    const int* sk1 = reinterpret_cast<const int*>(smem + p.off_k1);
     constexpr int ts = (kDst == DF_F32 || kDst == DF_S32) ? 4 : 1;
     const uint32_t swz_mask1 = (uint32_t)(g.swb1() / 16 - 1);
     const bool relu1 = p.relu1 != 0;
-    uint32_t c1count = 0;
+    const bool fast1 = G::is_static ? true : (p.fast1 != 0);
     Tracer tr(p, 3);
     if (threadIdx.x != kEpiWarp0 * 32) tr.base = nullptr;
-    for (int it = 0; it < n_local; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      // where does this row go?
-      const int q = q_first + tile * kTileM + m;
-      const int gq = q / p.Wp, wq = q - gq * p.Wp;
-      const int n = (gq - 1) / p.Hp, hp = (gq - 1) - n * p.Hp;
-      const bool valid = (wq < p.W) && (hp >= 1) && (n < p.N);
-      uint8_t* out_row = static_cast<uint8_t*>(p.dst) + ((size_t)(n * p.H + hp - 1) * p.W + wq) * g.OC1() * ts;
 
-      // ---- conv0 epilogue: acc0 -> u8 intermediate in smem (K-major, swizzled)
+    // ---- conv0 epilogue of local tile `it`
+    auto unit_e0 = [&](int it) {
       const int ab = it % g.n_acc0(), mb = it % p.NM;
       mbar_wait_warp(smem_u32(&bar->mid_empty[mb]), ((it / p.NM) & 1) ^ 1);
       mbar_wait_warp(smem_u32(&bar->acc0_full[ab]), (it / g.n_acc0()) & 1);
       tc_fence_after_sync();
       tr.ev(30);
       uint8_t* mid = smem + p.off_mid + mb * p.mid_bytes;
-      {
-        // two statically indexed register buffers: the TMEM load of the next group is in flight
-        // while this one is converted (a runtime-indexed acc[buf][] would live in local memory)
-        const int ngr = g.OC() / GC;
-        const uint32_t t_base = lane_addr + ab * g.OC();
-        uint32_t acc_a[GC], acc_b[GC];
-        auto emit = [&](const uint32_t* acc, int gr) {
-#pragma unroll
-          for (int sub = 0; sub < GC / 16; ++sub) {
-            const int c16 = gr * (GC / 16) + sub;  // 16-column (= 16-byte) unit
-            const float4* b4 = reinterpret_cast<const float4*>(sb0 + c16 * 16);
-            const float4* s4 = reinterpret_cast<const float4*>(ss0 + c16 * 16);
-            uint4 v;
-            v.x = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 0, b4[0], s4[0]);
-            v.y = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 4, b4[1], s4[1]);
-            v.z = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 8, b4[2], s4[2]);
-            v.w = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 12, b4[3], s4[3]);
-            const int kb = (c16 * 16) / g.swb1();
-            uint32_t off = (uint32_t)m * g.swb1() + (uint32_t)(c16 * 16 - kb * g.swb1());
-            off ^= ((off >> 7) & swz_mask1) << 4;  // Swizzle<B,4,3> on the (1024 B aligned) block offset
-            *reinterpret_cast<uint4*>(mid + kb * g.mid_kb_stride() + off) = v;
-          }
-        };
-        if (half < ngr) tmem_ld_cols<GC>(t_base + half * GC, acc_a);
-#pragma unroll
-        for (int gr = half; gr < ngr; gr += 4) {
-          tmem_ld_wait();
-          if (gr + 2 < ngr) tmem_ld_cols<GC>(t_base + (gr + 2) * GC, acc_b);
-          emit(acc_a, gr);
-          if (gr + 2 < ngr) {
+      const int ngr = g.OC() / GC;
+      const uint32_t t_base = lane_addr + ab * g.OC();
+      if constexpr (G::imm_consts) {
+        // compile-time columns: the constants become uniform-register / immediate operands (EpiConsts)
+        auto body = [&](auto half_c) {
+          constexpr int kHalf = decltype(half_c)::value;
+          static_for<G::OC / 64>([&](auto i_c) {
+            constexpr int gr = decltype(i_c)::value * 2 + kHalf;
+            uint32_t acc[32];
+            tmem_ld_x32(t_base + gr * 32, acc);
             tmem_ld_wait();
-            if (gr + 4 < ngr) tmem_ld_cols<GC>(t_base + (gr + 4) * GC, acc_a);
-            emit(acc_b, gr + 2);
-          }
+            static_for<2>([&](auto sub_c) {
+              constexpr int c16 = gr * 2 + decltype(sub_c)::value;
+              const uint4 v = requant16_static0<G>(acc + decltype(sub_c)::value * 16, ec, c16 * 16);
+              constexpr int kb = (c16 * 16) / G::swb1;
+              uint32_t off = (uint32_t)m * G::swb1 + (uint32_t)(c16 * 16 - kb * G::swb1);
+              off ^= ((off >> 7) & (uint32_t)(G::swb1 / 16 - 1)) << 4;
+              *reinterpret_cast<uint4*>(mid + kb * (kTileM * G::swb1) + off) = v;
+            });
+          });
+        };
+        if (half == 0) body(std::integral_constant<int, 0>{});
+        else body(std::integral_constant<int, 1>{});
+      } else
+#pragma unroll
+      for (int gr = half; gr < ngr; gr += 2) {
+        uint32_t acc[GC];
+        tmem_ld_cols<GC>(t_base + gr * GC, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int sub = 0; sub < GC / 16; ++sub) {
+          const int c16 = gr * (GC / 16) + sub;  // 16-column (= 16-byte) unit
+          const float4* b4 = reinterpret_cast<const float4*>(sb0 + c16 * 16);
+          const float4* s4 = reinterpret_cast<const float4*>(ss0 + c16 * 16);
+          uint4 v;
+          v.x = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 0, b4[0], s4[0]);
+          v.y = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 4, b4[1], s4[1]);
+          v.z = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 8, b4[2], s4[2]);
+          v.w = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 12, b4[3], s4[3]);
+          const int kb = (c16 * 16) / g.swb1();
+          uint32_t off = (uint32_t)m * g.swb1() + (uint32_t)(c16 * 16 - kb * g.swb1());
+          off ^= ((off >> 7) & swz_mask1) << 4;  // Swizzle<B,4,3> on the (1024 B aligned) block offset
+          *reinterpret_cast<uint4*>(mid + kb * g.mid_kb_stride() + off) = v;
         }
       }
       tc_fence_before_sync();
@@ -573,44 +703,84 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_arrive(smem_u32(&bar->mid_full[mb]));
       }
       tr.ev(31);
+    };
 
-      // ---- conv1 epilogue: acc1 chunks -> global
-      for (int j = 0; j < g.n_chunks(); ++j, ++c1count) {
-        const int cb = c1count & 1;
-        mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c1count >> 1) & 1);
-        tc_fence_after_sync();
-        tr.ev(32);
-        int ncols = g.OC1() - j * g.nc1();  // real columns in this chunk
-        if (ncols > g.nc1()) ncols = g.nc1();
-        const int ngr = ncols / GC;
-        const uint32_t t_base = lane_addr + kAcc1Col + cb * kAcc1Stride;
-        uint32_t acc_a[GC], acc_b[GC];
-        auto emit = [&](const uint32_t* acc, int gr) {
-          if (valid) {
-#pragma unroll
-            for (int sub = 0; sub < GC / 16; ++sub) {
-              const int col = j * g.nc1() + gr * GC + sub * 16;
-              store16<kDst, kDown1, kNanSafe>(acc + sub * 16, sb1 + col, ss1 + col, relu1, out_row + (size_t)col * ts);
-            }
-          }
-        };
-        if (half < ngr) tmem_ld_cols<GC>(t_base + half * GC, acc_a);
-#pragma unroll
-        for (int gr = half; gr < ngr; gr += 4) {
-          tmem_ld_wait();
-          if (gr + 2 < ngr) tmem_ld_cols<GC>(t_base + (gr + 2) * GC, acc_b);
-          emit(acc_a, gr);
-          if (gr + 2 < ngr) {
+    // ---- conv1 chunk j of local tile `it` (c = global chunk counter of this CTA)
+    auto unit_c = [&](int it, int j, uint32_t c) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int q = q_first + tile * kTileM + m;  // where does this row go?
+      const int gq = q / p.Wp, wq = q - gq * p.Wp;
+      const int n = (gq - 1) / p.Hp, hp = (gq - 1) - n * p.Hp;
+      const bool valid = (wq < p.W) && (hp >= 1) && (n < p.N);
+      uint8_t* out_row = static_cast<uint8_t*>(p.dst) + ((size_t)(n * p.H + hp - 1) * p.W + wq) * g.OC1() * ts;
+      const int cb = c & 1;
+      mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c >> 1) & 1);
+      tc_fence_after_sync();
+      tr.ev(32);
+      int ncols = g.OC1() - j * g.nc1();  // real columns in this chunk
+      if (ncols > g.nc1()) ncols = g.nc1();
+      const int ngr = ncols / GC;
+      const uint32_t t_base = lane_addr + kAcc1Col + cb * kAcc1Stride;
+      if constexpr (G::imm_consts) {
+        // compile-time chunk and columns: the constants become uniform-register / immediate operands
+        auto body = [&](auto j_c, auto half_c) {
+          constexpr int kJ = decltype(j_c)::value, kHalf = decltype(half_c)::value;
+          static_for<G::nc1 / 64>([&](auto i_c) {
+            constexpr int gr = decltype(i_c)::value * 2 + kHalf;
+            uint32_t acc[32];
+            tmem_ld_x32(t_base + gr * 32, acc);
             tmem_ld_wait();
-            if (gr + 4 < ngr) tmem_ld_cols<GC>(t_base + (gr + 4) * GC, acc_a);
-            emit(acc_b, gr + 2);
+            if (valid) {
+              static_for<2>([&](auto sub_c) {
+                constexpr int col = kJ * G::nc1 + gr * 32 + decltype(sub_c)::value * 16;
+                store16_static1<G, kDst>(acc + decltype(sub_c)::value * 16, ec, col, relu1, out_row + (size_t)col * ts);
+              });
+            }
+          });
+        };
+        static_for<G::n_chunks>([&](auto j_c) {
+          if (j == decltype(j_c)::value) {
+            if (half == 0) body(j_c, std::integral_constant<int, 0>{});
+            else body(j_c, std::integral_constant<int, 1>{});
+          }
+        });
+      } else
+#pragma unroll
+      for (int gr = half; gr < ngr; gr += 2) {
+        uint32_t acc[GC];
+        tmem_ld_cols<GC>(t_base + gr * GC, acc);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int sub = 0; sub < GC / 16; ++sub) {
+            const int col = j * g.nc1() + gr * GC + sub * 16;
+            if (fast1)
+              store16<kDst, kDown1, kNanSafe, true>(acc + sub * 16, sb1 + col, sk1 + col, ss1 + col, relu1, out_row + (size_t)col * ts);
+            else
+              store16<kDst, kDown1, kNanSafe, false>(acc + sub * 16, sb1 + col, sk1 + col, ss1 + col, relu1, out_row + (size_t)col * ts);
           }
         }
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bar->acc1_empty[cb]));
-        tr.ev(33);
       }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar->acc1_empty[cb]));
+      tr.ev(33);
+    };
+
+    // ---- the unit stream, identical in every epilogue warp; group u % kEpiGroups executes unit u
+    uint32_t u = 0, c = 0;
+    const int ahead = p.epi_ahead;
+    if (ahead && n_local > 0) {
+      if ((u++ % kEpiGroups) == (uint32_t)group) unit_e0(0);
+    }
+    for (int it = 0; it < n_local; ++it) {
+      if (ahead) {
+        if (it + 1 < n_local && (u++ % kEpiGroups) == (uint32_t)group) unit_e0(it + 1);
+      } else {
+        if ((u++ % kEpiGroups) == (uint32_t)group) unit_e0(it);
+      }
+      for (int j = 0; j < g.n_chunks(); ++j, ++c)
+        if ((u++ % kEpiGroups) == (uint32_t)group) unit_c(it, j, c);
     }
   }
 
@@ -641,7 +811,30 @@ CUtensorMapSwizzle swizzle_enum(int swb) {
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 inline int pick_swb(int k) { return k > 64 ? 128 : (k > 32 ? 64 : 32); }
 
-typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Params);
+// type-erased launcher: the epilogue-constant parameter type depends on the geometry
+typedef cudaError_t (*LaunchFn)(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
+                                const CUtensorMap& w1, const Params& p, const void* epi_consts);
+typedef cudaError_t (*AttrFn)(uint32_t smem);
+
+template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
+cudaError_t launch_conv(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
+                        const CUtensorMap& w1, const Params& p, const void* epi_consts) {
+  using EC = typename EpiConstsOf<G>::type;
+  static const EC none{};
+  const EC& ec = G::is_static ? *static_cast<const EC*>(epi_consts) : none;
+  conv_fused_kernel<G, kDst, kDown0, kDown1, kNanSafe><<<grid, kThreads, smem, st>>>(a, w0, w1, p, ec);
+  return cudaGetLastError();
+}
+template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
+cudaError_t attr_conv(uint32_t smem) {
+  return cudaFuncSetAttribute((const void*)conv_fused_kernel<G, kDst, kDown0, kDown1, kNanSafe>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+struct KernelFn {
+  LaunchFn launch;
+  AttrFn attr;
+};
+#define DF_KERNEL(G, DT, D0, D1, NS) KernelFn{launch_conv<G, DT, D0, D1, NS>, attr_conv<G, DT, D0, D1, NS>}
 
 // Static geometries = the BASELINE.json conv shapes together with the shared-memory plan
 // df_conv_create derives for them (weights resident? how many weight stages).
@@ -652,12 +845,11 @@ using GeoCfg4 = StaticGeom<256, 256, 1024, 0, 0, 2>;   // 14x14 256->256->1024: 
 template <class G>
 KernelFn pick_static(int dst_dt) {
   switch (dst_dt) {
-    case DF_U8: return conv_fused_kernel<G, DF_U8, false, false, false>;
-    case DF_S8: return conv_fused_kernel<G, DF_S8, false, false, false>;
-    case DF_S32: return conv_fused_kernel<G, DF_S32, false, false, false>;
-    case DF_F32: return conv_fused_kernel<G, DF_F32, false, false, false>;
+    case DF_U8: return DF_KERNEL(G, DF_U8, false, false, false);
+    case DF_S8: return DF_KERNEL(G, DF_S8, false, false, false);
+    case DF_S32: return DF_KERNEL(G, DF_S32, false, false, false);
+    default: return DF_KERNEL(G, DF_F32, false, false, false);
   }
-  return nullptr;
 }
 
 // geom_id: 0 = run-time geometry, 1 / 3 / 4 = GeoCfg1 / GeoCfg3 / GeoCfg4
@@ -667,21 +859,39 @@ KernelFn pick_kernel(int geom_id, int dst_dt, bool down0, bool down1, bool nan_s
     if (geom_id == 3) return pick_static<GeoCfg3>(dst_dt);
     if (geom_id == 4) return pick_static<GeoCfg4>(dst_dt);
   }
-#define DF_PICK(DT)                                                                                                   \
-  if (dst_dt == DT) {                                                                                                 \
-    if (nan_safe) {                                                                                                   \
-      if (down0) return down1 ? conv_fused_kernel<DynGeom, DT, true, true, true> : conv_fused_kernel<DynGeom, DT, true, false, true>;   \
-      return down1 ? conv_fused_kernel<DynGeom, DT, false, true, true> : conv_fused_kernel<DynGeom, DT, false, false, true>;            \
-    }                                                                                                                 \
-    if (down0) return down1 ? conv_fused_kernel<DynGeom, DT, true, true, false> : conv_fused_kernel<DynGeom, DT, true, false, false>;   \
-    return down1 ? conv_fused_kernel<DynGeom, DT, false, true, false> : conv_fused_kernel<DynGeom, DT, false, false, false>;            \
+#define DF_PICK(DT)                                                                                     \
+  if (dst_dt == DT) {                                                                                   \
+    if (nan_safe) {                                                                                     \
+      if (down0) return down1 ? DF_KERNEL(DynGeom, DT, true, true, true) : DF_KERNEL(DynGeom, DT, true, false, true);   \
+      return down1 ? DF_KERNEL(DynGeom, DT, false, true, true) : DF_KERNEL(DynGeom, DT, false, false, true);            \
+    }                                                                                                   \
+    if (down0) return down1 ? DF_KERNEL(DynGeom, DT, true, true, false) : DF_KERNEL(DynGeom, DT, true, false, false);   \
+    return down1 ? DF_KERNEL(DynGeom, DT, false, true, false) : DF_KERNEL(DynGeom, DT, false, false, false);            \
   }
   DF_PICK(DF_U8)
   DF_PICK(DF_S8)
   DF_PICK(DF_S32)
   DF_PICK(DF_F32)
 #undef DF_PICK
-  return nullptr;
+  return KernelFn{nullptr, nullptr};
+}
+
+// host copy of the by-value epilogue constants of a static geometry
+template <class G>
+std::vector<char> make_epi_consts(const std::vector<float>& b0, const std::vector<float>& s0, const std::vector<int>& k1,
+                                  const std::vector<float>& c1, const std::vector<float>& s1) {
+  std::vector<char> raw(sizeof(EpiConsts<G>), 0);
+  EpiConsts<G>* ec = reinterpret_cast<EpiConsts<G>*>(raw.data());
+  for (int i = 0; i < G::OC; ++i) {
+    ec->bias0[i] = b0[i];
+    ec->scale0[i] = s0[i];
+  }
+  for (int i = 0; i < G::OC1; ++i) {
+    ec->k1[i] = k1[i];
+    ec->c1[i] = c1[i];
+    ec->scale1[i] = s1[i];
+  }
+  return raw;
 }
 
 template <class G>
@@ -694,14 +904,19 @@ bool geom_matches(const Params& p) {
 }  // namespace
 
 struct df_conv {
+  df_conv() : desc(), prm(), kernel{nullptr, nullptr}, geom_id(0), smem_bytes(0), device(0), sms(0), d_w0(nullptr),
+              d_w1(nullptr), d_bias0(nullptr), d_scale0(nullptr), d_bias1(nullptr), d_scale1(nullptr), d_k1(nullptr),
+              tmW0(), tmW1(), tmA(), tmA_src(nullptr), tmA_n(-1), trace(nullptr), trace_cap(0) {}
   df_conv_desc desc;
   Params prm;        // everything except n-dependent fields and dst
   KernelFn kernel;
+  std::vector<char> epi_consts;  // by-value kernel parameter of the static geometries
   int geom_id;
   uint32_t smem_bytes;
   int device, sms;
   int8_t *d_w0, *d_w1;
   float *d_bias0, *d_scale0, *d_bias1, *d_scale1;
+  int* d_k1;
   CUtensorMap tmW0, tmW1;
   // cached activation map (re-encoded when the source pointer or batch changes)
   CUtensorMap tmA;
@@ -799,7 +1014,6 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   if (d->iw > 254) return df::fail(DF_E_UNSUPPORTED, "B200 path supports width <= 254 (TMA box limit)");
 
   df_conv* op = new df_conv();
-  memset(op, 0, sizeof(*op));
   op->desc = *d;
   Params& p = op->prm;
   p.H = d->ih;
@@ -834,6 +1048,8 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   p.off_bias1 = off;
   off += align_up(oc1_pad * 4, 128);
   p.off_scale1 = off;
+  off += align_up(oc1_pad * 4, 128);
+  p.off_k1 = off;
   off += align_up(oc1_pad * 4, 128);
   off = align_up(off, 1024);
   p.mid_kb_stride = kTileM * p.swb1;
@@ -928,6 +1144,28 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   }
   p.nan_safe = !finite;
 
+  // conv1 offset-magic conversion (see scale4_fast): exact iff the accumulator range of every
+  // channel is narrower than 2^23 and C[q] = bias + lo - 2^23 is exactly representable.
+  std::vector<int> k1(p.OC1, 0);
+  std::vector<float> c1(p.OC1, 0.f);
+  bool fast1 = finite;
+  for (int q = 0; q < p.OC1 && fast1; ++q) {
+    long long neg = 0, pos = 0;
+    for (int o = 0; o < p.OC; ++o) {
+      const int w = wei1[blocked_off(q, o, 0, 0, p.OC, 1, 1)];
+      if (w < 0) neg += w; else pos += w;
+    }
+    const long long lo = 255 * neg, hi = 255 * pos;
+    if (hi - lo >= (1ll << 23)) { fast1 = false; break; }
+    const double c = (double)b1[q] + (double)lo - 8388608.0;
+    if ((double)(float)c != c) { fast1 = false; break; }
+    k1[q] = (int)(0x4B000000ll - lo);
+    c1[q] = (float)c;
+  }
+  if (getenv("DF_NO_FAST_CONV1")) fast1 = false;  // test hook: exercise the I2F path
+  p.fast1 = fast1;
+  p.epi_ahead = (p.NM == 2 && p.n_acc0 == 2) ? 1 : 0;
+
 #define DF_TRY(expr)                          \
   do {                                        \
     int rc_ = (expr);                         \
@@ -957,17 +1195,25 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   DF_TRY_CUDA(cudaMemcpy(op->d_w1, w1.data(), w1.size(), cudaMemcpyHostToDevice));
   DF_TRY_CUDA(cudaMemcpy(op->d_bias0, b0.data(), p.OC * 4, cudaMemcpyHostToDevice));
   DF_TRY_CUDA(cudaMemcpy(op->d_scale0, s0.data(), p.OC * 4, cudaMemcpyHostToDevice));
-  DF_TRY_CUDA(cudaMemcpy(op->d_bias1, b1.data(), p.OC1 * 4, cudaMemcpyHostToDevice));
+  DF_TRY_CUDA(cudaMalloc(&op->d_k1, p.OC1 * 4));
+  DF_TRY_CUDA(cudaMemcpy(op->d_k1, k1.data(), p.OC1 * 4, cudaMemcpyHostToDevice));
+  DF_TRY_CUDA(cudaMemcpy(op->d_bias1, fast1 ? c1.data() : b1.data(), p.OC1 * 4, cudaMemcpyHostToDevice));
   DF_TRY_CUDA(cudaMemcpy(op->d_scale1, s1.data(), p.OC1 * 4, cudaMemcpyHostToDevice));
   p.bias0 = op->d_bias0;
   p.scale0 = op->d_scale0;
   p.bias1 = op->d_bias1;
   p.scale1 = op->d_scale1;
+  p.k1 = op->d_k1;
   DF_TRY(encode_2d(&op->tmW0, op->d_w0, p.swb, (long)9 * p.nkb * p.OC, p.OC));
   DF_TRY(encode_2d(&op->tmW1, op->d_w1, p.swb1, (long)p.n_chunks * p.nkb1 * p.nc1, p.nc1));
 
+  if (!p.fast1) op->geom_id = 0;  // the static kernels are built for the fast conv1 conversion only
+  if (d->round0 == DF_ROUND_DOWN || d->round1 == DF_ROUND_DOWN || p.nan_safe) op->geom_id = 0;
   op->kernel = pick_kernel(op->geom_id, d->dst_dt, d->round0 == DF_ROUND_DOWN, d->round1 == DF_ROUND_DOWN, p.nan_safe != 0);
-  DF_TRY_CUDA(cudaFuncSetAttribute((const void*)op->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)op->smem_bytes));
+  if (op->geom_id == 1) op->epi_consts = make_epi_consts<GeoCfg1>(b0, s0, k1, c1, s1);
+  if (op->geom_id == 3) op->epi_consts = make_epi_consts<GeoCfg3>(b0, s0, k1, c1, s1);
+  if (op->geom_id == 4) op->epi_consts = make_epi_consts<GeoCfg4>(b0, s0, k1, c1, s1);
+  DF_TRY_CUDA(op->kernel.attr(op->smem_bytes));
   *out = op;
   return 0;
 }
@@ -1007,8 +1253,8 @@ extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, vo
   p.trace_cap = op->trace_cap;
   const int grid = p.n_tiles < op->sms ? p.n_tiles : op->sms;
   p.tile_step_mod = (kTileM * grid) % p.Wp;
-  op->kernel<<<grid, kThreads, op->smem_bytes, (cudaStream_t)stream>>>(op->tmA, op->tmW0, op->tmW1, p);
-  DF_CUDA(cudaGetLastError());
+  DF_CUDA(op->kernel.launch(grid, op->smem_bytes, (cudaStream_t)stream, op->tmA, op->tmW0, op->tmW1, p,
+                            op->epi_consts.empty() ? nullptr : op->epi_consts.data()));
   return 0;
 }
 
@@ -1047,6 +1293,7 @@ extern "C" int df_conv_destroy(df_conv* op) {
   cudaFree(op->d_scale0);
   cudaFree(op->d_bias1);
   cudaFree(op->d_scale1);
+  cudaFree(op->d_k1);
   delete op;
   return 0;
 }
