@@ -49,6 +49,43 @@ __device__ __forceinline__ uint32_t relu_word(uint32_t x) {
   return x;
 }
 
+// Fast path: the total thread count is a multiple of the vectors per pixel, so a thread keeps ONE
+// channel position (input, offset) for the whole launch and only strides over pixels -- no division
+// or input search in the loop, kUnroll independent 128-bit loads in flight.
+template <int kMode>
+__global__ void __launch_bounds__(kThreads) concat_kernel_strided(const ConcatParams p, uint4* __restrict__ dst,
+                                                                  uint32_t n_pixels) {
+  const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;
+  const uint32_t off = tid % p.group_vecs;
+  uint32_t pixel = tid / p.group_vecs;
+  const uint32_t pstride = (gridDim.x * kThreads) / p.group_vecs;
+  uint32_t i = 0;
+  while (i + 1 < p.n_inputs && off >= p.vec_begin[i + 1]) ++i;
+  const uint32_t width = p.vec_begin[i + 1] - p.vec_begin[i];
+  const uint4* src = p.src[i] + (off - p.vec_begin[i]);
+  uint4* out = dst + p.dst_off + off;
+  for (; pixel < n_pixels; pixel += pstride * kUnroll) {
+    uint4 val[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t px = pixel + u * pstride;
+      if (px < n_pixels) val[u] = ld_stream(src + (size_t)px * width);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t px = pixel + u * pstride;
+      if (px < n_pixels) {
+        uint4 x = val[u];
+        x.x = relu_word<kMode>(x.x);
+        x.y = relu_word<kMode>(x.y);
+        x.z = relu_word<kMode>(x.z);
+        x.w = relu_word<kMode>(x.w);
+        out[(size_t)px * p.dst_pitch] = x;
+      }
+    }
+  }
+}
+
 template <int kMode>
 __global__ void __launch_bounds__(kThreads) concat_kernel(const ConcatParams p, uint4* __restrict__ dst) {
   const uint32_t stride = gridDim.x * kThreads;
@@ -112,8 +149,8 @@ extern "C" int df_concat_run(int dtype, int relu, int n_inputs, const void* cons
   if ((reinterpret_cast<uintptr_t>(dst_dev) & 15))
     return df::fail(DF_E_INVALID, "concat: dst not 16-byte aligned");
   const int mode = !relu ? kCopy : (dtype == DF_F32 ? kReluF32 : (dtype == DF_S32 ? kReluHalves : kReluBytes));
-  int sms = 148;
-  df_device_sm_count(&sms);
+  static thread_local int sms = 0;  // queried once per thread: keeps the per-launch host cost low
+  if (sms <= 0 && df_device_sm_count(&sms) != 0) sms = 148;
   uint32_t done_vecs = 0;
   for (int g0 = 0; g0 < n_inputs; g0 += kMaxInputs) {
     ConcatParams p;
@@ -135,6 +172,23 @@ extern "C" int df_concat_run(int dtype, int relu, int n_inputs, const void* cons
     const unsigned cap = (unsigned)sms * 8;  // a multiple of the SM count, 8 resident CTAs each
     if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
+    // strided fast path when a block-count with (blocks * 256) % vectors-per-pixel == 0 exists nearby
+    uint32_t g = p.group_vecs, a = kThreads;
+    while (a) { uint32_t t = g % a; g = a; a = t; }             // g = gcd(group_vecs, 256)
+    const uint32_t block_multiple = p.group_vecs / g;            // blocks must be a multiple of this
+    if (block_multiple <= 64 && (uint32_t)n_pixels >= 64) {
+      unsigned want = (p.total + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+      if (want > cap) want = cap;
+      unsigned sblocks = (want + block_multiple - 1) / block_multiple * block_multiple;
+      switch (mode) {
+        case kCopy: concat_kernel_strided<kCopy><<<sblocks, kThreads, 0, st>>>(p, (uint4*)dst_dev, (uint32_t)n_pixels); break;
+        case kReluBytes: concat_kernel_strided<kReluBytes><<<sblocks, kThreads, 0, st>>>(p, (uint4*)dst_dev, (uint32_t)n_pixels); break;
+        case kReluHalves: concat_kernel_strided<kReluHalves><<<sblocks, kThreads, 0, st>>>(p, (uint4*)dst_dev, (uint32_t)n_pixels); break;
+        default: concat_kernel_strided<kReluF32><<<sblocks, kThreads, 0, st>>>(p, (uint4*)dst_dev, (uint32_t)n_pixels); break;
+      }
+      DF_CUDA(cudaGetLastError());
+      continue;
+    }
     switch (mode) {
       case kCopy: concat_kernel<kCopy><<<blocks, kThreads, 0, st>>>(p, (uint4*)dst_dev); break;
       case kReluBytes: concat_kernel<kReluBytes><<<blocks, kThreads, 0, st>>>(p, (uint4*)dst_dev); break;

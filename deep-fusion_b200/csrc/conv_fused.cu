@@ -60,6 +60,7 @@ struct Params {
   int tile_step_mod;               // (128 * gridDim.x) mod Wp: halo-window offset step per tile
   uint32_t off_bias0, off_scale0, off_bias1, off_scale1, off_k1;
   int fast1;      // conv1 int->float by exact offset-magic conversion (k1 / bias1 hold K[q] / C[q])
+  int k1_uniform; // non-zero: one K serves every channel (global lower bound keeps the range < 2^23)
   int epi_ahead;  // epilogue does conv0 of tile i+1 before the conv1 chunks of tile i
   uint32_t off_a, a_stage_bytes, a_kb_stride;
   uint32_t off_mid, mid_bytes, mid_kb_stride;
@@ -188,6 +189,7 @@ __device__ __forceinline__ void scale4_fast(const uint32_t* acc, const int4 k, c
   asm("mov.b64 {%0, %1}, %2;" : "=f"(t[0]), "=f"(t[1]) : "l"(a));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(t[2]), "=f"(t[3]) : "l"(b));
 }
+__device__ __forceinline__ float4 load_scale4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 // vmaxps(zero, t): second source when NaN or both zero
 __device__ __forceinline__ float relu_x86(float t) { return (0.0f > t) ? 0.0f : t; }
 
@@ -236,19 +238,22 @@ __device__ __forceinline__ uint32_t pack_s8x4(float* t, bool relu) {
 }
 
 // 16 accumulator columns of one row -> destination (conv1 epilogue, jit_conv_kernel.cc:89-130).
-// kFast selects the offset-magic conversion (bias holds C[q], k the integer offsets K[q]).
-template <int kDst, bool kDown, bool kNanSafe, bool kFast>
-__device__ __forceinline__ void store16(const uint32_t* acc, const float* bias, const int* k, const float* scale,
+// kFast selects the offset-magic conversion (bias holds C[q]; K comes per channel from `k` or as the
+// one uniform `k_uni`).  `scale` is fetched through `ScaleFn` so that it can come from the constant
+// bank while bias/C come from shared memory: the two paths have separate return bandwidth
+// (profiles/r01_lds_broadcast_vs_constbank.log).
+template <int kDst, bool kDown, bool kNanSafe, bool kFast, class ScaleFn>
+__device__ __forceinline__ void store16(const uint32_t* acc, const float* bias, const int* k, int k_uni, ScaleFn scale4_of,
                                         bool relu, uint8_t* out) {
   const float4* b4 = reinterpret_cast<const float4*>(bias);
-  const float4* s4 = reinterpret_cast<const float4*>(scale);
   const int4* k4 = reinterpret_cast<const int4*>(k);
   uint32_t packed[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float t[4];
-    if (kFast) scale4_fast(acc + 4 * g, k4[g], b4[g], s4[g], t);
-    else scale4(acc + 4 * g, b4[g], s4[g], t);
+    const float4 s4 = scale4_of(g);
+    if (kFast) scale4_fast(acc + 4 * g, k_uni ? make_int4(k_uni, k_uni, k_uni, k_uni) : k4[g], b4[g], s4, t);
+    else scale4(acc + 4 * g, b4[g], s4, t);
     if (kDst == DF_U8) {
       packed[g] = pack_u8x4<kDown, kNanSafe>(t);
     } else if (kDst == DF_S8) {
@@ -331,7 +336,7 @@ __device__ __forceinline__ void store16_static1(const uint32_t* acc, const EpiCo
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int col = kCol0 + g4 * 4 + i;
-      const float f = __int_as_float((int)acc[g4 * 4 + i] + ec.k1[col]);   // == 2^23 + (acc - lo[col]) exactly
+      const float f = __int_as_float((int)acc[g4 * 4 + i] + ec.k1[col]);  // == 2^23 + (acc - lo[col]) exactly
       t[i] = __fmul_rn(__fadd_rn(f, ec.c1[col]), ec.scale1[col]);
     }
     if (kDst == DF_U8) {
@@ -523,94 +528,164 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t sa = 0, a_par = 0;
       Tracer tr(p, 1);
       tr.ev(9);
-      for (int it = 0; it <= n_local; ++it) {
-        if (it < n_local) {
-          // ---- GEMM1(it): acc0 = sum over 9 taps, K-blocks of halo(tile) x W0
-          const int ab = it % g.n_acc0();
-          mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / g.n_acc0()) & 1) ^ 1);
-          mbar_wait(smem_u32(&bar->a_full[sa]), a_par);
-          tc_fence_after_sync();
-          tr.ev(10);
-          const uint32_t d_tmem = tmem + ab * g.OC();
-          const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swb()) >> 4);
+
+      // ---- one tap row (kh) of GEMM1: 3 taps x K-blocks, descriptors by addition, weights in order
+      auto gemm1_row = [&](int kh, uint32_t d_tmem, uint64_t a_tile) {
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
+        for (int kw = 0; kw < 3; ++kw) {
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
+          for (int kb = 0; kb < g.nkb(); ++kb) {
+            const int blk_in_row = kw * g.nkb() + kb;      // compile-time inside the row
+            const int blk = kh * 3 * g.nkb() + blk_in_row;  // block index inside the tile
+            uint64_t b_desc;
+            uint32_t st = 0;
+            if (g.w0_res()) {
+              b_desc = w0_desc + blk * w0_step;
+            } else {
+              st = bs;
+              mbar_wait(smem_u32(&bar->b_full[st]), bph);
+              tc_fence_after_sync();
+              b_desc = bst0_desc + st * b_stage_step;
+            }
+            const uint64_t a_desc = a_tile + kh * a_step_kh + kw * a_step_kw + kb * a_step_kb;
+            const int nks = (kb == g.nkb() - 1) ? g.ks_last() : nks_full;
 #pragma unroll
-              for (int kb = 0; kb < g.nkb(); ++kb) {
-                const int blk = (kh * 3 + kw) * g.nkb() + kb;
-                uint64_t b_desc;
-                uint32_t st = 0;
-                if (g.w0_res()) {
-                  b_desc = w0_desc + blk * w0_step;
-                } else {
-                  st = G::is_static ? (uint32_t)(blk % g.SB()) : bs;
-                  const uint32_t par = G::is_static ? (bph ^ ((blk / g.SB()) & 1)) : bph;
-                  mbar_wait(smem_u32(&bar->b_full[st]), par);
-                  tc_fence_after_sync();
-                  b_desc = bst0_desc + st * b_stage_step;
-                }
-                const uint64_t a_desc = a_tile + kh * a_step_kh + kw * a_step_kw + kb * a_step_kb;
-                const int nks = (kb == g.nkb() - 1) ? g.ks_last() : nks_full;
-#pragma unroll
-                for (int ks = 0; ks < nks; ++ks) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
-                if (!g.w0_res()) {
-                  umma_commit(smem_u32(&bar->b_empty[st]));
-                  if (!G::is_static && ++bs == (uint32_t)g.SB()) { bs = 0; bph ^= 1; }
-                }
-              }
+            for (int ks = 0; ks < nks; ++ks) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+            if (!g.w0_res()) {
+              umma_commit(smem_u32(&bar->b_empty[st]));
+              if (++bs == (uint32_t)g.SB()) { bs = 0; bph ^= 1; }
             }
           }
-          if (G::is_static && !g.w0_res()) bph ^= ((9 * g.nkb() / g.SB()) & 1);
-          umma_commit(smem_u32(&bar->a_empty[sa]));
-          umma_commit(smem_u32(&bar->acc0_full[ab]));
-          tr.ev(11);
-          if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
-          a_off_px += p.tile_step_mod;
-          if (a_off_px >= p.Wp) a_off_px -= p.Wp;
         }
-        if (it >= 1) {
-          // ---- GEMM2(it-1): acc1[chunk] = mid x W1[chunk]
-          const int jt = it - 1, mb = jt % p.NM;
-          mbar_wait(smem_u32(&bar->mid_full[mb]), (jt / p.NM) & 1);
-          tc_fence_after_sync();
-          tr.ev(12);
-          const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid + mb * p.mid_bytes) >> 4);
+      };
+      // ---- one N-chunk of GEMM2 with W1 either resident or from the ring
+      auto gemm2_chunk = [&](int j, uint32_t d_tmem, uint64_t mid_desc) {
 #pragma unroll
-          for (int j = 0; j < g.n_chunks(); ++j, ++c1count) {
-            const int cb = c1count & 1;
-            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ 1);
+        for (int kb = 0; kb < g.nkb1(); ++kb) {
+          const int blk = j * g.nkb1() + kb;
+          uint64_t b_desc;
+          uint32_t st = 0;
+          if (g.w1_res()) {
+            b_desc = w1_desc + blk * w1_step;
+          } else {
+            st = bs;
+            mbar_wait(smem_u32(&bar->b_full[st]), bph);
             tc_fence_after_sync();
-            const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
+            b_desc = bst1_desc + st * b_stage_step;
+          }
+          const uint64_t a_desc = mid_desc + kb * mid_step_kb;
+          const int nks = (kb == g.nkb1() - 1) ? g.ks1_last() : nks1_full;
 #pragma unroll
-            for (int kb = 0; kb < g.nkb1(); ++kb) {
-              const int blk = j * g.nkb1() + kb;
-              uint64_t b_desc;
-              uint32_t st = 0;
-              if (g.w1_res()) {
-                b_desc = w1_desc + blk * w1_step;
-              } else {
-                st = G::is_static ? (uint32_t)(blk % g.SB()) : bs;
-                const uint32_t par = G::is_static ? (bph ^ ((blk / g.SB()) & 1)) : bph;
-                mbar_wait(smem_u32(&bar->b_full[st]), par);
+          for (int ks = 0; ks < nks; ++ks) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, (kb | ks) != 0);
+          if (!g.w1_res()) {
+            umma_commit(smem_u32(&bar->b_empty[st]));
+            if (++bs == (uint32_t)g.SB()) { bs = 0; bph ^= 1; }
+          }
+        }
+      };
+
+      if (g.w1_res()) {
+        // Readiness-driven issue.  With W1 resident only GEMM1 consumes the weight ring, so the two
+        // GEMM streams are independent: issue a GEMM2 chunk whenever its accumulator is free and the
+        // intermediate tile is there (it unblocks the epilogue, the longer path), otherwise the next
+        // tap row of the next GEMM1.  A fixed order suffers head-of-line blocking in both directions
+        // (profiles/r01_trace_cfg3_v4.log).
+        int g1_it = 0, g1_kh = 0, g2_it = 0, g2_j = 0;
+        bool g2_open = false;
+        uint64_t a_tile = 0;
+        uint32_t d0 = 0;
+        while (g2_it < n_local) {
+          bool did = false;
+          if (g2_it < g1_it) {  // GEMM1(g2_it) has been issued completely
+            const int mb = g2_it % p.NM;
+            if (!g2_open && mbar_test_wait(smem_u32(&bar->mid_full[mb]), (g2_it / p.NM) & 1)) {
+              g2_open = true;
+              tr.ev(12);
+            }
+            if (g2_open) {
+              const int cb = c1count & 1;
+              if (mbar_test_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ 1)) {
                 tc_fence_after_sync();
-                b_desc = bst1_desc + st * b_stage_step;
-              }
-              const uint64_t a_desc = mid_desc + kb * mid_step_kb;
-              const int nks = (kb == g.nkb1() - 1) ? g.ks1_last() : nks1_full;
-#pragma unroll
-              for (int ks = 0; ks < nks; ++ks) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, (kb | ks) != 0);
-              if (!g.w1_res()) {
-                umma_commit(smem_u32(&bar->b_empty[st]));
-                if (!G::is_static && ++bs == (uint32_t)g.SB()) { bs = 0; bph ^= 1; }
+                const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid + mb * p.mid_bytes) >> 4);
+                gemm2_chunk(g2_j, tmem + kAcc1Col + cb * kAcc1Stride, mid_desc);
+                umma_commit(smem_u32(&bar->acc1_full[cb]));
+                tr.ev(13);
+                ++c1count;
+                did = true;
+                if (++g2_j == g.n_chunks()) {
+                  umma_commit(smem_u32(&bar->mid_empty[mb]));
+                  g2_j = 0;
+                  g2_open = false;
+                  ++g2_it;
+                }
               }
             }
-            umma_commit(smem_u32(&bar->acc1_full[cb]));
-            tr.ev(13);
           }
-          if (G::is_static && !g.w1_res()) bph ^= ((g.n_chunks() * g.nkb1() / g.SB()) & 1);
-          umma_commit(smem_u32(&bar->mid_empty[mb]));
+          if (!did && g1_it < n_local) {
+            bool ok = true;
+            if (g1_kh == 0) {
+              const int ab = g1_it % g.n_acc0();
+              ok = mbar_test_wait(smem_u32(&bar->acc0_empty[ab]), ((g1_it / g.n_acc0()) & 1) ^ 1) &&
+                   mbar_test_wait(smem_u32(&bar->a_full[sa]), a_par);
+              if (ok) {
+                tc_fence_after_sync();
+                tr.ev(10);
+                d0 = tmem + ab * g.OC();
+                a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swb()) >> 4);
+              }
+            }
+            if (ok) {
+              gemm1_row(g1_kh, d0, a_tile);
+              did = true;
+              if (++g1_kh == 3) {
+                umma_commit(smem_u32(&bar->a_empty[sa]));
+                umma_commit(smem_u32(&bar->acc0_full[g1_it % g.n_acc0()]));
+                tr.ev(11);
+                g1_kh = 0;
+                ++g1_it;
+                if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
+                a_off_px += p.tile_step_mod;
+                if (a_off_px >= p.Wp) a_off_px -= p.Wp;
+              }
+            }
+          }
+        }
+      } else {
+        // W0 and W1 share one ring: the order is fixed -- GEMM1(it) then GEMM2(it-1)
+        for (int it = 0; it <= n_local; ++it) {
+          if (it < n_local) {
+            const int ab = it % g.n_acc0();
+            mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / g.n_acc0()) & 1) ^ 1);
+            mbar_wait(smem_u32(&bar->a_full[sa]), a_par);
+            tc_fence_after_sync();
+            tr.ev(10);
+            const uint32_t d_tmem = tmem + ab * g.OC();
+            const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swb()) >> 4);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) gemm1_row(kh, d_tmem, a_tile);
+            umma_commit(smem_u32(&bar->a_empty[sa]));
+            umma_commit(smem_u32(&bar->acc0_full[ab]));
+            tr.ev(11);
+            if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
+            a_off_px += p.tile_step_mod;
+            if (a_off_px >= p.Wp) a_off_px -= p.Wp;
+          }
+          if (it >= 1) {
+            const int jt = it - 1, mb = jt % p.NM;
+            mbar_wait(smem_u32(&bar->mid_full[mb]), (jt / p.NM) & 1);
+            tc_fence_after_sync();
+            tr.ev(12);
+            const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid + mb * p.mid_bytes) >> 4);
+            for (int j = 0; j < g.n_chunks(); ++j, ++c1count) {
+              const int cb = c1count & 1;
+              mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ 1);
+              tc_fence_after_sync();
+              gemm2_chunk(j, tmem + kAcc1Col + cb * kAcc1Stride, mid_desc);
+              umma_commit(smem_u32(&bar->acc1_full[cb]));
+              tr.ev(13);
+            }
+            umma_commit(smem_u32(&bar->mid_empty[mb]));
+          }
         }
       }
     }
@@ -683,12 +758,19 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int sub = 0; sub < GC / 16; ++sub) {
           const int c16 = gr * (GC / 16) + sub;  // 16-column (= 16-byte) unit
           const float4* b4 = reinterpret_cast<const float4*>(sb0 + c16 * 16);
-          const float4* s4 = reinterpret_cast<const float4*>(ss0 + c16 * 16);
+          auto s4 = [&](int i) -> float4 {
+            if constexpr (G::is_static) {  // scales through the constant bank, biases through smem
+              const int c0 = c16 * 16 + i * 4;
+              return make_float4(ec.scale0[c0], ec.scale0[c0 + 1], ec.scale0[c0 + 2], ec.scale0[c0 + 3]);
+            } else {
+              return load_scale4(ss0 + c16 * 16 + i * 4);
+            }
+          };
           uint4 v;
-          v.x = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 0, b4[0], s4[0]);
-          v.y = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 4, b4[1], s4[1]);
-          v.z = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 8, b4[2], s4[2]);
-          v.w = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 12, b4[3], s4[3]);
+          v.x = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 0, b4[0], s4(0));
+          v.y = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 4, b4[1], s4(1));
+          v.z = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 8, b4[2], s4(2));
+          v.w = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 12, b4[3], s4(3));
           const int kb = (c16 * 16) / g.swb1();
           uint32_t off = (uint32_t)m * g.swb1() + (uint32_t)(c16 * 16 - kb * g.swb1());
           off ^= ((off >> 7) & swz_mask1) << 4;  // Swizzle<B,4,3> on the (1024 B aligned) block offset
@@ -754,10 +836,18 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int sub = 0; sub < GC / 16; ++sub) {
             const int col = j * g.nc1() + gr * GC + sub * 16;
+            auto s4 = [&](int i) -> float4 {
+              if constexpr (G::is_static) {
+                const int c0 = col + i * 4;
+                return make_float4(ec.scale1[c0], ec.scale1[c0 + 1], ec.scale1[c0 + 2], ec.scale1[c0 + 3]);
+              } else {
+                return load_scale4(ss1 + col + i * 4);
+              }
+            };
             if (fast1)
-              store16<kDst, kDown1, kNanSafe, true>(acc + sub * 16, sb1 + col, sk1 + col, ss1 + col, relu1, out_row + (size_t)col * ts);
+              store16<kDst, kDown1, kNanSafe, true>(acc + sub * 16, sb1 + col, sk1 + col, p.k1_uniform, s4, relu1, out_row + (size_t)col * ts);
             else
-              store16<kDst, kDown1, kNanSafe, false>(acc + sub * 16, sb1 + col, sk1 + col, ss1 + col, relu1, out_row + (size_t)col * ts);
+              store16<kDst, kDown1, kNanSafe, false>(acc + sub * 16, sb1 + col, sk1 + col, 0, s4, relu1, out_row + (size_t)col * ts);
           }
         }
       }
@@ -1149,20 +1239,39 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   std::vector<int> k1(p.OC1, 0);
   std::vector<float> c1(p.OC1, 0.f);
   bool fast1 = finite;
-  for (int q = 0; q < p.OC1 && fast1; ++q) {
-    long long neg = 0, pos = 0;
-    for (int o = 0; o < p.OC; ++o) {
-      const int w = wei1[blocked_off(q, o, 0, 0, p.OC, 1, 1)];
-      if (w < 0) neg += w; else pos += w;
+  {
+    std::vector<long long> lo(p.OC1), hi(p.OC1);
+    long long lo_min = 0, hi_max = 0;
+    for (int q = 0; q < p.OC1; ++q) {
+      long long neg = 0, pos = 0;
+      for (int o = 0; o < p.OC; ++o) {
+        const int w = wei1[blocked_off(q, o, 0, 0, p.OC, 1, 1)];
+        if (w < 0) neg += w; else pos += w;
+      }
+      lo[q] = 255 * neg;
+      hi[q] = 255 * pos;
+      lo_min = lo[q] < lo_min ? lo[q] : lo_min;
+      hi_max = hi[q] > hi_max ? hi[q] : hi_max;
     }
-    const long long lo = 255 * neg, hi = 255 * pos;
-    if (hi - lo >= (1ll << 23)) { fast1 = false; break; }
-    const double c = (double)b1[q] + (double)lo - 8388608.0;
-    if ((double)(float)c != c) { fast1 = false; break; }
-    k1[q] = (int)(0x4B000000ll - lo);
-    c1[q] = (float)c;
+    // one K for every channel when a single lower bound keeps all ranges inside [0, 2^23)
+    bool uniform = hi_max - lo_min < (1ll << 23);
+    for (int pass = 0; pass < 2; ++pass) {
+      bool ok = finite;
+      for (int q = 0; q < p.OC1 && ok; ++q) {
+        const long long base = uniform ? lo_min : lo[q];
+        if (hi[q] - base >= (1ll << 23)) { ok = false; break; }
+        const double c = (double)b1[q] + (double)base - 8388608.0;
+        if ((double)(float)c != c) { ok = false; break; }
+        k1[q] = (int)(0x4B000000ll - base);
+        c1[q] = (float)c;
+      }
+      if (ok || !uniform) { fast1 = ok; break; }
+      uniform = false;  // retry with per-channel offsets
+    }
+    p.k1_uniform = (fast1 && uniform) ? k1[0] : 0;
   }
   if (getenv("DF_NO_FAST_CONV1")) fast1 = false;  // test hook: exercise the I2F path
+  if (!fast1) p.k1_uniform = 0;
   p.fast1 = fast1;
   p.epi_ahead = (p.NM == 2 && p.n_acc0 == 2) ? 1 : 0;
 

@@ -239,6 +239,21 @@ class Conv:
             pass
 
 
+class ConcatCall:
+    """A prepared df_concat_run call (argument marshalling done once; used by benchmarks)."""
+
+    def __init__(self, dtype, relu, src_ptrs, ics, dst_ptr, n_pixels, stream=None):
+        n = len(src_ptrs)
+        self._args = (dtype, int(relu), n, (C.c_void_p * n)(*src_ptrs), (C.c_int * n)(*ics), C.c_void_p(dst_ptr),
+                      C.c_long(n_pixels), stream)
+        self._fn = lib().df_concat_run
+
+    def __call__(self):
+        rc = self._fn(*self._args)
+        if rc:
+            check(rc)
+
+
 def concat_run(dtype, relu, src_ptrs, ics, dst_ptr, n_pixels, stream=None):
     n = len(src_ptrs)
     ptrs = (C.c_void_p * n)(*src_ptrs)
