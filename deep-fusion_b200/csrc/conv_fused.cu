@@ -594,8 +594,13 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         bool g2_open = false;
         uint64_t a_tile = 0;
         uint32_t d0 = 0;
+        uint32_t idle = 0;
         while (g2_it < n_local) {
           bool did = false;
+          if (++idle > (1u << 27)) {
+            printf("conv MMA scheduler stuck: block %d g1 %d/%d g2 %d/%d\n", blockIdx.x, g1_it, g1_kh, g2_it, g2_j);
+            __trap();
+          }
           if (g2_it < g1_it) {  // GEMM1(g2_it) has been issued completely
             const int mb = g2_it % p.NM;
             if (!g2_open && mbar_test_wait(smem_u32(&bar->mid_full[mb]), (g2_it / p.NM) & 1)) {
@@ -612,6 +617,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tr.ev(13);
                 ++c1count;
                 did = true;
+                idle = 0;
                 if (++g2_j == g.n_chunks()) {
                   umma_commit(smem_u32(&bar->mid_empty[mb]));
                   g2_j = 0;
@@ -637,6 +643,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (ok) {
               gemm1_row(g1_kh, d0, a_tile);
               did = true;
+              idle = 0;
               if (++g1_kh == 3) {
                 umma_commit(smem_u32(&bar->a_empty[sa]));
                 umma_commit(smem_u32(&bar->acc0_full[g1_it % g.n_acc0()]));
@@ -879,6 +886,349 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 3) tmem_dealloc<512>(tmem);
 }
 
+// =============================================================================== CTA-pair kernel
+// cta_group::2 version for shapes whose weights fit in shared memory once they are SPLIT across a
+// pair of CTAs (BASELINE cfg3: 144 KB + 64 KB -> 72 + 32 KB per CTA): no weight streaming at all.
+// A cluster of 2 CTAs works on two adjacent 128-position tiles as one M = 256 MMA tile:
+//   * each CTA loads its own halo (TMA, completion bytes reported to the LEADER's barrier), owns the
+//     128 TMEM lanes of its tile and runs its own 16 epilogue warps;
+//   * each CTA holds rows [64r, 64r+64) of every weight block; the tensor cores of both SMs read both
+//     halves (that is what cta_group::2 does), so B is fetched from HBM/L2 once per pair and never again;
+//   * only the leader issues tcgen05.mma / tcgen05.commit (multicast to both CTAs' barriers); the
+//     peer's epilogue warps arrive on the leader's barriers through shared::cluster addresses.
+// One descriptor must address both CTAs' halo buffers, so instead of shifting the descriptor by the
+// tile's offset inside its halo window, every CTA shifts the TMA DESTINATION such that its tile origin
+// always lands at the same shared-memory offset.
+struct PairBarriers {
+  uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
+  uint64_t res_full, peer_ready;
+  uint64_t acc0_full[2], acc0_empty[2];
+  uint64_t mid_full[2], mid_empty[2];
+  uint64_t acc1_full[2], acc1_empty[2];
+  uint32_t tmem_base;
+};
+
+template <class G, int kDst>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
+                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ Params p,
+                 const __grid_constant__ EpiConsts<G> ec) {
+  static_assert(G::is_static && G::n_acc0 == 2 && G::nc1 == 128 && G::OC % 64 == 0, "pair kernel: unsupported geometry");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  PairBarriers* bar = reinterpret_cast<PairBarriers*>(smem);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int n_pair_tiles = (p.n_tiles + 1) >> 1;
+  const int n_local = (n_pair_tiles - cid + ncl - 1) / ncl;
+  constexpr int kHalfRows0 = G::OC / 2, kHalfRows1 = G::nc1 / 2;
+  constexpr uint32_t kW0Half = kHalfRows0 * G::swb, kW1Half = kHalfRows1 * G::swb1;
+  constexpr int kNW0 = 9 * G::nkb, kNW1 = G::n_chunks * G::nkb1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kMaxAStages; ++i) {
+      mbar_init(smem_u32(&bar->a_full[i]), 2);  // one expect_tx arrival per CTA of the pair
+      mbar_init(smem_u32(&bar->a_empty[i]), 1);
+    }
+    mbar_init(smem_u32(&bar->res_full), 1);
+    mbar_init(smem_u32(&bar->peer_ready), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar->acc0_full[i]), 1);
+      mbar_init(smem_u32(&bar->acc0_empty[i]), 2 * kEpiWarps);
+      mbar_init(smem_u32(&bar->mid_full[i]), 2 * kEpiWarps);
+      mbar_init(smem_u32(&bar->mid_empty[i]), 1);
+      mbar_init(smem_u32(&bar->acc1_full[i]), 1);
+      mbar_init(smem_u32(&bar->acc1_empty[i]), 2 * kEpiWarps);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW0);
+    tma_prefetch_desc(&tmW1);
+  }
+  if (warp == 3) tmem_alloc_pair<512>(smem_u32(&bar->tmem_base));
+  {
+    float* sb0 = reinterpret_cast<float*>(smem + p.off_bias0);
+    float* sb1 = reinterpret_cast<float*>(smem + p.off_bias1);
+    int* sk1 = reinterpret_cast<int*>(smem + p.off_k1);
+    for (int i = threadIdx.x; i < G::OC; i += kThreads) sb0[i] = p.bias0[i];
+    for (int i = threadIdx.x; i < G::OC1; i += kThreads) {
+      sb1[i] = p.bias1[i];
+      sk1[i] = p.k1[i];
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before anyone arrives remotely
+  tc_fence_after_sync();
+  const uint32_t tmem = bar->tmem_base;
+  const int q_first = 2 * p.Wp;
+  const uint32_t a_origin = (uint32_t)p.Wp * G::swb;  // tile origin inside a halo stage (same in both CTAs)
+
+  if (warp == 0) {
+    // ================================ halo producer (both CTAs) ================================
+    if (elect_one()) {
+      Tracer tr(p, 0);
+      for (int it = 0; it < n_local; ++it) {
+        const int tile = 2 * (cid + it * ncl) + (int)rank;
+        const int s = it % p.SA;
+        mbar_wait(smem_u32(&bar->a_empty[s]), ((it / p.SA) & 1) ^ 1);
+        tr.ev(1);
+        const int q0 = q_first + tile * kTileM;
+        const int g_lo = (q0 - p.Wp - 1) / p.Wp;
+        const int g_hi = (q0 + kTileM + p.Wp) / p.Wp;
+        const int nrows = g_hi - g_lo + 1;
+        const int a_off_px = (q0 - p.Wp - 1) - g_lo * p.Wp;
+        const uint32_t leader_full = mapa_u32(smem_u32(&bar->a_full[s]), 0);
+        mbar_expect_tx_cluster(leader_full, (uint32_t)(nrows * G::nkb * p.Wp * G::swb));
+        int n = (g_lo > 0) ? (g_lo - 1) / p.Hp : 0;
+        int h = (g_lo > 0) ? (g_lo - 1) - n * p.Hp - 1 : -2;
+        uint32_t dst = sbase + p.off_a + s * p.a_stage_bytes + a_origin - (uint32_t)a_off_px * G::swb;
+        const uint32_t row_bytes = p.Wp * G::swb;
+        for (int r = 0; r < nrows; ++r, dst += row_bytes) {
+#pragma unroll
+          for (int kb = 0; kb < G::nkb; ++kb) tma_load_4d_pair(dst + kb * p.a_kb_stride, &tmA, leader_full, kb * G::swb, 0, h, n);
+          if (h == -2) {
+            h = -1;
+          } else if (++h == p.H) {
+            h = -1;
+            ++n;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ============================ resident weight halves (both CTAs) ===========================
+    if (elect_one()) {
+      const uint32_t full = smem_u32(&bar->res_full);
+      mbar_expect_tx(full, kNW0 * kW0Half + kNW1 * kW1Half);
+      for (int b = 0; b < kNW0; ++b) tma_load_2d(sbase + p.off_w0 + b * kW0Half, &tmW0, full, 0, b * G::OC + (int)rank * kHalfRows0);
+      for (int b = 0; b < kNW1; ++b) tma_load_2d(sbase + p.off_w1 + b * kW1Half, &tmW1, full, 0, b * G::nc1 + (int)rank * kHalfRows1);
+      mbar_wait(full, 0);
+      if (rank == 1) mbar_arrive_cluster(mapa_u32(smem_u32(&bar->peer_ready), 0));
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (leader only) =================================
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc0 = make_idesc_i8(2 * kTileM, G::OC, 0, 1);
+      const uint32_t idesc1 = make_idesc_i8(2 * kTileM, G::nc1, 0, 1);
+      const uint64_t desc0_hi = make_smem_desc(0, 16, 8 * G::swb, layout_of(G::swb));
+      const uint64_t desc1_hi = make_smem_desc(0, 16, 8 * G::swb1, layout_of(G::swb1));
+      const uint32_t a_step_kw = G::swb >> 4, a_step_kh = (p.Wp * G::swb) >> 4, a_step_kb = p.a_kb_stride >> 4;
+      const uint64_t w0_desc = desc0_hi | ((sbase + p.off_w0) >> 4), w1_desc = desc1_hi | ((sbase + p.off_w1) >> 4);
+      Tracer tr(p, 1);
+      tr.ev(8);
+      mbar_wait(smem_u32(&bar->res_full), 0);
+      mbar_wait(smem_u32(&bar->peer_ready), 0);
+      tc_fence_after_sync();
+      tr.ev(9);
+      uint32_t c1count = 0, sa = 0, a_par = 0;
+      int g1_it = 0, g1_kh = 0, g2_it = 0, g2_j = 0;
+      bool g2_open = false;
+      uint64_t a_tile = 0;
+      uint32_t d0 = 0;
+      uint32_t idle = 0;
+      while (g2_it < n_local) {
+        bool did = false;
+        if (++idle > (1u << 27)) {
+          printf("conv MMA scheduler stuck: block %d g1 %d/%d g2 %d/%d\n", blockIdx.x, g1_it, g1_kh, g2_it, g2_j);
+          __trap();
+        }
+        if (g2_it < g1_it) {
+          const int mb = g2_it & 1;
+          if (!g2_open && mbar_test_wait(smem_u32(&bar->mid_full[mb]), (g2_it >> 1) & 1)) g2_open = true;
+          if (g2_open) {
+            const int cb = c1count & 1;
+            if (mbar_test_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ 1)) {
+              tc_fence_after_sync();
+              const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid + mb * p.mid_bytes) >> 4);
+              const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
+#pragma unroll
+              for (int kb = 0; kb < G::nkb1; ++kb) {
+                const uint64_t b_desc = w1_desc + (uint64_t)((g2_j * G::nkb1 + kb) * (kW1Half >> 4));
+                const uint64_t a_desc = mid_desc + kb * ((kTileM * G::swb1) >> 4);
+                constexpr int nks_full = G::swb1 >> 5;
+                const int nks = (kb == G::nkb1 - 1) ? G::ks1_last : nks_full;
+#pragma unroll
+                for (int ks = 0; ks < nks; ++ks) umma_i8_pair(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, (kb | ks) != 0);
+              }
+              umma_commit_pair(smem_u32(&bar->acc1_full[cb]));
+              tr.ev(13);
+              ++c1count;
+              did = true;
+              idle = 0;
+              if (++g2_j == G::n_chunks) {
+                umma_commit_pair(smem_u32(&bar->mid_empty[mb]));
+                g2_j = 0;
+                g2_open = false;
+                ++g2_it;
+              }
+            }
+          }
+        }
+        if (!did && g1_it < n_local) {
+          bool ok = true;
+          if (g1_kh == 0) {
+            const int ab = g1_it & 1;
+            ok = mbar_test_wait(smem_u32(&bar->acc0_empty[ab]), ((g1_it >> 1) & 1) ^ 1) &&
+                 mbar_test_wait(smem_u32(&bar->a_full[sa]), a_par);
+            if (ok) {
+              tc_fence_after_sync();
+              tr.ev(10);
+              d0 = tmem + ab * G::OC;
+              a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_origin) >> 4);
+            }
+          }
+          if (ok) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int kb = 0; kb < G::nkb; ++kb) {
+                const int blk = (g1_kh * 3 + kw) * G::nkb + kb;
+                const uint64_t b_desc = w0_desc + (uint64_t)(blk * (kW0Half >> 4));
+                const uint64_t a_desc = a_tile + g1_kh * a_step_kh + kw * a_step_kw + kb * a_step_kb;
+                constexpr int nks_full = G::swb >> 5;
+                const int nks = (kb == G::nkb - 1) ? G::ks_last : nks_full;
+#pragma unroll
+                for (int ks = 0; ks < nks; ++ks) umma_i8_pair(d0, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+              }
+            }
+            did = true;
+            idle = 0;
+            if (++g1_kh == 3) {
+              umma_commit_pair(smem_u32(&bar->a_empty[sa]));
+              umma_commit_pair(smem_u32(&bar->acc0_full[g1_it & 1]));
+              tr.ev(11);
+              g1_kh = 0;
+              ++g1_it;
+              if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ================================== epilogue (both CTAs) ===================================
+    const int ew = warp - kEpiWarp0;
+    const int group = ew / kEpiWarps;
+    const int quarter = warp & 3;
+    const int half = (ew % kEpiWarps) >> 2;
+    const int m = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+    const float* sb0 = reinterpret_cast<const float*>(smem + p.off_bias0);
+    const float* sb1 = reinterpret_cast<const float*>(smem + p.off_bias1);
+    const int* sk1 = reinterpret_cast<const int*>(smem + p.off_k1);
+    constexpr int ts = (kDst == DF_F32 || kDst == DF_S32) ? 4 : 1;
+    const bool relu1 = p.relu1 != 0;
+    // the leader owns the barriers the MMA thread waits on
+    uint32_t l_acc0_empty[2], l_mid_full[2], l_acc1_empty[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      l_acc0_empty[i] = mapa_u32(smem_u32(&bar->acc0_empty[i]), 0);
+      l_mid_full[i] = mapa_u32(smem_u32(&bar->mid_full[i]), 0);
+      l_acc1_empty[i] = mapa_u32(smem_u32(&bar->acc1_empty[i]), 0);
+    }
+
+    Tracer tr(p, 3);
+    if (threadIdx.x != kEpiWarp0 * 32) tr.base = nullptr;
+    auto unit_e0 = [&](int it) {
+      const int ab = it & 1, mb = it & 1;
+      mbar_wait_warp(smem_u32(&bar->mid_empty[mb]), ((it >> 1) & 1) ^ 1);
+      mbar_wait_warp(smem_u32(&bar->acc0_full[ab]), (it >> 1) & 1);
+      tc_fence_after_sync();
+      tr.ev(30);
+      uint8_t* mid = smem + p.off_mid + mb * p.mid_bytes;
+      const uint32_t t_base = lane_addr + ab * G::OC;
+#pragma unroll
+      for (int i = 0; i < G::OC / 64; ++i) {
+        const int gr = i * 2 + half;
+        uint32_t acc[32];
+        tmem_ld_x32(t_base + gr * 32, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          const int c16 = gr * 2 + sub;
+          const float4* b4 = reinterpret_cast<const float4*>(sb0 + c16 * 16);
+          auto s4 = [&](int k) -> float4 {
+            const int c0 = c16 * 16 + k * 4;
+            return make_float4(ec.scale0[c0], ec.scale0[c0 + 1], ec.scale0[c0 + 2], ec.scale0[c0 + 3]);
+          };
+          uint4 v;
+          v.x = requant_u8x4<false, false>(acc + sub * 16 + 0, b4[0], s4(0));
+          v.y = requant_u8x4<false, false>(acc + sub * 16 + 4, b4[1], s4(1));
+          v.z = requant_u8x4<false, false>(acc + sub * 16 + 8, b4[2], s4(2));
+          v.w = requant_u8x4<false, false>(acc + sub * 16 + 12, b4[3], s4(3));
+          const int kb = (c16 * 16) / G::swb1;
+          uint32_t off = (uint32_t)m * G::swb1 + (uint32_t)(c16 * 16 - kb * G::swb1);
+          off ^= ((off >> 7) & (uint32_t)(G::swb1 / 16 - 1)) << 4;
+          *reinterpret_cast<uint4*>(mid + kb * (kTileM * G::swb1) + off) = v;
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(l_acc0_empty[ab]);
+        mbar_arrive_cluster(l_mid_full[mb]);
+      }
+      tr.ev(31);
+    };
+
+    auto unit_c = [&](int it, int j, uint32_t c) {
+      const int tile = 2 * (cid + it * ncl) + (int)rank;
+      const int q = q_first + tile * kTileM + m;
+      const int gq = q / p.Wp, wq = q - gq * p.Wp;
+      const int n = (gq - 1) / p.Hp, hp = (gq - 1) - n * p.Hp;
+      const bool valid = (wq < p.W) && (hp >= 1) && (n < p.N);
+      uint8_t* out_row = static_cast<uint8_t*>(p.dst) + ((size_t)(n * p.H + hp - 1) * p.W + wq) * G::OC1 * ts;
+      const int cb = c & 1;
+      mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c >> 1) & 1);
+      tc_fence_after_sync();
+      tr.ev(32);
+      const uint32_t t_base = lane_addr + kAcc1Col + cb * kAcc1Stride;
+#pragma unroll
+      for (int i = 0; i < G::nc1 / 64; ++i) {
+        const int gr = i * 2 + half;
+        uint32_t acc[32];
+        tmem_ld_x32(t_base + gr * 32, acc);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const int col = j * G::nc1 + gr * 32 + sub * 16;
+            auto s4 = [&](int k) -> float4 {
+              const int c0 = col + k * 4;
+              return make_float4(ec.scale1[c0], ec.scale1[c0 + 1], ec.scale1[c0 + 2], ec.scale1[c0 + 3]);
+            };
+            store16<kDst, false, false, true>(acc + sub * 16, sb1 + col, sk1 + col, p.k1_uniform, s4, relu1,
+                                              out_row + (size_t)col * ts);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(l_acc1_empty[cb]);
+      tr.ev(33);
+    };
+
+    uint32_t u = 0, c = 0;
+    if (n_local > 0) {
+      if ((u++ % kEpiGroups) == (uint32_t)group) unit_e0(0);
+    }
+    for (int it = 0; it < n_local; ++it) {
+      if (it + 1 < n_local && (u++ % kEpiGroups) == (uint32_t)group) unit_e0(it + 1);
+      for (int j = 0; j < G::n_chunks; ++j, ++c)
+        if ((u++ % kEpiGroups) == (uint32_t)group) unit_c(it, j, c);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still touch it
+  if (warp == 3) tmem_dealloc_pair<512>(tmem);
+}
+
 // ================================================================================ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -924,6 +1274,26 @@ struct KernelFn {
   LaunchFn launch;
   AttrFn attr;
 };
+
+template <class G, int kDst>
+cudaError_t launch_pair(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
+                        const CUtensorMap& w1, const Params& p, const void* epi_consts) {
+  conv_pair_kernel<G, kDst><<<grid, kThreads, smem, st>>>(a, w0, w1, p, *static_cast<const EpiConsts<G>*>(epi_consts));
+  return cudaGetLastError();
+}
+template <class G, int kDst>
+cudaError_t attr_pair(uint32_t smem) {
+  return cudaFuncSetAttribute((const void*)conv_pair_kernel<G, kDst>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <class G>
+KernelFn pick_pair(int dst_dt) {
+  switch (dst_dt) {
+    case DF_U8: return KernelFn{launch_pair<G, DF_U8>, attr_pair<G, DF_U8>};
+    case DF_S8: return KernelFn{launch_pair<G, DF_S8>, attr_pair<G, DF_S8>};
+    case DF_S32: return KernelFn{launch_pair<G, DF_S32>, attr_pair<G, DF_S32>};
+    default: return KernelFn{launch_pair<G, DF_F32>, attr_pair<G, DF_F32>};
+  }
+}
 #define DF_KERNEL(G, DT, D0, D1, NS) KernelFn{launch_conv<G, DT, D0, D1, NS>, attr_conv<G, DT, D0, D1, NS>}
 
 // Static geometries = the BASELINE.json conv shapes together with the shared-memory plan
@@ -931,6 +1301,7 @@ struct KernelFn {
 using GeoCfg1 = StaticGeom<64, 64, 256, 1, 1, 1>;      // 56x56  64->64->256 : everything resident
 using GeoCfg3 = StaticGeom<128, 128, 512, 0, 1, 3>;    // 28x28 128->128->512: W1 resident, W0 through 3 stages
 using GeoCfg4 = StaticGeom<256, 256, 1024, 0, 0, 2>;   // 14x14 256->256->1024: all weights through 2 stages
+using GeoCfg3P = StaticGeom<128, 128, 512, 1, 1, 1>;   // cfg3 on CTA pairs: weight halves resident (conv_pair_kernel)
 
 template <class G>
 KernelFn pick_static(int dst_dt) {
@@ -994,12 +1365,19 @@ bool geom_matches(const Params& p) {
 }  // namespace
 
 struct df_conv {
-  df_conv() : desc(), prm(), kernel{nullptr, nullptr}, geom_id(0), smem_bytes(0), device(0), sms(0), d_w0(nullptr),
+  df_conv() : desc(), prm(), kernel{nullptr, nullptr}, pair(false), pair_kernel{nullptr, nullptr}, pair_prm(), pair_smem(0),
+              tmW0h(), tmW1h(), geom_id(0), smem_bytes(0), device(0), sms(0), d_w0(nullptr),
               d_w1(nullptr), d_bias0(nullptr), d_scale0(nullptr), d_bias1(nullptr), d_scale1(nullptr), d_k1(nullptr),
               tmW0(), tmW1(), tmA(), tmA_src(nullptr), tmA_n(-1), trace(nullptr), trace_cap(0) {}
   df_conv_desc desc;
   Params prm;        // everything except n-dependent fields and dst
   KernelFn kernel;
+  // CTA-pair variant (conv_pair_kernel), used when `pair` is set
+  bool pair;
+  KernelFn pair_kernel;
+  Params pair_prm;
+  uint32_t pair_smem;
+  CUtensorMap tmW0h, tmW1h;
   std::vector<char> epi_consts;  // by-value kernel parameter of the static geometries
   int geom_id;
   uint32_t smem_bytes;
@@ -1323,6 +1701,39 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   if (op->geom_id == 3) op->epi_consts = make_epi_consts<GeoCfg3>(b0, s0, k1, c1, s1);
   if (op->geom_id == 4) op->epi_consts = make_epi_consts<GeoCfg4>(b0, s0, k1, c1, s1);
   DF_TRY_CUDA(op->kernel.attr(op->smem_bytes));
+
+  // ---- CTA-pair variant: BASELINE cfg3 with everything resident once the weights are split in two
+  // Opt-in (DF_PAIR=1): it removes weight streaming entirely, but both variants are currently bound by
+  // the epilogue and the single-CTA kernel is ~8 % faster end to end (profiles/README.md).
+  if (op->geom_id == 3 && getenv("DF_PAIR") && atoi(getenv("DF_PAIR")) != 0) {
+    Params q = p;
+    q.w0_res = q.w1_res = 1;
+    q.SB = 1;
+    q.NM = 2;
+    uint32_t off2 = fixed_one_mid - p.mid_bytes;  // = start of the intermediate buffers
+    q.off_mid = off2;
+    off2 += 2 * q.mid_bytes;
+    q.off_w0 = off2;
+    off2 += align_up(9 * q.nkb * (q.w0_block_bytes / 2), 1024);
+    q.off_w1 = off2;
+    off2 += align_up(q.n_chunks * q.nkb1 * (q.w1_block_bytes / 2), 1024);
+    q.off_a = off2;
+    q.a_kb_stride = (uint32_t)(q.NR + 1) * q.Wp * q.swb;  // one extra row of slack before the tile origin
+    q.a_stage_bytes = align_up(q.nkb * q.a_kb_stride, 1024);
+    const int sa = (int)((avail - q.off_a) / q.a_stage_bytes);
+    if (sa >= 2) {
+      q.SA = sa > kMaxAStages ? kMaxAStages : sa;
+      q.off_b = q.off_a + q.SA * q.a_stage_bytes;
+      q.b_stage_bytes = 0;
+      op->pair_prm = q;
+      op->pair_smem = q.off_b + 1024;
+      op->pair_kernel = pick_pair<GeoCfg3P>(d->dst_dt);
+      DF_TRY_CUDA(op->pair_kernel.attr(op->pair_smem));
+      DF_TRY(encode_2d(&op->tmW0h, op->d_w0, q.swb, (long)9 * q.nkb * q.OC, q.OC / 2));
+      DF_TRY(encode_2d(&op->tmW1h, op->d_w1, q.swb1, (long)q.n_chunks * q.nkb1 * q.nc1, q.nc1 / 2));
+      op->pair = true;
+    }
+  }
   *out = op;
   return 0;
 }
@@ -1338,7 +1749,7 @@ extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, vo
   if (n == 0) return 0;
   if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
     return df::fail(DF_E_INVALID, "conv run: src/dst must be 16-byte aligned");
-  Params p = op->prm;
+  Params p = op->pair ? op->pair_prm : op->prm;
   if ((long)n * p.Hp * p.Wp + 4L * p.Wp + kTileM >= (1L << 31))
     return df::fail(DF_E_UNSUPPORTED, "conv run: batch too large for 32-bit position index");
   if (op->tmA_src != src || op->tmA_n != n) {
@@ -1360,6 +1771,13 @@ extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, vo
   p.dst = dst;
   p.trace = op->trace;
   p.trace_cap = op->trace_cap;
+  if (op->pair) {
+    const int pair_tiles = (p.n_tiles + 1) / 2, clusters = pair_tiles < op->sms / 2 ? pair_tiles : op->sms / 2;
+    p.tile_step_mod = 0;
+    DF_CUDA(op->pair_kernel.launch(2 * clusters, op->pair_smem, (cudaStream_t)stream, op->tmA, op->tmW0h, op->tmW1h, p,
+                                   op->epi_consts.data()));
+    return 0;
+  }
   const int grid = p.n_tiles < op->sms ? p.n_tiles : op->sms;
   p.tile_step_mod = (kTileM * grid) % p.Wp;
   DF_CUDA(op->kernel.launch(grid, op->smem_bytes, (cudaStream_t)stream, op->tmA, op->tmW0, op->tmW1, p,
@@ -1382,11 +1800,11 @@ extern "C" int df_conv_query(const df_conv* op, df_conv_info* info) {
   info->tiles_per_launch = tiles_for(p, op->desc.n);
   info->grid = info->tiles_per_launch < op->sms ? info->tiles_per_launch : op->sms;
   info->block = kThreads;
-  info->smem_bytes = (int)op->smem_bytes;
-  info->w0_resident = p.w0_res;
-  info->w1_resident = p.w1_res;
-  info->a_stages = p.SA;
-  info->b_stages = p.SB;
+  info->smem_bytes = (int)(op->pair ? op->pair_smem : op->smem_bytes);
+  info->w0_resident = op->pair ? 2 : p.w0_res;  // 2 = resident, split across a CTA pair
+  info->w1_resident = op->pair ? 2 : p.w1_res;
+  info->a_stages = op->pair ? op->pair_prm.SA : p.SA;
+  info->b_stages = op->pair ? 0 : p.SB;
   info->padded_w = p.Wp;
   info->padded_h = p.Hp;
   info->macs_per_image = (double)p.H * p.W * (9.0 * p.IC * p.OC + (double)p.OC * p.OC1);

@@ -193,3 +193,44 @@ def test_concat_many_inputs_and_odd_widths(df):
         assert np.array_equal(df.concat(ins, cases.DT["s8"], relu), O.concat(O.S8, relu, ins))
     ins32 = cases.concat_inputs("s32", [(2, c, 3, 3) for c in (4, 12, 20, 8)], "full")
     assert np.array_equal(df.concat(ins32, cases.DT["s32"], True), O.concat(O.S32, True, ins32))
+
+
+# ------------------------------------------------------------------- alternative kernel paths
+def _run_cfg3_in_subprocess(env_extra):
+    """cfg3 (N=8) through the C-ABI in a fresh process with a kernel-selection hook set."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import sys
+sys.path.insert(0, {os.path.join(root, 'tests')!r}); sys.path.insert(0, {os.path.join(root, 'deep-fusion_b200')!r})
+import numpy as np, cases, dfb200 as df, oracle_lib as O
+c = cases.ConvCase("alt", 8, 28, 28, 128, 128, 512, "u8", "s32", "s32")
+src, w0, w1, b0, b1, s0, s1 = c.tensors()
+wb, w1b = c.blocked(w0, w1)
+op = df.Conv(c.n, c.h, c.w, c.ic, c.oc, c.oc1, df.U8, wb, w1b, b0, b1, s0, s1, df.S32, df.S32)
+i = op.info()
+got = op(src)
+d = O.make_desc(c.n, c.h, c.w, c.ic, c.oc, c.oc1, O.U8, O.S32, O.S32, nscale0=c.oc, nscale1=c.oc1)
+fn = O.replay_conv if O.replay_supported() else O.conv
+want = fn(d, src, wb, b0, s0, w1b, b1, s1)
+print("RES", i.w0_resident, i.w1_resident, "OK" if np.array_equal(got, want) else "MISMATCH")
+"""
+    env = dict(os.environ)
+    env.update(env_extra)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout
+
+
+def test_conv_cta_pair_kernel(df):
+    """cta_group::2 variant (weight halves resident in a CTA pair), opt-in through DF_PAIR=1."""
+    out = _run_cfg3_in_subprocess({"DF_PAIR": "1"})
+    assert "RES 2 2 OK" in out, out
+
+
+def test_conv_generic_geometry_and_i2f_paths(df):
+    """The run-time-geometry kernel and the plain I2F conv1 epilogue on a BASELINE shape."""
+    assert "OK" in _run_cfg3_in_subprocess({"DF_FORCE_DYNAMIC_GEOMETRY": "1"})
+    assert "OK" in _run_cfg3_in_subprocess({"DF_NO_FAST_CONV1": "1"})
+    assert "OK" in _run_cfg3_in_subprocess({"DF_FORCE_DYNAMIC_GEOMETRY": "1", "DF_NO_FAST_CONV1": "1"})
