@@ -163,10 +163,20 @@ def cpu_port_time(p, budget_s, min_runs=2):
     return n * runs / dt, runs, n, kind, int(O.lib().dfr_num_threads())
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is specified to use every host thread.  Must
+    run before the oracle library (libgomp) is loaded."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.setdefault("OMP_PROC_BIND", "close")  # analogue of the reference's run_benchmark.sh pinning
+    return n
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path on the host cores."""
     if rank != 0:
         return
+    use_all_host_threads()
     p = conv_params(args.workload)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
@@ -304,6 +314,7 @@ def run_ours(args, rank, world, local_rank):
         return
     cpu = None
     if world == 1 and not args.no_cpu:
+        use_all_host_threads()
         ips, runs, imgs, kind, cores = cpu_port_time(p, budget_s=args.cpu_seconds)
         cpu = {"value": ips * ops_per_image(p) / 1e12, "unit": "TOPS", "images_per_s": ips, "cores": cores, "kind": "port",
                "sample": f"{runs} passes over {imgs} images of the same workload ({kind}); the reference binary needs Xbyak and cannot be built offline"}

@@ -90,6 +90,10 @@ int df_event_record(void* e, void* s) {
   DF_CUDA(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s));
   return 0;
 }
+int df_stream_wait_event(void* s, void* e) {
+  DF_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0));
+  return 0;
+}
 int df_event_elapsed_ms(void* a, void* b, float* ms) {
   DF_CUDA(cudaEventSynchronize((cudaEvent_t)b));
   DF_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));

@@ -228,13 +228,17 @@ public:
       error_and_exit("Init Conv op failed!");
     }
   }
-  ~conv_op() override { df_conv_destroy(handle_); }
+  ~conv_op() override {
+    df_conv_destroy(handle_);
+    for (void *e : events_) df_event_destroy(e);
+    for (void *st : streams_) df_stream_destroy(st);
+  }
 
   void launch(void *stream) override {
     cuda_or_exit(df_conv_run(handle_, static_cast<const uint8_t *>(mirror(*src_)), mirror(*dst_), desc_.n, stream),
                  "conv launch");
   }
-  int launches() const override { return 1; }
+  int launches() const override { return desc_.n >= 8 ? 4 : 1; }  // slabs of the pipelined submit()
 
 protected:
   // op_conv<T>::init_conf (src/op_conv.cc:262-365) + the format gate of
@@ -337,11 +341,45 @@ protected:
     return true;
   }
 
+  // submit(): host -> device, kernel, device -> host, synchronous like the reference.  Images are
+  // independent, so the batch is cut into slabs that flow through three streams: the upload of slab
+  // i+1, the kernel of slab i and the download of slab i-1 overlap (PCIe is full duplex), which is
+  // what bounds this path -- the kernel itself is ~4 % of it.
   void infer() override {
-    cuda_or_exit(df_h2d(mirror(*src_), src_->data(), src_->buffer_size(), nullptr), "conv H2D");
-    launch(nullptr);
-    cuda_or_exit(df_d2h(dst_->data(), mirror(*dst_), dst_->buffer_size(), nullptr), "conv D2H");
-    cuda_or_exit(df_stream_sync(nullptr), "conv sync");
+    const int n = desc_.n;
+    const int slabs = n >= 8 ? 4 : 1;
+    uint8_t *d_src = static_cast<uint8_t *>(mirror(*src_)), *d_dst = static_cast<uint8_t *>(mirror(*dst_));
+    const uint8_t *h_src = static_cast<const uint8_t *>(src_->data());
+    uint8_t *h_dst = static_cast<uint8_t *>(dst_->data());
+    if (slabs == 1) {
+      cuda_or_exit(df_h2d(d_src, h_src, src_->buffer_size(), nullptr), "conv H2D");
+      launch(nullptr);
+      cuda_or_exit(df_d2h(h_dst, d_dst, dst_->buffer_size(), nullptr), "conv D2H");
+      cuda_or_exit(df_stream_sync(nullptr), "conv sync");
+      return;
+    }
+    if (streams_.empty()) {
+      detail::memory_state *ss = src_->state(), *ds = dst_->state();  // pinned buffers make the copies truly asynchronous
+      if (!ss->pinned && df_host_register(src_->data(), src_->buffer_size()) == 0) ss->pinned = true;
+      if (!ds->pinned && df_host_register(dst_->data(), dst_->buffer_size()) == 0) ds->pinned = true;
+      streams_.resize(3);
+      for (void *&st : streams_) cuda_or_exit(df_stream_create(&st), "stream create");
+      events_.resize(2 * slabs);
+      for (void *&e : events_) cuda_or_exit(df_event_create(&e), "event create");
+    }
+    const size_t src_img = src_->buffer_size() / n, dst_img = dst_->buffer_size() / n;
+    const int per = (n + slabs - 1) / slabs;
+    for (int i = 0, first = 0; i < slabs && first < n; ++i, first += per) {
+      const int cnt = first + per <= n ? per : n - first;
+      cuda_or_exit(df_h2d(d_src + first * src_img, h_src + first * src_img, cnt * src_img, streams_[0]), "conv H2D");
+      cuda_or_exit(df_event_record(events_[2 * i], streams_[0]), "event record");
+      cuda_or_exit(df_stream_wait_event(streams_[1], events_[2 * i]), "stream wait");
+      cuda_or_exit(df_conv_run(handle_, d_src + first * src_img, d_dst + first * dst_img, cnt, streams_[1]), "conv launch");
+      cuda_or_exit(df_event_record(events_[2 * i + 1], streams_[1]), "event record");
+      cuda_or_exit(df_stream_wait_event(streams_[2], events_[2 * i + 1]), "stream wait");
+      cuda_or_exit(df_d2h(h_dst + first * dst_img, d_dst + first * dst_img, cnt * dst_img, streams_[2]), "conv D2H");
+    }
+    cuda_or_exit(df_stream_sync(streams_[2]), "conv sync");
   }
   const char *name() override { return "conv"; }
 
@@ -349,6 +387,7 @@ private:
   memory *src_, *dst_;
   df_conv_desc desc_;
   df_conv *handle_ = nullptr;
+  std::vector<void *> streams_, events_;  // created on the first pipelined submit()
 };
 
 }  // namespace

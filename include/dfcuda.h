@@ -53,6 +53,7 @@ int df_stream_sync(void *stream);
 int df_stream_destroy(void *stream);
 int df_event_create(void **event);
 int df_event_record(void *event, void *stream);
+int df_stream_wait_event(void *stream, void *event);
 int df_event_elapsed_ms(void *start, void *stop, float *ms); /* synchronises on `stop` */
 int df_event_destroy(void *event);
 
