@@ -39,9 +39,9 @@ using namespace sm100;
 namespace {
 
 constexpr int kEpiWarp0 = 4;    // warps 0..3: TMA(A) | MMA | TMA(W) | TMEM alloc
-constexpr int kEpiWarps = 8;    // warps per epilogue group (two per TMEM lane quarter)
-constexpr int kEpiGroups = 2;   // groups take alternate work units (conv0 tile / conv1 chunk)
-constexpr int kThreads = 32 * (kEpiWarp0 + kEpiGroups * kEpiWarps);  // 640
+constexpr int kEpiWarps = 16;   // epilogue warps (four per TMEM lane quarter), all on the same work unit
+constexpr int kStageBufs = 2;   // output staging buffers (unit c uses buffer c & 1)
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);  // 640
 constexpr int kTileM = 128;
 constexpr int kMaxAStages = 4;
 constexpr int kMaxBStages = 8;
@@ -58,15 +58,20 @@ struct Params {
   int nc1, n_chunks, n_acc0;
   int SA, SB, NM, w0_res, w1_res;  // halo stages, weight stages, intermediate buffers
   int tile_step_mod;               // (128 * gridDim.x) mod Wp: halo-window offset step per tile
+  // position steps for the epilogue's division-free bookkeeping (PosState): from a tile to the next tile of
+  // the same CTA, and 8 positions down inside a tile; each as (columns, images, rows) with
+  // step = ((images * Hp + rows) * Wp + columns) positions
+  int ts_dw, ts_dn, ts_dh, r8_dw, r8_dn, r8_dh;
   uint32_t off_bias0, off_scale0, off_bias1, off_scale1, off_k1;
   int fast1;      // conv1 int->float by exact offset-magic conversion (k1 / bias1 hold K[q] / C[q])
   int k1_uniform; // non-zero: one K serves every channel (global lower bound keeps the range < 2^23)
-  int epi_ahead;  // epilogue does conv0 of tile i+1 before the conv1 chunks of tile i
   uint32_t off_a, a_stage_bytes, a_kb_stride;
   uint32_t off_mid, mid_bytes, mid_kb_stride;
   uint32_t off_w0, w0_block_bytes, off_w1, w1_block_bytes;
   uint32_t off_b, b_stage_bytes;
   int relu1, round0, round1, nan_safe;
+  int stage_out;       // 1-byte destinations: conv1 chunks are staged in smem and leave by TMA store
+  uint32_t off_stage;  // kStageBufs staging buffers of kTileM x 128 B (128 B-swizzled rows)
   const float *bias0, *scale0, *bias1, *scale1;
   const int* k1;
   void* dst;
@@ -94,11 +99,93 @@ struct Barriers {
   uint64_t acc0_full[2], acc0_empty[2];
   uint64_t mid_full[2], mid_empty[2];
   uint64_t acc1_full[2], acc1_empty[2];
+  uint64_t stage_full[2], stage_empty[2];  // staged output: epilogue group <-> store thread (warp 3)
   uint32_t tmem_base;
 };
 
 __device__ __forceinline__ uint32_t layout_of(int swb) {
   return swb == 128 ? kLayoutSW128 : (swb == 64 ? kLayoutSW64 : kLayoutSW32);
+}
+
+constexpr uint32_t kStageBytes = kTileM * 128;  // one staged conv1 chunk: 128 positions x 128 channels (1 byte each)
+
+// Staged output of the conv1 chunks (1-byte destinations).  Plain per-thread stores are the wrong tool
+// here: a thread owns one position (row) of the tile, so a warp-wide 16-byte store touches 32 different
+// 128-byte lines and the LSU spends ~32 cycles on it (profiles/r01_epilogue_unit_bench.log: stores tripled
+// the epilogue time).  Instead the epilogue group writes the chunk into shared memory and the TMA unit
+// sends it out:
+//   * the destination is viewed as a 2-D tensor [N*H*W pixels][OC1 channels]; the valid positions of a
+//     tile are a CONTIGUOUS pixel range [f0, f0 + V) of it (padding positions simply do not exist there);
+//   * the thread of valid position q writes its 16-byte units to staging row  valid_before(q) - f0  (rows of
+//     128 B, units XOR-swizzled with row & 7 = SWIZZLE_128B), threads of padding positions write nothing;
+//   * one thread (warp 3) stores rows [0, P) and [V - P, V), P = largest power of two <= V, with the
+//     tensor map whose box is {128 channels, P pixels}: at most two TMA stores per chunk, overlapping rows
+//     carry identical bytes.  (Negative start coordinates, which would allow a single clipped box, are
+//     rejected by the hardware for stores -- probe/tma_store_probe.cu.)
+struct DstMaps {
+  CUtensorMap m[8];  // m[i]: box = {128, 128 >> i}
+};
+
+// number of valid (= real pixel) positions with linear index < q; for a valid q this is its flat NHW
+// pixel index
+__device__ __forceinline__ int valid_before(const Params& p, int q) {
+  const int gq = q / p.Wp, wq = q - gq * p.Wp;
+  const int t = gq - 1;
+  const int n = t / p.Hp, hp = t - n * p.Hp;
+  if (n >= p.N) return p.N * p.H * p.W;
+  if (hp < 1) return n * p.H * p.W;
+  return (n * p.H + hp - 1) * p.W + min(wq, p.W);
+}
+
+// Position q = ((n * Hp + hp) + 1) * Wp + wq of the linearised padded pixel space, kept as (wq, n, hp) and
+// advanced by precomputed steps: the epilogue needs the coordinates of four positions per thread and
+// tile, and computing them with integer divisions cost more than a conv1 chunk's arithmetic
+// (~1500 cycles per tile with 16 warps, profiles/r01_trace_cfg3_v10.log).
+struct PosState {
+  int wq, n, hp;
+};
+__device__ __forceinline__ PosState pos_of(const Params& p, int q) {
+  const int gq = q / p.Wp;
+  PosState s;
+  s.wq = q - gq * p.Wp;
+  s.n = (gq - 1) / p.Hp;
+  s.hp = (gq - 1) - s.n * p.Hp;
+  return s;
+}
+__device__ __forceinline__ void pos_step(const Params& p, PosState& s, int dw, int dn, int dh) {
+  s.wq += dw;
+  int carry = 0;
+  if (s.wq >= p.Wp) {
+    s.wq -= p.Wp;
+    carry = 1;
+  }
+  s.hp += dh + carry;
+  s.n += dn;
+  if (s.hp >= p.Hp) {
+    s.hp -= p.Hp;
+    ++s.n;
+  }
+}
+// NHW pixel index of a position, -1 for padding positions
+__device__ __forceinline__ int pos_pixel(const Params& p, const PosState& s) {
+  const bool ok = (s.wq < p.W) && (s.hp >= 1) && (s.n < p.N);
+  return ok ? (s.n * p.H + s.hp - 1) * p.W + s.wq : -1;
+}
+// = valid_before(q) for the position's q
+__device__ __forceinline__ int pos_valid_before(const Params& p, const PosState& s) {
+  if (s.n >= p.N) return p.N * p.H * p.W;
+  if (s.hp < 1) return s.n * p.H * p.W;
+  return (s.n * p.H + s.hp - 1) * p.W + min(s.wq, p.W);
+}
+
+__device__ __forceinline__ void store_staged_chunk(const DstMaps& dm, uint32_t stage, int f0, int V, int ch0) {
+  if (V > 0) {
+    const int lg = 31 - __clz(V), P = 1 << lg;
+    const CUtensorMap* tm = &dm.m[7 - lg];
+    tma_store_2d(tm, stage, ch0, f0);
+    if (V != P) tma_store_2d(tm, stage + (uint32_t)(V - P) * 128u, ch0, f0 + V - P);
+  }
+  bulk_commit_group();
 }
 
 // ------------------------------------------------------------------------ geometry policies
@@ -119,15 +206,9 @@ struct StaticGeom {
   static constexpr int nc1 = kOC1 < 128 ? kOC1 : 128;
   static constexpr int n_chunks = (kOC1 + nc1 - 1) / nc1;
   static constexpr int n_acc0 = kOC <= 128 ? 2 : 1;
-  // Epilogue constants as immediate constant-bank operands need the column loops fully unrolled
-  // (per chunk and per column half); beyond two chunks that code no longer fits the instruction
-  // caches (measured: 35 % no_instruction stalls at 110 KB of SASS), so larger shapes read the
-  // constants from shared memory instead.
-  static constexpr bool imm_consts = n_chunks <= 2;
 };
 struct DynGeom {
   static constexpr bool is_static = false;
-  static constexpr bool imm_consts = false;
 };
 
 #define DF_GEO(name)                                  \
@@ -237,142 +318,384 @@ __device__ __forceinline__ uint32_t pack_s8x4(float* t, bool relu) {
   return lo;
 }
 
-// 16 accumulator columns of one row -> destination (conv1 epilogue, jit_conv_kernel.cc:89-130).
-// kFast selects the offset-magic conversion (bias holds C[q]; K comes per channel from `k` or as the
-// one uniform `k_uni`).  `scale` is fetched through `ScaleFn` so that it can come from the constant
-// bank while bias/C come from shared memory: the two paths have separate return bandwidth
-// (profiles/r01_lds_broadcast_vs_constbank.log).
-template <int kDst, bool kDown, bool kNanSafe, bool kFast, class ScaleFn>
-__device__ __forceinline__ void store16(const uint32_t* acc, const float* bias, const int* k, int k_uni, ScaleFn scale4_of,
-                                        bool relu, uint8_t* out) {
-  const float4* b4 = reinterpret_cast<const float4*>(bias);
-  const int4* k4 = reinterpret_cast<const int4*>(k);
-  uint32_t packed[4];
+// ---------------------------------------------------------------- TMEM fragments and channel order
+// The epilogue reads accumulators as 16-lane "row pair" fragments: tcgen05.ld.16x256b.xN hands thread t of
+// the warp rows (t/4) and (t/4)+8 of a 16-lane block and, for k = 0..N-1, columns 8k + 2(t%4) + {0,1}:
+//   r[4k + 2*hl + e] = (row t/4 + 8*hl, column 8k + 2(t%4) + e).
+// df_conv_create orders the output channels (= rows of the weight matrices = accumulator columns) such
+// that inside a block of NB columns (NB = 32 read with .x4, or NB = 16 read with .x2 for channel counts
+// that are not multiples of 32) column 8k + 2m + e holds channel (NB/4)*m + 2k + e.  Thread t therefore
+// owns NB/4 CONSECUTIVE channels (starting at (NB/4)*(t%4)) of four rows (two 16-lane loads):
+//   * one set of per-channel constants (bias, scale, K) serves four rows -- with one row per thread
+//     (32x32b fragments) every thread needs the constants of every column, and feeding them (broadcast
+//     LDS: ~1.8 constants/clk/SM, profiles/r01_lds_broadcast_vs_constbank.log) costs more than the math;
+//   * the thread's result is one contiguous 8-byte piece (1-byte types, NB = 32) of a row, and the four
+//     lanes of a quad cover a contiguous 32-byte run (128 bytes for 4-byte types).
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// CH = channels per thread (8: block of 32 columns, 4: block of 16 columns); fills 2 * CH registers
+template <int CH>
+__device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, uint32_t* r) {
+  if constexpr (CH == 16) tmem_ld_16x256b_x8(taddr, r);
+  else if constexpr (CH == 8) tmem_ld_16x256b_x4(taddr, r);
+  else tmem_ld_16x256b_x2(taddr, r);
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, const uint32_t* w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t w) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, const uint32_t* w) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(w[0]), "r"(w[1]) : "memory");
+}
+// CH packed bytes (CH / 4 words) -> shared memory
+template <int CH>
+__device__ __forceinline__ void sts_bytes(uint32_t addr, const uint32_t* packed) {
+  if constexpr (CH == 16) sts128(addr, packed);
+  else if constexpr (CH == 8) sts64(addr, packed);
+  else sts32(addr, packed[0]);
+}
+
+// conv0: CH accumulators (channel order) of one row -> CH bytes (CH / 4 packed words)
+template <bool kDown, bool kNanSafe, int CH>
+__device__ __forceinline__ void finish_conv0(const uint32_t* v, const float4* b4, const float4* s4, uint32_t* packed) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < CH / 4; ++g) packed[g] = requant_u8x4<kDown, kNanSafe>(v + 4 * g, b4[g], s4[g]);
+}
+
+// conv1: CH accumulators (channel order) of one row -> CH / 4 packed words (1-byte destinations) or CH
+// 32-bit words (jit_conv_kernel.cc:89-130).  `fast` selects the offset-magic conversion (c4 then holds
+// C[q]; K comes per channel from k4 or, kUniK, as the one uniform `k_uni`).
+template <int kDst, bool kDown, bool kNanSafe, int CH, bool kUniK>
+__device__ __forceinline__ void finish_conv1(const uint32_t* v, const float4* c4, const float4* s4, const int4* k4, int k_uni,
+                                             bool fast, bool relu, uint32_t* w) {
+#pragma unroll
+  for (int g = 0; g < CH / 4; ++g) {
     float t[4];
-    const float4 s4 = scale4_of(g);
-    if (kFast) scale4_fast(acc + 4 * g, k_uni ? make_int4(k_uni, k_uni, k_uni, k_uni) : k4[g], b4[g], s4, t);
-    else scale4(acc + 4 * g, b4[g], s4, t);
+    if (fast) scale4_fast(v + 4 * g, kUniK ? make_int4(k_uni, k_uni, k_uni, k_uni) : k4[g], c4[g], s4[g], t);
+    else scale4(v + 4 * g, c4[g], s4[g], t);
     if (kDst == DF_U8) {
-      packed[g] = pack_u8x4<kDown, kNanSafe>(t);
+      w[g] = pack_u8x4<kDown, kNanSafe>(t);
     } else if (kDst == DF_S8) {
-      packed[g] = pack_s8x4<kDown>(t, relu);
+      w[g] = pack_s8x4<kDown>(t, relu);
     } else {
       if (relu) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) t[i] = relu_x86(t[i]);
       }
-      uint4 v;
-      if (kDst == DF_F32) {
-        v = make_uint4(__float_as_uint(t[0]), __float_as_uint(t[1]), __float_as_uint(t[2]), __float_as_uint(t[3]));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[4 * g + i] = (kDst == DF_F32) ? __float_as_uint(t[i]) : (uint32_t)cvt_x86<kDown>(t[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ epilogue role
+// Work units: E0(t) = conv0 epilogue of tile t (TMEM acc0 -> u8 tile in smem) and C_j(t) = conv1 chunk j
+// of tile t (TMEM acc1 -> destination).  ALL 16 epilogue warps work on the same unit: warp w reads TMEM
+// lane quarter w % 4 and every fourth column block.  Units run in ONE fixed order,
+//     E0(0) | C_0(t) .. C_{n-2}(t)  E0(t+1)  C_{n-1}(t) | ...
+// which keeps the single intermediate buffer and the two conv1 accumulators busy without ever making
+// the tensor pipe wait for the epilogue it feeds: E0(t+1) starts when GEMM2(t) has read the intermediate
+// tile for the last time (its last chunk was issued when C_{n-3}(t) released an accumulator), and while the
+// epilogue works on C_{n-1}(t), GEMM2(t+1) already fills the other accumulator.  Tile of local iteration
+// `it` = tile0 + it * tile_stride.  kPair: the barriers the MMA thread waits on live in the leader CTA.
+//
+// The epilogue is bound by instruction issue (16 warps on 4 schedulers; ~2.5 instructions per element
+// are the floor: IADD/I2F, half a packed FADD2, half a packed FMUL2, half an F2IP), so everything that
+// is not per-element work is hoisted: shared-memory addresses are 32-bit and advanced by constants, the
+// static geometries always stage 1-byte output and always use ONE offset-magic constant K.
+template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe, bool kPair, class Bar>
+__device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Bar* bar, uint32_t tmem, int warp, int lane,
+                                              int n_local, int tile0, int tile_stride) {
+  const Geo<G> g{p};
+  const uint32_t sbase = smem_u32(smem);
+  const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+  const int cbi = (warp - kEpiWarp0) >> 2;      // this warp takes column blocks cbi, cbi + 4, ...
+  const int m4 = lane & 3, r8 = lane >> 2;      // position inside the row-pair fragment
+  const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+  const float* sb0 = reinterpret_cast<const float*>(smem + p.off_bias0);
+  const float* ss0 = reinterpret_cast<const float*>(smem + p.off_scale0);
+  const float* sb1 = reinterpret_cast<const float*>(smem + p.off_bias1);
+  const float* ss1 = reinterpret_cast<const float*>(smem + p.off_scale1);
+  const int* sk1 = reinterpret_cast<const int*>(smem + p.off_k1);
+  constexpr int ts = (kDst == DF_F32 || kDst == DF_S32) ? 4 : 1;
+  const uint32_t swz_mask1 = (uint32_t)(g.swb1() / 16 - 1);
+  const bool relu1 = p.relu1 != 0;
+  const bool fast1 = G::is_static ? true : (p.fast1 != 0);
+  const int k_uni = p.k1_uniform;  // static geometries: never 0 (df_conv_create)
+  const int q_first = 2 * p.Wp;
+  // staged output (1-byte destinations, see store_staged_chunk): always for the static geometries
+  constexpr bool kCanStage = (kDst == DF_U8 || kDst == DF_S8);
+  const bool staged = kCanStage && (G::is_static || p.stage_out != 0);
+  // where this thread's four rows (ri = 2 * h16 + hl -> tile row quarter * 32 + 8 * ri + r8) of the
+  // current tile go: staging row (staged) or NHW pixel index (direct); -1 for padding positions
+  int row_it = -1, rinfo[4];
+  const int m_row0 = quarter * 32 + r8;
+  // position bookkeeping is spread over the warp: lane l tracks tile row quarter * 32 + l and the four
+  // rows a thread needs come by shuffle from lanes r8, r8 + 8, r8 + 16, r8 + 24
+  PosState pos_tile = pos_of(p, q_first + tile0 * kTileM);                         // first position of the current tile
+  PosState pos_lane = pos_of(p, q_first + tile0 * kTileM + quarter * 32 + lane);   // this lane's row of it
+
+  // arrive targets (buffer i of a pair of barriers sits 8 bytes after buffer 0)
+  uint32_t a_acc0_empty = smem_u32(&bar->acc0_empty[0]), a_acc1_empty = smem_u32(&bar->acc1_empty[0]);
+  uint32_t a_mid_full = smem_u32(&bar->mid_full[0]);
+  if constexpr (kPair) {
+    a_acc0_empty = mapa_u32(a_acc0_empty, 0);
+    a_acc1_empty = mapa_u32(a_acc1_empty, 0);
+    a_mid_full = mapa_u32(a_mid_full, 0);
+  }
+  auto arrive = [&](uint32_t a) {
+    if constexpr (kPair) mbar_arrive_cluster(a);
+    else mbar_arrive(a);
+  };
+  Tracer tr(p, 3);
+  if (threadIdx.x != kEpiWarp0 * 32) tr.base = nullptr;
+
+  // ---- conv0 epilogue of local tile `it`
+  auto unit_e0 = [&](int it) {
+    const int ab = it % g.n_acc0();
+    mbar_wait_warp(smem_u32(&bar->mid_empty[0]), (it & 1) ^ 1);
+    mbar_wait_warp(smem_u32(&bar->acc0_full[ab]), (it / g.n_acc0()) & 1);
+    tc_fence_after_sync();
+    tr.ev(30);
+    const uint32_t mid = sbase + p.off_mid;
+    const uint32_t t_base = lane_addr + ab * g.OC();
+    const int nb32 = g.OC() / 32, nblk = nb32 + (g.OC() - nb32 * 32) / 16;
+    auto block = [&](auto ch_c, int col0, bool last) {
+      constexpr int CH = decltype(ch_c)::value;
+      const int ch0 = col0 + CH * m4;  // this thread's CH consecutive conv0 channels
+      uint32_t acc[2][2 * CH];
+      tmem_ld_frag<CH>(t_base + col0, acc[0]);
+      tmem_ld_frag<CH>(t_base + (16u << 16) + col0, acc[1]);
+      float4 b4[CH / 4], s4[CH / 4];
+#pragma unroll
+      for (int i = 0; i < CH / 4; ++i) {
+        b4[i] = *reinterpret_cast<const float4*>(sb0 + ch0 + 4 * i);
+        s4[i] = *reinterpret_cast<const float4*>(ss0 + ch0 + 4 * i);
+      }
+      const int kb = ch0 / g.swb1();
+      // byte offset of (row m_row0, channel ch0) inside the K-block, before the swizzle
+      const uint32_t off0 = (uint32_t)m_row0 * g.swb1() + (uint32_t)(ch0 - kb * g.swb1());
+      const uint32_t mid_kb = mid + kb * g.mid_kb_stride();
+      tmem_ld_wait();
+      if (last) {  // accumulator is in registers: the tensor pipe may overwrite it
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) arrive(a_acc0_empty + 8 * ab);
+      }
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri) {
+        uint32_t v[CH], packed[CH / 4];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = acc[ri >> 1][4 * (i / 2) + 2 * (ri & 1) + (i & 1)];
+        uint32_t off = off0 + (uint32_t)(ri * 8) * g.swb1();
+        off ^= ((off >> 7) & swz_mask1) << 4;  // Swizzle<B,4,3> on the (1024 B aligned) block offset
+        finish_conv0<kDown0, kNanSafe, CH>(v, b4, s4, packed);
+        sts_bytes<CH>(mid_kb + off, packed);
+      }
+    };
+    bool released = false;
+    for (int b = cbi; b < nblk; b += 4) {
+      const bool last = b + 4 >= nblk;
+      released |= last;
+      if (b < nb32) block(std::integral_constant<int, 8>{}, b * 32, last);
+      else block(std::integral_constant<int, 4>{}, nb32 * 32, last);
+    }
+    if (!released) {  // warps without a block in this unit
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) arrive(a_acc0_empty + 8 * ab);
+    }
+    fence_proxy_async_smem();  // intermediate tile -> visible to the tensor pipe (async proxy)
+    __syncwarp();
+    if (lane == 0) arrive(a_mid_full);
+    tr.ev(31);
+  };
+
+  // ---- conv1 chunk j of local tile `it` (c = global chunk counter of this CTA)
+  auto unit_c = [&](int it, int j, uint32_t c) {
+    if (row_it != it) {  // tiles come in order: it == row_it + 1
+      if (row_it >= 0) {
+        pos_step(p, pos_tile, p.ts_dw, p.ts_dn, p.ts_dh);
+        pos_step(p, pos_lane, p.ts_dw, p.ts_dn, p.ts_dh);
+      }
+      row_it = it;
+      int rr = pos_pixel(p, pos_lane);
+      if (rr >= 0 && staged) {
+        rr -= pos_valid_before(p, pos_tile);
+        // byte offset of the staging row's 16-byte unit 0 after the swizzle, row * 128 + ((row & 7) << 4);
+        // unit u of the row then sits at this value XOR (u << 4)
+        rr = rr * 128 + ((rr & 7) << 4);
+      }
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri) rinfo[ri] = __shfl_sync(0xffffffffu, rr, r8 + 8 * ri);
+    }
+    const int cb = c & 1;
+    tr.ev(36);
+    if (staged)  // chunk c - 2 must have left this staging buffer
+      mbar_wait_warp(smem_u32(&bar->stage_empty[cb]), ((c >> 1) & 1) ^ 1);
+    tr.ev(34);
+    mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c >> 1) & 1);
+    tc_fence_after_sync();
+    tr.ev(32);
+    int ncols = g.OC1() - j * g.nc1();  // real columns in this chunk
+    if (ncols > g.nc1()) ncols = g.nc1();
+    const uint32_t t_base = lane_addr + kAcc1Col + cb * kAcc1Stride;
+    const uint32_t stage_buf = sbase + p.off_stage + cb * kStageBytes;
+    const int nb32 = ncols / 32, nblk = nb32 + (ncols - nb32 * 32) / 16;
+    auto block = [&](auto ch_c, auto unik_c, int col0, bool last) {
+      constexpr int CH = decltype(ch_c)::value;
+      constexpr bool kUniK = decltype(unik_c)::value;
+      const int ccol = col0 + CH * m4;      // first of this thread's CH channels inside the chunk
+      const int ch0 = j * g.nc1() + ccol;   // ... and as conv1 output channel
+      uint32_t acc[2][2 * CH];
+      tmem_ld_frag<CH>(t_base + col0, acc[0]);
+      tmem_ld_frag<CH>(t_base + (16u << 16) + col0, acc[1]);
+      float4 c4[CH / 4], s4[CH / 4];
+      int4 k4[kUniK ? 1 : CH / 4];
+#pragma unroll
+      for (int i = 0; i < CH / 4; ++i) {
+        c4[i] = *reinterpret_cast<const float4*>(sb1 + ch0 + 4 * i);
+        s4[i] = *reinterpret_cast<const float4*>(ss1 + ch0 + 4 * i);
+        if constexpr (!kUniK) k4[i] = *reinterpret_cast<const int4*>(sk1 + ch0 + 4 * i);
+      }
+      // where the four rows go, computed while the TMEM loads are in flight and pinned in registers (left
+      // to itself the compiler re-derives every address from the kernel parameters inside the row loop,
+      // and the epilogue is bound by instruction issue)
+      uint32_t saddr[4];
+      if constexpr (ts == 1) {
+        const uint32_t unit_x = ((uint32_t)ccol >> 4) << 4, stage_col = stage_buf + ((uint32_t)ccol & 15);
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri) {
+          saddr[ri] = stage_col + ((uint32_t)rinfo[ri] ^ unit_x);
+          asm volatile("" : "+r"(saddr[ri]));
+        }
+      }
+      tmem_ld_wait();
+      if (last) {  // accumulator is in registers: the tensor pipe may overwrite it
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) arrive(a_acc1_empty + 8 * cb);
+      }
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri) {
+        const int rr = rinfo[ri];
+        if (rr >= 0) {
+          uint32_t v[CH], w[ts == 1 ? CH / 4 : CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = acc[ri >> 1][4 * (i / 2) + 2 * (ri & 1) + (i & 1)];
+          finish_conv1<kDst, kDown1, kNanSafe, CH, kUniK>(v, c4, s4, k4, k_uni, fast1, relu1, w);
+          if constexpr (ts == 1) {
+            if (staged) {  // 16-byte unit XOR row-inside-the-1024-B-atom, as SWIZZLE_128B wants
+              sts_bytes<CH>(saddr[ri], w);
+            } else {
+              uint8_t* out = static_cast<uint8_t*>(p.dst) + (size_t)rr * g.OC1() + ch0;
+              if constexpr (CH == 8) *reinterpret_cast<uint2*>(out) = make_uint2(w[0], w[1]);
+              else *reinterpret_cast<uint32_t*>(out) = w[0];
+            }
+          } else {
+            uint4* out = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.dst) + ((size_t)rr * g.OC1() + ch0) * 4);
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) out[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          }
+        }
+      }
+    };
+    bool released = false;
+    for (int b = cbi; b < nblk; b += 4) {
+      const bool last = b + 4 >= nblk;
+      released |= last;
+      if (G::is_static || k_uni != 0) {
+        if (b < nb32) block(std::integral_constant<int, 8>{}, std::true_type{}, b * 32, last);
+        else block(std::integral_constant<int, 4>{}, std::true_type{}, nb32 * 32, last);
       } else {
-        v = make_uint4((uint32_t)cvt_x86<kDown>(t[0]), (uint32_t)cvt_x86<kDown>(t[1]), (uint32_t)cvt_x86<kDown>(t[2]),
-                       (uint32_t)cvt_x86<kDown>(t[3]));
+        if (b < nb32) block(std::integral_constant<int, 8>{}, std::false_type{}, b * 32, last);
+        else block(std::integral_constant<int, 4>{}, std::false_type{}, nb32 * 32, last);
       }
-      reinterpret_cast<uint4*>(out)[g] = v;
     }
-  }
-  if (kDst == DF_U8 || kDst == DF_S8) *reinterpret_cast<uint4*>(out) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-}
+    if (!released) {
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) arrive(a_acc1_empty + 8 * cb);
+    }
+    tr.ev(35);
+    if (staged) {
+      fence_proxy_async_smem();  // this thread's staging writes -> visible to the TMA unit
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar->stage_full[cb]));
+    }
+    tr.ev(33);
+  };
 
-// Per-channel epilogue constants of the static geometries travel as a by-value kernel parameter, i.e.
-// they sit in the constant bank.  With compile-time column indices (the static epilogue is fully
-// unrolled) every FADD / FMUL / IADD takes its constant as an immediate c[0][off] operand and no load
-// instruction is issued at all.  Broadcast LDS of the same values tops out at ~1.8 constants/clk/SM
-// (probe/lds_bcast.cu, profiles/r01_lds_broadcast_vs_constbank.log), which capped the epilogue at
-// ~19 elements/clk/SM -- below what the tensor pipe produces.
-template <class G>
-struct EpiConsts {
-  float bias0[G::OC], scale0[G::OC];
-  int k1[G::n_chunks * G::nc1];
-  float c1[G::n_chunks * G::nc1], scale1[G::n_chunks * G::nc1];
-};
-struct EpiConstsNone {
-  int unused;
-};
-template <class G, bool kStatic = G::is_static>
-struct EpiConstsOf {
-  using type = EpiConstsNone;
-};
-template <class G>
-struct EpiConstsOf<G, true> {
-  using type = EpiConsts<G>;
-};
-
-template <int N, class F, int I = 0>
-__device__ __forceinline__ void static_for(F&& f) {
-  if constexpr (I < N) {
-    f(std::integral_constant<int, I>{});
-    static_for<N, F, I + 1>(static_cast<F&&>(f));
+  // ---- the unit stream (see above), identical in every epilogue warp
+  const int nch = g.n_chunks();
+  uint32_t c = 0;
+  if (n_local > 0) unit_e0(0);
+  for (int it = 0; it < n_local; ++it) {
+    for (int j = 0; j < nch; ++j, ++c) {
+      if (j == nch - 1 && it + 1 < n_local) unit_e0(it + 1);
+      unit_c(it, j, c);
+    }
   }
 }
 
-// conv0, static geometry: 16 columns starting at compile-time column kCol0 -> 16 bytes of u8
-template <class G>
-__device__ __forceinline__ uint4 requant16_static0(const uint32_t* acc, const EpiConsts<G>& ec, int kCol0) {
-  uint32_t w[4];
-#pragma unroll
-  for (int g4 = 0; g4 < 4; ++g4) {
-    float t[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int col = kCol0 + g4 * 4 + i;
-      t[i] = __fmul_rn(__fadd_rn(__int2float_rn((int)acc[g4 * 4 + i]), ec.bias0[col]), ec.scale0[col]);
-    }
-    w[g4] = pack_u8x4<false, false>(t);
-  }
-  return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// conv1, static geometry, offset-magic conversion: 16 columns from compile-time column kCol0
-template <class G, int kDst>
-__device__ __forceinline__ void store16_static1(const uint32_t* acc, const EpiConsts<G>& ec, int kCol0, bool relu,
-                                                uint8_t* out) {
-  uint32_t packed[4];
-#pragma unroll
-  for (int g4 = 0; g4 < 4; ++g4) {
-    float t[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int col = kCol0 + g4 * 4 + i;
-      const float f = __int_as_float((int)acc[g4 * 4 + i] + ec.k1[col]);  // == 2^23 + (acc - lo[col]) exactly
-      t[i] = __fmul_rn(__fadd_rn(f, ec.c1[col]), ec.scale1[col]);
-    }
-    if (kDst == DF_U8) {
-      packed[g4] = pack_u8x4<false, false>(t);
-    } else if (kDst == DF_S8) {
-      packed[g4] = pack_s8x4<false>(t, relu);
-    } else {
-      if (relu) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) t[i] = relu_x86(t[i]);
-      }
-      uint4 v;
-      if (kDst == DF_F32) {
-        v = make_uint4(__float_as_uint(t[0]), __float_as_uint(t[1]), __float_as_uint(t[2]), __float_as_uint(t[3]));
-      } else {
-        v = make_uint4((uint32_t)cvt_x86<false>(t[0]), (uint32_t)cvt_x86<false>(t[1]), (uint32_t)cvt_x86<false>(t[2]),
-                       (uint32_t)cvt_x86<false>(t[3]));
-      }
-      reinterpret_cast<uint4*>(out)[g4] = v;
+// ---- store thread of the staged output path (one elected thread of warp 3): sends every staged conv1
+// chunk to the destination (store_staged_chunk) in the order the epilogue produces them
+template <class G, class Bar>
+__device__ __forceinline__ void store_role(const Params& p, const DstMaps& tmD, Bar* bar, uint32_t sbase, int n_local,
+                                           int tile0, int tile_stride) {
+  const Geo<G> g{p};
+  const int q_first = 2 * p.Wp;
+  Tracer tr(p, 2);
+  uint32_t c = 0;
+  for (int it = 0; it < n_local; ++it) {
+    const int q0 = q_first + (tile0 + it * tile_stride) * kTileM;
+    const int f0 = valid_before(p, q0), V = valid_before(p, q0 + kTileM) - f0;
+    for (int j = 0; j < g.n_chunks(); ++j, ++c) {
+      const uint32_t cb = c & 1;
+      mbar_wait(smem_u32(&bar->stage_full[cb]), (c >> 1) & 1);
+      tr.ev(40);
+      store_staged_chunk(tmD, sbase + p.off_stage + cb * kStageBytes, f0, V, j * g.nc1());
+      tr.ev(41);
+      bulk_wait_read_all();
+      tr.ev(42);
+      mbar_arrive(smem_u32(&bar->stage_empty[cb]));
     }
   }
-  if (kDst == DF_U8 || kDst == DF_S8) *reinterpret_cast<uint4*>(out) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-}
-
-template <int kCols>
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
-  if constexpr (kCols == 32) tmem_ld_x32(taddr, r);
-  else tmem_ld_x16(taddr, r);
+  bulk_wait_all();  // the staging buffers must outlive the last TMA stores
 }
 
 // ------------------------------------------------------------------------------- the kernel
 template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
-                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ Params p,
-                  const __grid_constant__ typename EpiConstsOf<G>::type ec) {
+                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ DstMaps tmD,
+                  const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // align in the shared address space (keeps LDS/STS instead of generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -403,6 +726,8 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(smem_u32(&bar->mid_empty[i]), 1);
       mbar_init(smem_u32(&bar->acc1_full[i]), 1);
       mbar_init(smem_u32(&bar->acc1_empty[i]), kEpiWarps);
+      mbar_init(smem_u32(&bar->stage_full[i]), kEpiWarps);
+      mbar_init(smem_u32(&bar->stage_empty[i]), 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -410,7 +735,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmW1);
   }
   if (warp == 3) tmem_alloc<512>(smem_u32(&bar->tmem_base));
-  if constexpr (!G::imm_consts) {
+  {
     // per-channel f32 bias / scale vectors -> smem (read by every epilogue thread)
     float* sb0 = reinterpret_cast<float*>(smem + p.off_bias0);
     float* ss0 = reinterpret_cast<float*>(smem + p.off_scale0);
@@ -529,14 +854,13 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       Tracer tr(p, 1);
       tr.ev(9);
 
-      // ---- one tap row (kh) of GEMM1: 3 taps x K-blocks, descriptors by addition, weights in order
-      auto gemm1_row = [&](int kh, uint32_t d_tmem, uint64_t a_tile) {
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
+      // ---- taps [kw0, kw1) of tap row kh of GEMM1: K-blocks x K-steps each, descriptors by addition,
+      //      weights in order
+      auto gemm1_taps = [&](int kh, int kw0, int kw1, uint32_t d_tmem, uint64_t a_tile) {
+        for (int kw = kw0; kw < kw1; ++kw) {
 #pragma unroll
           for (int kb = 0; kb < g.nkb(); ++kb) {
-            const int blk_in_row = kw * g.nkb() + kb;      // compile-time inside the row
-            const int blk = kh * 3 * g.nkb() + blk_in_row;  // block index inside the tile
+            const int blk = (kh * 3 + kw) * g.nkb() + kb;  // block index inside the tile
             uint64_t b_desc;
             uint32_t st = 0;
             if (g.w0_res()) {
@@ -588,9 +912,10 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // Readiness-driven issue.  With W1 resident only GEMM1 consumes the weight ring, so the two
         // GEMM streams are independent: issue a GEMM2 chunk whenever its accumulator is free and the
         // intermediate tile is there (it unblocks the epilogue, the longer path), otherwise the next
-        // tap row of the next GEMM1.  A fixed order suffers head-of-line blocking in both directions
+        // TAP of the next GEMM1 (a whole tap row queued in front of a chunk leaves the epilogue idle for
+        // longer than the chunk takes).  A fixed order suffers head-of-line blocking in both directions
         // (profiles/r01_trace_cfg3_v4.log).
-        int g1_it = 0, g1_kh = 0, g2_it = 0, g2_j = 0;
+        int g1_it = 0, g1_kh = 0, g1_kw = 0, g2_it = 0, g2_j = 0;
         bool g2_open = false;
         uint64_t a_tile = 0;
         uint32_t d0 = 0;
@@ -629,7 +954,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (!did && g1_it < n_local) {
             bool ok = true;
-            if (g1_kh == 0) {
+            if (g1_kh == 0 && g1_kw == 0) {
               const int ab = g1_it % g.n_acc0();
               ok = mbar_test_wait(smem_u32(&bar->acc0_empty[ab]), ((g1_it / g.n_acc0()) & 1) ^ 1) &&
                    mbar_test_wait(smem_u32(&bar->a_full[sa]), a_par);
@@ -641,10 +966,14 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
             if (ok) {
-              gemm1_row(g1_kh, d0, a_tile);
+              gemm1_taps(g1_kh, g1_kw, g1_kw + 1, d0, a_tile);
               did = true;
               idle = 0;
-              if (++g1_kh == 3) {
+              if (++g1_kw == 3) {
+                g1_kw = 0;
+                ++g1_kh;
+              }
+              if (g1_kh == 3) {
                 umma_commit(smem_u32(&bar->a_empty[sa]));
                 umma_commit(smem_u32(&bar->acc0_full[g1_it % g.n_acc0()]));
                 tr.ev(11);
@@ -669,7 +998,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t d_tmem = tmem + ab * g.OC();
             const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swb()) >> 4);
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) gemm1_row(kh, d_tmem, a_tile);
+            for (int kh = 0; kh < 3; ++kh) gemm1_taps(kh, 0, 3, d_tmem, a_tile);
             umma_commit(smem_u32(&bar->a_empty[sa]));
             umma_commit(smem_u32(&bar->acc0_full[ab]));
             tr.ev(11);
@@ -698,187 +1027,12 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= kEpiWarp0) {
     // ====================================== epilogue =======================================
-    // Work units: E0(t) = conv0 epilogue of tile t (TMEM acc0 -> u8 tile in smem) and C_j(t) = conv1
-    // chunk j of tile t (TMEM acc1 -> global).  The kEpiGroups groups of 8 warps take alternate
-    // units of one common stream, so two units are in flight at any time; with epi_ahead the stream
-    // runs E0(t+1) before C_*(t) so that GEMM2(t) is never waiting for the epilogue it feeds.
-    // Inside a unit the two warps sharing a TMEM lane quarter take alternate column groups of
-    // GC = 32 (16 when the channel counts are not multiples of 64).
-    constexpr bool kWide = G::is_static;  // static shapes have OC % 64 == 0 and nc1 % 64 == 0
-    constexpr int GC = kWide ? 32 : 16;
-    const int ew = warp - kEpiWarp0;
-    const int group = ew / kEpiWarps;
-    const int quarter = warp & 3;               // TMEM lane quarter this warp may read
-    const int half = (ew % kEpiWarps) >> 2;     // which half of the column groups
-    const int m = quarter * 32 + lane;          // tile row = TMEM lane
-    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    const float* sb0 = reinterpret_cast<const float*>(smem + p.off_bias0);
-    const float* ss0 = reinterpret_cast<const float*>(smem + p.off_scale0);
-    const float* sb1 = reinterpret_cast<const float*>(smem + p.off_bias1);
-    const float* ss1 = reinterpret_cast<const float*>(smem + p.off_scale1);
-    const int* sk1 = reinterpret_cast<const int*>(smem + p.off_k1);
-    constexpr int ts = (kDst == DF_F32 || kDst == DF_S32) ? 4 : 1;
-    const uint32_t swz_mask1 = (uint32_t)(g.swb1() / 16 - 1);
-    const bool relu1 = p.relu1 != 0;
-    const bool fast1 = G::is_static ? true : (p.fast1 != 0);
-    Tracer tr(p, 3);
-    if (threadIdx.x != kEpiWarp0 * 32) tr.base = nullptr;
-
-    // ---- conv0 epilogue of local tile `it`
-    auto unit_e0 = [&](int it) {
-      const int ab = it % g.n_acc0(), mb = it % p.NM;
-      mbar_wait_warp(smem_u32(&bar->mid_empty[mb]), ((it / p.NM) & 1) ^ 1);
-      mbar_wait_warp(smem_u32(&bar->acc0_full[ab]), (it / g.n_acc0()) & 1);
-      tc_fence_after_sync();
-      tr.ev(30);
-      uint8_t* mid = smem + p.off_mid + mb * p.mid_bytes;
-      const int ngr = g.OC() / GC;
-      const uint32_t t_base = lane_addr + ab * g.OC();
-      if constexpr (G::imm_consts) {
-        // compile-time columns: the constants become uniform-register / immediate operands (EpiConsts)
-        auto body = [&](auto half_c) {
-          constexpr int kHalf = decltype(half_c)::value;
-          static_for<G::OC / 64>([&](auto i_c) {
-            constexpr int gr = decltype(i_c)::value * 2 + kHalf;
-            uint32_t acc[32];
-            tmem_ld_x32(t_base + gr * 32, acc);
-            tmem_ld_wait();
-            static_for<2>([&](auto sub_c) {
-              constexpr int c16 = gr * 2 + decltype(sub_c)::value;
-              const uint4 v = requant16_static0<G>(acc + decltype(sub_c)::value * 16, ec, c16 * 16);
-              constexpr int kb = (c16 * 16) / G::swb1;
-              uint32_t off = (uint32_t)m * G::swb1 + (uint32_t)(c16 * 16 - kb * G::swb1);
-              off ^= ((off >> 7) & (uint32_t)(G::swb1 / 16 - 1)) << 4;
-              *reinterpret_cast<uint4*>(mid + kb * (kTileM * G::swb1) + off) = v;
-            });
-          });
-        };
-        if (half == 0) body(std::integral_constant<int, 0>{});
-        else body(std::integral_constant<int, 1>{});
-      } else
-#pragma unroll
-      for (int gr = half; gr < ngr; gr += 2) {
-        uint32_t acc[GC];
-        tmem_ld_cols<GC>(t_base + gr * GC, acc);
-        tmem_ld_wait();
-#pragma unroll
-        for (int sub = 0; sub < GC / 16; ++sub) {
-          const int c16 = gr * (GC / 16) + sub;  // 16-column (= 16-byte) unit
-          const float4* b4 = reinterpret_cast<const float4*>(sb0 + c16 * 16);
-          auto s4 = [&](int i) -> float4 {
-            if constexpr (G::is_static) {  // scales through the constant bank, biases through smem
-              const int c0 = c16 * 16 + i * 4;
-              return make_float4(ec.scale0[c0], ec.scale0[c0 + 1], ec.scale0[c0 + 2], ec.scale0[c0 + 3]);
-            } else {
-              return load_scale4(ss0 + c16 * 16 + i * 4);
-            }
-          };
-          uint4 v;
-          v.x = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 0, b4[0], s4(0));
-          v.y = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 4, b4[1], s4(1));
-          v.z = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 8, b4[2], s4(2));
-          v.w = requant_u8x4<kDown0, kNanSafe>(acc + sub * 16 + 12, b4[3], s4(3));
-          const int kb = (c16 * 16) / g.swb1();
-          uint32_t off = (uint32_t)m * g.swb1() + (uint32_t)(c16 * 16 - kb * g.swb1());
-          off ^= ((off >> 7) & swz_mask1) << 4;  // Swizzle<B,4,3> on the (1024 B aligned) block offset
-          *reinterpret_cast<uint4*>(mid + kb * g.mid_kb_stride() + off) = v;
-        }
-      }
-      tc_fence_before_sync();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(smem_u32(&bar->acc0_empty[ab]));
-        mbar_arrive(smem_u32(&bar->mid_full[mb]));
-      }
-      tr.ev(31);
-    };
-
-    // ---- conv1 chunk j of local tile `it` (c = global chunk counter of this CTA)
-    auto unit_c = [&](int it, int j, uint32_t c) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int q = q_first + tile * kTileM + m;  // where does this row go?
-      const int gq = q / p.Wp, wq = q - gq * p.Wp;
-      const int n = (gq - 1) / p.Hp, hp = (gq - 1) - n * p.Hp;
-      const bool valid = (wq < p.W) && (hp >= 1) && (n < p.N);
-      uint8_t* out_row = static_cast<uint8_t*>(p.dst) + ((size_t)(n * p.H + hp - 1) * p.W + wq) * g.OC1() * ts;
-      const int cb = c & 1;
-      mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c >> 1) & 1);
-      tc_fence_after_sync();
-      tr.ev(32);
-      int ncols = g.OC1() - j * g.nc1();  // real columns in this chunk
-      if (ncols > g.nc1()) ncols = g.nc1();
-      const int ngr = ncols / GC;
-      const uint32_t t_base = lane_addr + kAcc1Col + cb * kAcc1Stride;
-      if constexpr (G::imm_consts) {
-        // compile-time chunk and columns: the constants become uniform-register / immediate operands
-        auto body = [&](auto j_c, auto half_c) {
-          constexpr int kJ = decltype(j_c)::value, kHalf = decltype(half_c)::value;
-          static_for<G::nc1 / 64>([&](auto i_c) {
-            constexpr int gr = decltype(i_c)::value * 2 + kHalf;
-            uint32_t acc[32];
-            tmem_ld_x32(t_base + gr * 32, acc);
-            tmem_ld_wait();
-            if (valid) {
-              static_for<2>([&](auto sub_c) {
-                constexpr int col = kJ * G::nc1 + gr * 32 + decltype(sub_c)::value * 16;
-                store16_static1<G, kDst>(acc + decltype(sub_c)::value * 16, ec, col, relu1, out_row + (size_t)col * ts);
-              });
-            }
-          });
-        };
-        static_for<G::n_chunks>([&](auto j_c) {
-          if (j == decltype(j_c)::value) {
-            if (half == 0) body(j_c, std::integral_constant<int, 0>{});
-            else body(j_c, std::integral_constant<int, 1>{});
-          }
-        });
-      } else
-#pragma unroll
-      for (int gr = half; gr < ngr; gr += 2) {
-        uint32_t acc[GC];
-        tmem_ld_cols<GC>(t_base + gr * GC, acc);
-        tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int sub = 0; sub < GC / 16; ++sub) {
-            const int col = j * g.nc1() + gr * GC + sub * 16;
-            auto s4 = [&](int i) -> float4 {
-              if constexpr (G::is_static) {
-                const int c0 = col + i * 4;
-                return make_float4(ec.scale1[c0], ec.scale1[c0 + 1], ec.scale1[c0 + 2], ec.scale1[c0 + 3]);
-              } else {
-                return load_scale4(ss1 + col + i * 4);
-              }
-            };
-            if (fast1)
-              store16<kDst, kDown1, kNanSafe, true>(acc + sub * 16, sb1 + col, sk1 + col, p.k1_uniform, s4, relu1, out_row + (size_t)col * ts);
-            else
-              store16<kDst, kDown1, kNanSafe, false>(acc + sub * 16, sb1 + col, sk1 + col, 0, s4, relu1, out_row + (size_t)col * ts);
-          }
-        }
-      }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar->acc1_empty[cb]));
-      tr.ev(33);
-    };
-
-    // ---- the unit stream, identical in every epilogue warp; group u % kEpiGroups executes unit u
-    uint32_t u = 0, c = 0;
-    const int ahead = p.epi_ahead;
-    if (ahead && n_local > 0) {
-      if ((u++ % kEpiGroups) == (uint32_t)group) unit_e0(0);
-    }
-    for (int it = 0; it < n_local; ++it) {
-      if (ahead) {
-        if (it + 1 < n_local && (u++ % kEpiGroups) == (uint32_t)group) unit_e0(it + 1);
-      } else {
-        if ((u++ % kEpiGroups) == (uint32_t)group) unit_e0(it);
-      }
-      for (int j = 0; j < g.n_chunks(); ++j, ++c)
-        if ((u++ % kEpiGroups) == (uint32_t)group) unit_c(it, j, c);
-    }
+    epilogue_role<G, kDst, kDown0, kDown1, kNanSafe, false>(p, smem, bar, tmem, warp, lane, n_local, (int)blockIdx.x,
+                                                            (int)gridDim.x);
+  } else if (warp == 3) {
+    // ================================ store thread (staged output) ==========================
+    if ((kDst == DF_U8 || kDst == DF_S8) && p.stage_out && elect_one())
+      store_role<G>(p, tmD, bar, sbase, n_local, (int)blockIdx.x, (int)gridDim.x);
   }
 
   tc_fence_before_sync();
@@ -901,18 +1055,19 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // always lands at the same shared-memory offset.
 struct PairBarriers {
   uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
-  uint64_t res_full, peer_ready;
+  uint64_t res_full[4], peer_ready[4];  // resident weights arrive in four parts: W0 tap rows 0..2, W1
   uint64_t acc0_full[2], acc0_empty[2];
   uint64_t mid_full[2], mid_empty[2];
   uint64_t acc1_full[2], acc1_empty[2];
+  uint64_t stage_full[2], stage_empty[2];
   uint32_t tmem_base;
 };
 
 template <class G, int kDst>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
-                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ Params p,
-                 const __grid_constant__ EpiConsts<G> ec) {
+                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ DstMaps tmD,
+                 const __grid_constant__ Params p) {
   static_assert(G::is_static && G::n_acc0 == 2 && G::nc1 == 128 && G::OC % 64 == 0, "pair kernel: unsupported geometry");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -932,8 +1087,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&bar->a_full[i]), 2);  // one expect_tx arrival per CTA of the pair
       mbar_init(smem_u32(&bar->a_empty[i]), 1);
     }
-    mbar_init(smem_u32(&bar->res_full), 1);
-    mbar_init(smem_u32(&bar->peer_ready), 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(smem_u32(&bar->res_full[i]), 1);
+      mbar_init(smem_u32(&bar->peer_ready[i]), 1);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar->acc0_full[i]), 1);
       mbar_init(smem_u32(&bar->acc0_empty[i]), 2 * kEpiWarps);
@@ -941,6 +1098,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&bar->mid_empty[i]), 1);
       mbar_init(smem_u32(&bar->acc1_full[i]), 1);
       mbar_init(smem_u32(&bar->acc1_empty[i]), 2 * kEpiWarps);
+      mbar_init(smem_u32(&bar->stage_full[i]), kEpiWarps);
+      mbar_init(smem_u32(&bar->stage_empty[i]), 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -950,11 +1109,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 3) tmem_alloc_pair<512>(smem_u32(&bar->tmem_base));
   {
     float* sb0 = reinterpret_cast<float*>(smem + p.off_bias0);
+    float* ss0 = reinterpret_cast<float*>(smem + p.off_scale0);
     float* sb1 = reinterpret_cast<float*>(smem + p.off_bias1);
+    float* ss1 = reinterpret_cast<float*>(smem + p.off_scale1);
     int* sk1 = reinterpret_cast<int*>(smem + p.off_k1);
-    for (int i = threadIdx.x; i < G::OC; i += kThreads) sb0[i] = p.bias0[i];
+    for (int i = threadIdx.x; i < G::OC; i += kThreads) {
+      sb0[i] = p.bias0[i];
+      ss0[i] = p.scale0[i];
+    }
     for (int i = threadIdx.x; i < G::OC1; i += kThreads) {
       sb1[i] = p.bias1[i];
+      ss1[i] = p.scale1[i];
       sk1[i] = p.k1[i];
     }
   }
@@ -1001,226 +1166,113 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 2) {
     // ============================ resident weight halves (both CTAs) ===========================
     if (elect_one()) {
-      const uint32_t full = smem_u32(&bar->res_full);
-      mbar_expect_tx(full, kNW0 * kW0Half + kNW1 * kW1Half);
-      for (int b = 0; b < kNW0; ++b) tma_load_2d(sbase + p.off_w0 + b * kW0Half, &tmW0, full, 0, b * G::OC + (int)rank * kHalfRows0);
-      for (int b = 0; b < kNW1; ++b) tma_load_2d(sbase + p.off_w1 + b * kW1Half, &tmW1, full, 0, b * G::nc1 + (int)rank * kHalfRows1);
-      mbar_wait(full, 0);
-      if (rank == 1) mbar_arrive_cluster(mapa_u32(smem_u32(&bar->peer_ready), 0));
+      // four parts with their own barriers, so that GEMM1 of the first tile starts after a third of W0
+      constexpr int kRowBlocks = 3 * G::nkb;
+      for (int part = 0; part < 3; ++part) {
+        const uint32_t full = smem_u32(&bar->res_full[part]);
+        mbar_expect_tx(full, kRowBlocks * kW0Half);
+        for (int b = part * kRowBlocks; b < (part + 1) * kRowBlocks; ++b)
+          tma_load_2d(sbase + p.off_w0 + b * kW0Half, &tmW0, full, 0, b * G::OC + (int)rank * kHalfRows0);
+      }
+      {
+        const uint32_t full = smem_u32(&bar->res_full[3]);
+        mbar_expect_tx(full, kNW1 * kW1Half);
+        for (int b = 0; b < kNW1; ++b) tma_load_2d(sbase + p.off_w1 + b * kW1Half, &tmW1, full, 0, b * G::nc1 + (int)rank * kHalfRows1);
+      }
+      for (int part = 0; part < 4; ++part) {
+        mbar_wait(smem_u32(&bar->res_full[part]), 0);
+        if (rank == 1) mbar_arrive_cluster(mapa_u32(smem_u32(&bar->peer_ready[part]), 0));
+      }
+      // ============================== GEMM2 issuer (leader only) ==============================
+      // Its own thread, so that a conv1 chunk -- the thing the epilogue is waiting for -- is issued the
+      // moment its accumulator is free, instead of after whatever GEMM1 work a single scheduler thread
+      // happens to be in the middle of (a polling scheduler spent ~110 cycles per MMA on issue and left
+      // the tensor pipe idle: profiles/r01_trace_cfg3_v8.log).
+      if (rank == 0) {
+        const uint32_t idesc1 = make_idesc_i8(2 * kTileM, G::nc1, 0, 1);
+        const uint64_t desc1_hi = make_smem_desc(0, 16, 8 * G::swb1, layout_of(G::swb1));
+        const uint64_t w1_desc = desc1_hi | ((sbase + p.off_w1) >> 4);
+        const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid) >> 4);
+        Tracer tr(p, 1);
+        mbar_wait(smem_u32(&bar->peer_ready[3]), 0);
+        uint32_t c = 0;
+        for (int it = 0; it < n_local; ++it) {
+          mbar_wait(smem_u32(&bar->mid_full[0]), it & 1);
+          tr.ev(12);
+#pragma unroll
+          for (int j = 0; j < G::n_chunks; ++j, ++c) {
+            const uint32_t cb = c & 1;
+            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
+#pragma unroll
+            for (int kb = 0; kb < G::nkb1; ++kb) {
+              const uint64_t b_desc = w1_desc + (uint64_t)((j * G::nkb1 + kb) * (kW1Half >> 4));
+              const uint64_t a_desc = mid_desc + kb * ((kTileM * G::swb1) >> 4);
+              constexpr int nks_full = G::swb1 >> 5;
+              const int nks = (kb == G::nkb1 - 1) ? G::ks1_last : nks_full;
+#pragma unroll
+              for (int ks = 0; ks < nks; ++ks) umma_i8_pair(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, (kb | ks) != 0);
+            }
+            umma_commit_pair(smem_u32(&bar->acc1_full[cb]));
+            tr.ev(13);
+          }
+          umma_commit_pair(smem_u32(&bar->mid_empty[0]));
+        }
+      }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer (leader only) =================================
+    // ================================ GEMM1 issuer (leader only) ================================
     if (rank == 0 && elect_one()) {
       const uint32_t idesc0 = make_idesc_i8(2 * kTileM, G::OC, 0, 1);
-      const uint32_t idesc1 = make_idesc_i8(2 * kTileM, G::nc1, 0, 1);
       const uint64_t desc0_hi = make_smem_desc(0, 16, 8 * G::swb, layout_of(G::swb));
-      const uint64_t desc1_hi = make_smem_desc(0, 16, 8 * G::swb1, layout_of(G::swb1));
       const uint32_t a_step_kw = G::swb >> 4, a_step_kh = (p.Wp * G::swb) >> 4, a_step_kb = p.a_kb_stride >> 4;
-      const uint64_t w0_desc = desc0_hi | ((sbase + p.off_w0) >> 4), w1_desc = desc1_hi | ((sbase + p.off_w1) >> 4);
+      const uint64_t w0_desc = desc0_hi | ((sbase + p.off_w0) >> 4);
       Tracer tr(p, 1);
-      tr.ev(8);
-      mbar_wait(smem_u32(&bar->res_full), 0);
-      mbar_wait(smem_u32(&bar->peer_ready), 0);
-      tc_fence_after_sync();
       tr.ev(9);
-      uint32_t c1count = 0, sa = 0, a_par = 0;
-      int g1_it = 0, g1_kh = 0, g2_it = 0, g2_j = 0;
-      bool g2_open = false;
-      uint64_t a_tile = 0;
-      uint32_t d0 = 0;
-      uint32_t idle = 0;
-      while (g2_it < n_local) {
-        bool did = false;
-        if (++idle > (1u << 27)) {
-          printf("conv MMA scheduler stuck: block %d g1 %d/%d g2 %d/%d\n", blockIdx.x, g1_it, g1_kh, g2_it, g2_j);
-          __trap();
-        }
-        if (g2_it < g1_it) {
-          const int mb = g2_it & 1;
-          if (!g2_open && mbar_test_wait(smem_u32(&bar->mid_full[mb]), (g2_it >> 1) & 1)) g2_open = true;
-          if (g2_open) {
-            const int cb = c1count & 1;
-            if (mbar_test_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ 1)) {
-              tc_fence_after_sync();
-              const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid + mb * p.mid_bytes) >> 4);
-              const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
+      uint32_t sa = 0, a_par = 0;
+      for (int it = 0; it < n_local; ++it) {
+        const int ab = it & 1;
+        mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it >> 1) & 1) ^ 1);
+        mbar_wait(smem_u32(&bar->a_full[sa]), a_par);
+        tc_fence_after_sync();
+        tr.ev(10);
+        const uint32_t d0 = tmem + ab * G::OC;
+        const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_origin) >> 4);
 #pragma unroll
-              for (int kb = 0; kb < G::nkb1; ++kb) {
-                const uint64_t b_desc = w1_desc + (uint64_t)((g2_j * G::nkb1 + kb) * (kW1Half >> 4));
-                const uint64_t a_desc = mid_desc + kb * ((kTileM * G::swb1) >> 4);
-                constexpr int nks_full = G::swb1 >> 5;
-                const int nks = (kb == G::nkb1 - 1) ? G::ks1_last : nks_full;
+        for (int kh = 0; kh < 3; ++kh) {
+          if (it == 0) {  // first tile: this tap row's weights must have landed in both CTAs
+            mbar_wait(smem_u32(&bar->res_full[kh]), 0);
+            mbar_wait(smem_u32(&bar->peer_ready[kh]), 0);
+            tc_fence_after_sync();
+          }
 #pragma unroll
-                for (int ks = 0; ks < nks; ++ks) umma_i8_pair(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, (kb | ks) != 0);
-              }
-              umma_commit_pair(smem_u32(&bar->acc1_full[cb]));
-              tr.ev(13);
-              ++c1count;
-              did = true;
-              idle = 0;
-              if (++g2_j == G::n_chunks) {
-                umma_commit_pair(smem_u32(&bar->mid_empty[mb]));
-                g2_j = 0;
-                g2_open = false;
-                ++g2_it;
-              }
+          for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+            for (int kb = 0; kb < G::nkb; ++kb) {
+              const int blk = (kh * 3 + kw) * G::nkb + kb;
+              const uint64_t b_desc = w0_desc + (uint64_t)(blk * (kW0Half >> 4));
+              const uint64_t a_desc = a_tile + kh * a_step_kh + kw * a_step_kw + kb * a_step_kb;
+              constexpr int nks_full = G::swb >> 5;
+              const int nks = (kb == G::nkb - 1) ? G::ks_last : nks_full;
+#pragma unroll
+              for (int ks = 0; ks < nks; ++ks) umma_i8_pair(d0, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
             }
           }
         }
-        if (!did && g1_it < n_local) {
-          bool ok = true;
-          if (g1_kh == 0) {
-            const int ab = g1_it & 1;
-            ok = mbar_test_wait(smem_u32(&bar->acc0_empty[ab]), ((g1_it >> 1) & 1) ^ 1) &&
-                 mbar_test_wait(smem_u32(&bar->a_full[sa]), a_par);
-            if (ok) {
-              tc_fence_after_sync();
-              tr.ev(10);
-              d0 = tmem + ab * G::OC;
-              a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_origin) >> 4);
-            }
-          }
-          if (ok) {
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-#pragma unroll
-              for (int kb = 0; kb < G::nkb; ++kb) {
-                const int blk = (g1_kh * 3 + kw) * G::nkb + kb;
-                const uint64_t b_desc = w0_desc + (uint64_t)(blk * (kW0Half >> 4));
-                const uint64_t a_desc = a_tile + g1_kh * a_step_kh + kw * a_step_kw + kb * a_step_kb;
-                constexpr int nks_full = G::swb >> 5;
-                const int nks = (kb == G::nkb - 1) ? G::ks_last : nks_full;
-#pragma unroll
-                for (int ks = 0; ks < nks; ++ks) umma_i8_pair(d0, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
-              }
-            }
-            did = true;
-            idle = 0;
-            if (++g1_kh == 3) {
-              umma_commit_pair(smem_u32(&bar->a_empty[sa]));
-              umma_commit_pair(smem_u32(&bar->acc0_full[g1_it & 1]));
-              tr.ev(11);
-              g1_kh = 0;
-              ++g1_it;
-              if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
-            }
-          }
-        }
+        umma_commit_pair(smem_u32(&bar->a_empty[sa]));
+        umma_commit_pair(smem_u32(&bar->acc0_full[ab]));
+        tr.ev(11);
+        if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
       }
     }
   } else if (warp >= kEpiWarp0) {
     // ================================== epilogue (both CTAs) ===================================
-    const int ew = warp - kEpiWarp0;
-    const int group = ew / kEpiWarps;
-    const int quarter = warp & 3;
-    const int half = (ew % kEpiWarps) >> 2;
-    const int m = quarter * 32 + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
-    const float* sb0 = reinterpret_cast<const float*>(smem + p.off_bias0);
-    const float* sb1 = reinterpret_cast<const float*>(smem + p.off_bias1);
-    const int* sk1 = reinterpret_cast<const int*>(smem + p.off_k1);
-    constexpr int ts = (kDst == DF_F32 || kDst == DF_S32) ? 4 : 1;
-    const bool relu1 = p.relu1 != 0;
-    // the leader owns the barriers the MMA thread waits on
-    uint32_t l_acc0_empty[2], l_mid_full[2], l_acc1_empty[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      l_acc0_empty[i] = mapa_u32(smem_u32(&bar->acc0_empty[i]), 0);
-      l_mid_full[i] = mapa_u32(smem_u32(&bar->mid_full[i]), 0);
-      l_acc1_empty[i] = mapa_u32(smem_u32(&bar->acc1_empty[i]), 0);
-    }
-
-    Tracer tr(p, 3);
-    if (threadIdx.x != kEpiWarp0 * 32) tr.base = nullptr;
-    auto unit_e0 = [&](int it) {
-      const int ab = it & 1, mb = it & 1;
-      mbar_wait_warp(smem_u32(&bar->mid_empty[mb]), ((it >> 1) & 1) ^ 1);
-      mbar_wait_warp(smem_u32(&bar->acc0_full[ab]), (it >> 1) & 1);
-      tc_fence_after_sync();
-      tr.ev(30);
-      uint8_t* mid = smem + p.off_mid + mb * p.mid_bytes;
-      const uint32_t t_base = lane_addr + ab * G::OC;
-#pragma unroll
-      for (int i = 0; i < G::OC / 64; ++i) {
-        const int gr = i * 2 + half;
-        uint32_t acc[32];
-        tmem_ld_x32(t_base + gr * 32, acc);
-        tmem_ld_wait();
-#pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const int c16 = gr * 2 + sub;
-          const float4* b4 = reinterpret_cast<const float4*>(sb0 + c16 * 16);
-          auto s4 = [&](int k) -> float4 {
-            const int c0 = c16 * 16 + k * 4;
-            return make_float4(ec.scale0[c0], ec.scale0[c0 + 1], ec.scale0[c0 + 2], ec.scale0[c0 + 3]);
-          };
-          uint4 v;
-          v.x = requant_u8x4<false, false>(acc + sub * 16 + 0, b4[0], s4(0));
-          v.y = requant_u8x4<false, false>(acc + sub * 16 + 4, b4[1], s4(1));
-          v.z = requant_u8x4<false, false>(acc + sub * 16 + 8, b4[2], s4(2));
-          v.w = requant_u8x4<false, false>(acc + sub * 16 + 12, b4[3], s4(3));
-          const int kb = (c16 * 16) / G::swb1;
-          uint32_t off = (uint32_t)m * G::swb1 + (uint32_t)(c16 * 16 - kb * G::swb1);
-          off ^= ((off >> 7) & (uint32_t)(G::swb1 / 16 - 1)) << 4;
-          *reinterpret_cast<uint4*>(mid + kb * (kTileM * G::swb1) + off) = v;
-        }
-      }
-      tc_fence_before_sync();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_cluster(l_acc0_empty[ab]);
-        mbar_arrive_cluster(l_mid_full[mb]);
-      }
-      tr.ev(31);
-    };
-
-    auto unit_c = [&](int it, int j, uint32_t c) {
-      const int tile = 2 * (cid + it * ncl) + (int)rank;
-      const int q = q_first + tile * kTileM + m;
-      const int gq = q / p.Wp, wq = q - gq * p.Wp;
-      const int n = (gq - 1) / p.Hp, hp = (gq - 1) - n * p.Hp;
-      const bool valid = (wq < p.W) && (hp >= 1) && (n < p.N);
-      uint8_t* out_row = static_cast<uint8_t*>(p.dst) + ((size_t)(n * p.H + hp - 1) * p.W + wq) * G::OC1 * ts;
-      const int cb = c & 1;
-      mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c >> 1) & 1);
-      tc_fence_after_sync();
-      tr.ev(32);
-      const uint32_t t_base = lane_addr + kAcc1Col + cb * kAcc1Stride;
-#pragma unroll
-      for (int i = 0; i < G::nc1 / 64; ++i) {
-        const int gr = i * 2 + half;
-        uint32_t acc[32];
-        tmem_ld_x32(t_base + gr * 32, acc);
-        tmem_ld_wait();
-        if (valid) {
-#pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const int col = j * G::nc1 + gr * 32 + sub * 16;
-            auto s4 = [&](int k) -> float4 {
-              const int c0 = col + k * 4;
-              return make_float4(ec.scale1[c0], ec.scale1[c0 + 1], ec.scale1[c0 + 2], ec.scale1[c0 + 3]);
-            };
-            store16<kDst, false, false, true>(acc + sub * 16, sb1 + col, sk1 + col, p.k1_uniform, s4, relu1,
-                                              out_row + (size_t)col * ts);
-          }
-        }
-      }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(l_acc1_empty[cb]);
-      tr.ev(33);
-    };
-
-    uint32_t u = 0, c = 0;
-    if (n_local > 0) {
-      if ((u++ % kEpiGroups) == (uint32_t)group) unit_e0(0);
-    }
-    for (int it = 0; it < n_local; ++it) {
-      if (it + 1 < n_local && (u++ % kEpiGroups) == (uint32_t)group) unit_e0(it + 1);
-      for (int j = 0; j < G::n_chunks; ++j, ++c)
-        if ((u++ % kEpiGroups) == (uint32_t)group) unit_c(it, j, c);
-    }
+    epilogue_role<G, kDst, false, false, false, true>(p, smem, bar, tmem, warp, lane, n_local, 2 * cid + (int)rank, 2 * ncl);
+  } else if (warp == 3) {
+    // ================================ store thread (staged output) ==========================
+    if ((kDst == DF_U8 || kDst == DF_S8) && p.stage_out && elect_one())
+      store_role<G>(p, tmD, bar, sbase, n_local, 2 * cid + (int)rank, 2 * ncl);
   }
 
   tc_fence_before_sync();
@@ -1253,16 +1305,13 @@ inline int pick_swb(int k) { return k > 64 ? 128 : (k > 32 ? 64 : 32); }
 
 // type-erased launcher: the epilogue-constant parameter type depends on the geometry
 typedef cudaError_t (*LaunchFn)(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
-                                const CUtensorMap& w1, const Params& p, const void* epi_consts);
+                                const CUtensorMap& w1, const DstMaps& d, const Params& p);
 typedef cudaError_t (*AttrFn)(uint32_t smem);
 
 template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
 cudaError_t launch_conv(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
-                        const CUtensorMap& w1, const Params& p, const void* epi_consts) {
-  using EC = typename EpiConstsOf<G>::type;
-  static const EC none{};
-  const EC& ec = G::is_static ? *static_cast<const EC*>(epi_consts) : none;
-  conv_fused_kernel<G, kDst, kDown0, kDown1, kNanSafe><<<grid, kThreads, smem, st>>>(a, w0, w1, p, ec);
+                        const CUtensorMap& w1, const DstMaps& d, const Params& p) {
+  conv_fused_kernel<G, kDst, kDown0, kDown1, kNanSafe><<<grid, kThreads, smem, st>>>(a, w0, w1, d, p);
   return cudaGetLastError();
 }
 template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
@@ -1277,8 +1326,8 @@ struct KernelFn {
 
 template <class G, int kDst>
 cudaError_t launch_pair(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
-                        const CUtensorMap& w1, const Params& p, const void* epi_consts) {
-  conv_pair_kernel<G, kDst><<<grid, kThreads, smem, st>>>(a, w0, w1, p, *static_cast<const EpiConsts<G>*>(epi_consts));
+                        const CUtensorMap& w1, const DstMaps& d, const Params& p) {
+  conv_pair_kernel<G, kDst><<<grid, kThreads, smem, st>>>(a, w0, w1, d, p);
   return cudaGetLastError();
 }
 template <class G, int kDst>
@@ -1337,24 +1386,6 @@ KernelFn pick_kernel(int geom_id, int dst_dt, bool down0, bool down1, bool nan_s
   return KernelFn{nullptr, nullptr};
 }
 
-// host copy of the by-value epilogue constants of a static geometry
-template <class G>
-std::vector<char> make_epi_consts(const std::vector<float>& b0, const std::vector<float>& s0, const std::vector<int>& k1,
-                                  const std::vector<float>& c1, const std::vector<float>& s1) {
-  std::vector<char> raw(sizeof(EpiConsts<G>), 0);
-  EpiConsts<G>* ec = reinterpret_cast<EpiConsts<G>*>(raw.data());
-  for (int i = 0; i < G::OC; ++i) {
-    ec->bias0[i] = b0[i];
-    ec->scale0[i] = s0[i];
-  }
-  for (int i = 0; i < G::OC1; ++i) {
-    ec->k1[i] = k1[i];
-    ec->c1[i] = c1[i];
-    ec->scale1[i] = s1[i];
-  }
-  return raw;
-}
-
 template <class G>
 bool geom_matches(const Params& p) {
   return p.IC == G::IC && p.OC == G::OC && p.OC1 == G::OC1 && p.w0_res == G::w0_res && p.w1_res == G::w1_res &&
@@ -1368,7 +1399,7 @@ struct df_conv {
   df_conv() : desc(), prm(), kernel{nullptr, nullptr}, pair(false), pair_kernel{nullptr, nullptr}, pair_prm(), pair_smem(0),
               tmW0h(), tmW1h(), geom_id(0), smem_bytes(0), device(0), sms(0), d_w0(nullptr),
               d_w1(nullptr), d_bias0(nullptr), d_scale0(nullptr), d_bias1(nullptr), d_scale1(nullptr), d_k1(nullptr),
-              tmW0(), tmW1(), tmA(), tmA_src(nullptr), tmA_n(-1), trace(nullptr), trace_cap(0) {}
+              tmW0(), tmW1(), a_maps(), d_maps(), a_next(0), d_next(0), trace(nullptr), trace_cap(0) {}
   df_conv_desc desc;
   Params prm;        // everything except n-dependent fields and dst
   KernelFn kernel;
@@ -1378,7 +1409,6 @@ struct df_conv {
   Params pair_prm;
   uint32_t pair_smem;
   CUtensorMap tmW0h, tmW1h;
-  std::vector<char> epi_consts;  // by-value kernel parameter of the static geometries
   int geom_id;
   uint32_t smem_bytes;
   int device, sms;
@@ -1386,10 +1416,22 @@ struct df_conv {
   float *d_bias0, *d_scale0, *d_bias1, *d_scale1;
   int* d_k1;
   CUtensorMap tmW0, tmW1;
-  // cached activation map (re-encoded when the source pointer or batch changes)
-  CUtensorMap tmA;
-  const void* tmA_src;
-  int tmA_n;
+  // activation / destination tensor maps depend on (pointer, batch): a small round-robin cache keeps
+  // callers that cycle through a few buffers from re-encoding on every call
+  struct SrcSlot {
+    const void* ptr;
+    int n;
+    CUtensorMap map;
+  };
+  struct DstSlot {
+    const void* ptr;
+    int n;
+    DstMaps maps;
+  };
+  static constexpr int kMapSlots = 16;
+  SrcSlot a_maps[kMapSlots];
+  DstSlot d_maps[kMapSlots];
+  int a_next, d_next;
   unsigned long long* trace;
   int trace_cap;
 };
@@ -1449,6 +1491,23 @@ size_t blocked_off(int o, int i, int h, int w, int ic, int kh, int kw) {
   return blk * 256 + (size_t)((i % 16) / 4) * 64 + (size_t)(o % 16) * 4 + (i % 4);
 }
 
+// accumulator column -> output channel for an accumulator of `ncols` real columns (a multiple of 16):
+// blocks of 32 columns, then one block of 16; inside a block of NB columns, column 8k + 2m + e holds
+// channel (NB/4) * m + 2k + e (see tmem_ld_16x256b_x8)
+int col_to_channel(int col, int ncols) {
+  const int full = ncols / 32 * 32;
+  int base, nb;
+  if (col < full) {
+    base = col / 32 * 32;
+    nb = 32;
+  } else {
+    base = full + (col - full) / 16 * 16;
+    nb = 16;
+  }
+  const int r = col - base, k = r / 8, m = (r % 8) / 2, e = r % 2;
+  return base + (nb / 4) * m + 2 * k + e;
+}
+
 int encode_2d(CUtensorMap* tm, void* base, int row_bytes, long rows, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return df::fail(DF_E_NODRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -1499,6 +1558,9 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   const int wp_align = 128 / p.swb;  // every halo row must start 128 B aligned for TMA
   p.Wp = (d->iw + 1 + wp_align - 1) / wp_align * wp_align;
   p.NR = (kTileM + 2 * p.Wp) / p.Wp + 2;  // rows touched by 128 + 2*Wp + 2 consecutive positions
+  p.r8_dw = 8 % p.Wp;
+  p.r8_dn = (8 / p.Wp) / p.Hp;
+  p.r8_dh = (8 / p.Wp) % p.Hp;
   p.nc1 = d->oc1 < 128 ? d->oc1 : 128;
   p.n_chunks = (d->oc1 + p.nc1 - 1) / p.nc1;
   p.n_acc0 = d->oc <= 128 ? 2 : 1;
@@ -1523,9 +1585,8 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   p.mid_kb_stride = kTileM * p.swb1;
   p.mid_bytes = align_up(p.nkb1 * p.mid_kb_stride, 1024);
   p.off_mid = off;
-  const uint32_t fixed_one_mid = off + p.mid_bytes;
-  off += 2 * p.mid_bytes;
-  p.NM = 2;
+  off += p.mid_bytes;
+  p.NM = 1;  // one intermediate buffer is enough with the epilogue's unit order (see epilogue_role)
   p.a_kb_stride = (uint32_t)p.NR * p.Wp * p.swb;
   p.a_stage_bytes = align_up(p.nkb * p.a_kb_stride, 1024);
   p.w0_block_bytes = (uint32_t)p.OC * p.swb;
@@ -1533,15 +1594,7 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   const uint32_t w0_bytes = align_up(9 * p.nkb * p.w0_block_bytes, 1024);
   const uint32_t w1_bytes = align_up(p.n_chunks * p.nkb1 * p.w1_block_bytes, 1024);
   const uint32_t avail = kSmemLimit - 1024;  // base alignment slack
-  uint32_t fixed = off;
-  {
-    // large shapes: give the second intermediate buffer up before giving weight stages up
-    const uint32_t stage = align_up(p.w0_block_bytes > p.w1_block_bytes ? p.w0_block_bytes : p.w1_block_bytes, 1024);
-    if (fixed + 2 * p.a_stage_bytes + 3 * stage > avail) {
-      p.NM = 1;
-      fixed = fixed_one_mid;
-    }
-  }
+  const uint32_t fixed = off;
   if (fixed + 2 * p.a_stage_bytes + w0_bytes + w1_bytes <= avail) {
     p.w0_res = p.w1_res = 1;
     p.off_w0 = fixed;
@@ -1580,24 +1633,50 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   if (geom_matches<GeoCfg1>(p)) { op->geom_id = 1; p.SB = GeoCfg1::SB; }
   else if (geom_matches<GeoCfg3>(p)) { op->geom_id = 3; p.SB = GeoCfg3::SB; }
   else if (geom_matches<GeoCfg4>(p)) { op->geom_id = 4; p.SB = GeoCfg4::SB; }
-  if (getenv("DF_FORCE_DYNAMIC_GEOMETRY")) op->geom_id = 0;  // test hook: exercise the generic path
-  op->smem_bytes = p.off_b + p.SB * p.b_stage_bytes + 1024;
+  const int shape_id = op->geom_id;  // which BASELINE shape this is (0: none), whatever kernel ends up running it
+  // Staged output (store_staged_chunk): two 16 KB buffers behind the weight stages.  The run-time
+  // geometry gives weight stages beyond four up for it; the static plans keep their stage counts.
+  const bool can_stage = (d->dst_dt == DF_U8 || d->dst_dt == DF_S8) && p.nc1 == 128 &&
+                         !(getenv("DF_NO_STAGED_STORE") && atoi(getenv("DF_NO_STAGED_STORE")) != 0);
+  p.stage_out = 0;
+  p.off_stage = 0;
+  {
+    const uint32_t need = kStageBufs * kStageBytes;
+    if (can_stage && !shape_id)
+      while (p.SB > 4 && p.off_b + p.SB * p.b_stage_bytes + need > avail) --p.SB;
+    uint32_t end = p.off_b + p.SB * p.b_stage_bytes;
+    if (can_stage && end + need <= avail) {
+      p.stage_out = 1;
+      p.off_stage = end;
+      end += need;
+    }
+    op->smem_bytes = end + 1024;
+  }
 
   // ---- parameters: weights re-laid out K-major per (tap, K-block); bias -> f32; scales expanded
+  // Row r of a weight block (= MMA N index = accumulator column r) holds output channel
+  // col_to_channel(r): the order the epilogue's row-pair fragments want (see tmem_ld_16x256b_x8).
   std::vector<int8_t> w0((size_t)9 * p.nkb * p.OC * p.swb, 0);
   for (int tap = 0; tap < 9; ++tap)
-    for (int o = 0; o < p.OC; ++o)
+    for (int r = 0; r < p.OC; ++r) {
+      const int o = col_to_channel(r, p.OC);
       for (int i = 0; i < p.IC; ++i) {
         const int kb = i / p.swb;
-        w0[(((size_t)tap * p.nkb + kb) * p.OC + o) * p.swb + (i - kb * p.swb)] =
+        w0[(((size_t)tap * p.nkb + kb) * p.OC + r) * p.swb + (i - kb * p.swb)] =
             wei[blocked_off(o, i, tap / 3, tap % 3, p.IC, 3, 3)];
       }
-  std::vector<int8_t> w1((size_t)p.n_chunks * p.nkb1 * p.nc1 * p.swb1, 0);
-  for (int q = 0; q < p.OC1; ++q)
-    for (int o = 0; o < p.OC; ++o) {
-      const int j = q / p.nc1, r = q - j * p.nc1, kb = o / p.swb1;
-      w1[(((size_t)j * p.nkb1 + kb) * p.nc1 + r) * p.swb1 + (o - kb * p.swb1)] = wei1[blocked_off(q, o, 0, 0, p.OC, 1, 1)];
     }
+  std::vector<int8_t> w1((size_t)p.n_chunks * p.nkb1 * p.nc1 * p.swb1, 0);
+  for (int j = 0; j < p.n_chunks; ++j) {
+    const int ncols = p.OC1 - j * p.nc1 < p.nc1 ? p.OC1 - j * p.nc1 : p.nc1;  // real columns of this chunk
+    for (int r = 0; r < ncols; ++r) {
+      const int q = j * p.nc1 + col_to_channel(r, ncols);
+      for (int o = 0; o < p.OC; ++o) {
+        const int kb = o / p.swb1;
+        w1[(((size_t)j * p.nkb1 + kb) * p.nc1 + r) * p.swb1 + (o - kb * p.swb1)] = wei1[blocked_off(q, o, 0, 0, p.OC, 1, 1)];
+      }
+    }
+  }
   std::vector<float> b0(p.OC), s0(p.OC), b1(p.OC1), s1(p.OC1);
   bool finite = true;
   for (int o = 0; o < p.OC; ++o) {
@@ -1651,7 +1730,6 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   if (getenv("DF_NO_FAST_CONV1")) fast1 = false;  // test hook: exercise the I2F path
   if (!fast1) p.k1_uniform = 0;
   p.fast1 = fast1;
-  p.epi_ahead = (p.NM == 2 && p.n_acc0 == 2) ? 1 : 0;
 
 #define DF_TRY(expr)                          \
   do {                                        \
@@ -1694,29 +1772,31 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   DF_TRY(encode_2d(&op->tmW0, op->d_w0, p.swb, (long)9 * p.nkb * p.OC, p.OC));
   DF_TRY(encode_2d(&op->tmW1, op->d_w1, p.swb1, (long)p.n_chunks * p.nkb1 * p.nc1, p.nc1));
 
-  if (!p.fast1) op->geom_id = 0;  // the static kernels are built for the fast conv1 conversion only
-  if (d->round0 == DF_ROUND_DOWN || d->round1 == DF_ROUND_DOWN || p.nan_safe) op->geom_id = 0;
+  // The static kernels are built for round-to-nearest, finite constants, the offset-magic conv1
+  // conversion with ONE constant K, and (1-byte destinations) staged output; anything else runs the
+  // run-time-geometry kernel.
+  const bool one_byte = d->dst_dt == DF_U8 || d->dst_dt == DF_S8;
+  const bool static_ok = p.fast1 && p.k1_uniform != 0 && d->round0 == DF_ROUND_NEAREST && d->round1 == DF_ROUND_NEAREST &&
+                         !p.nan_safe && !getenv("DF_FORCE_DYNAMIC_GEOMETRY");  // (env: test hook for the generic path)
+  if (!static_ok || (one_byte && !p.stage_out)) op->geom_id = 0;
   op->kernel = pick_kernel(op->geom_id, d->dst_dt, d->round0 == DF_ROUND_DOWN, d->round1 == DF_ROUND_DOWN, p.nan_safe != 0);
-  if (op->geom_id == 1) op->epi_consts = make_epi_consts<GeoCfg1>(b0, s0, k1, c1, s1);
-  if (op->geom_id == 3) op->epi_consts = make_epi_consts<GeoCfg3>(b0, s0, k1, c1, s1);
-  if (op->geom_id == 4) op->epi_consts = make_epi_consts<GeoCfg4>(b0, s0, k1, c1, s1);
   DF_TRY_CUDA(op->kernel.attr(op->smem_bytes));
 
-  // ---- CTA-pair variant: BASELINE cfg3 with everything resident once the weights are split in two
-  // Opt-in (DF_PAIR=1): it removes weight streaming entirely, but both variants are currently bound by
-  // the epilogue and the single-CTA kernel is ~8 % faster end to end (profiles/README.md).
-  if (op->geom_id == 3 && getenv("DF_PAIR") && atoi(getenv("DF_PAIR")) != 0) {
+  // ---- CTA-pair variant: BASELINE cfg3 with everything resident once the weights are split in two.
+  // Default for that shape (DF_PAIR=0 selects the single-CTA kernel, which has to stream 144 KB of
+  // 3x3 weights per 128-position tile -- more than the L2 delivers at tensor-pipe speed).
+  if (shape_id == 3 && static_ok && !(getenv("DF_PAIR") && atoi(getenv("DF_PAIR")) == 0)) {
     Params q = p;
     q.w0_res = q.w1_res = 1;
     q.SB = 1;
-    q.NM = 2;
-    uint32_t off2 = fixed_one_mid - p.mid_bytes;  // = start of the intermediate buffers
-    q.off_mid = off2;
-    off2 += 2 * q.mid_bytes;
+    q.stage_out = one_byte ? 1 : 0;
+    uint32_t off2 = p.off_mid + q.mid_bytes;
     q.off_w0 = off2;
     off2 += align_up(9 * q.nkb * (q.w0_block_bytes / 2), 1024);
     q.off_w1 = off2;
     off2 += align_up(q.n_chunks * q.nkb1 * (q.w1_block_bytes / 2), 1024);
+    q.off_stage = off2;
+    if (q.stage_out) off2 += kStageBufs * kStageBytes;
     q.off_a = off2;
     q.a_kb_stride = (uint32_t)(q.NR + 1) * q.Wp * q.swb;  // one extra row of slack before the tile origin
     q.a_stage_bytes = align_up(q.nkb * q.a_kb_stride, 1024);
@@ -1743,6 +1823,63 @@ static int tiles_for(const Params& p, int n) {
   return (int)((q_end - q_first + kTileM - 1) / kTileM);
 }
 
+// Activation map: 4-D u8 {IC, W, H, n} over the NHWC source, box {swb, Wp, 1, 1} (one halo row of one
+// K-block).  Looked up in / added to a round-robin cache keyed by (pointer, batch).
+static int src_map(df_conv* op, const Params& p, const void* ptr, int n, const CUtensorMap** out) {
+  for (int i = 0; i < df_conv::kMapSlots; ++i)
+    if (op->a_maps[i].ptr == ptr && op->a_maps[i].n == n) {
+      *out = &op->a_maps[i].map;
+      return 0;
+    }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return df::fail(DF_E_NODRIVER, "cuTensorMapEncodeTiled unavailable");
+  df_conv::SrcSlot& s = op->a_maps[op->a_next];
+  op->a_next = (op->a_next + 1) % df_conv::kMapSlots;
+  cuuint64_t gd[4] = {(cuuint64_t)p.IC, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)n};
+  cuuint64_t gs[3] = {(cuuint64_t)p.IC, (cuuint64_t)p.W * p.IC, (cuuint64_t)p.H * p.W * p.IC};
+  cuuint32_t box[4] = {(cuuint32_t)p.swb, (cuuint32_t)p.Wp, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  s.ptr = nullptr;
+  CUresult r = enc(&s.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(ptr), gd, gs, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(p.swb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return df::fail(DF_E_INTERNAL, "cuTensorMapEncodeTiled(src) failed: %d", (int)r);
+  s.ptr = ptr;
+  s.n = n;
+  *out = &s.map;
+  return 0;
+}
+
+// Destination maps of the staged output path: the 1-byte NHWC destination as 2-D [n*H*W pixels][OC1],
+// boxes {128 channels, 128 >> i pixels}, SWIZZLE_128B (store_staged_chunk).
+static int dst_maps(df_conv* op, const Params& p, const void* ptr, int n, const DstMaps** out) {
+  for (int i = 0; i < df_conv::kMapSlots; ++i)
+    if (op->d_maps[i].ptr == ptr && op->d_maps[i].n == n) {
+      *out = &op->d_maps[i].maps;
+      return 0;
+    }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return df::fail(DF_E_NODRIVER, "cuTensorMapEncodeTiled unavailable");
+  df_conv::DstSlot& s = op->d_maps[op->d_next];
+  op->d_next = (op->d_next + 1) % df_conv::kMapSlots;
+  s.ptr = nullptr;
+  const cuuint64_t pixels = (cuuint64_t)n * p.H * p.W;
+  for (int i = 0; i < 8; ++i) {
+    cuuint64_t gd[2] = {(cuuint64_t)p.OC1, pixels};
+    cuuint64_t gs[1] = {(cuuint64_t)p.OC1};
+    cuuint32_t box[2] = {128, (cuuint32_t)(128 >> i)};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&s.maps.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gd, gs, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return df::fail(DF_E_INTERNAL, "cuTensorMapEncodeTiled(dst) failed: %d", (int)r);
+  }
+  s.ptr = ptr;
+  s.n = n;
+  *out = &s.maps;
+  return 0;
+}
+
 extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, void* stream) {
   if (!op || !src || !dst) return df::fail(DF_E_INVALID, "conv run: null argument");
   if (n < 0 || n > op->desc.n) return df::fail(DF_E_INVALID, "conv run: batch %d outside [0, %d]", n, op->desc.n);
@@ -1752,36 +1889,36 @@ extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, vo
   Params p = op->pair ? op->pair_prm : op->prm;
   if ((long)n * p.Hp * p.Wp + 4L * p.Wp + kTileM >= (1L << 31))
     return df::fail(DF_E_UNSUPPORTED, "conv run: batch too large for 32-bit position index");
-  if (op->tmA_src != src || op->tmA_n != n) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return df::fail(DF_E_NODRIVER, "cuTensorMapEncodeTiled unavailable");
-    cuuint64_t gd[4] = {(cuuint64_t)p.IC, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)n};
-    cuuint64_t gs[3] = {(cuuint64_t)p.IC, (cuuint64_t)p.W * p.IC, (cuuint64_t)p.H * p.W * p.IC};
-    cuuint32_t box[4] = {(cuuint32_t)p.swb, (cuuint32_t)p.Wp, 1, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&op->tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(src), gd, gs, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(p.swb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return df::fail(DF_E_INTERNAL, "cuTensorMapEncodeTiled(src) failed: %d", (int)r);
-    op->tmA_src = src;
-    op->tmA_n = n;
+  const CUtensorMap* tmA = nullptr;
+  const DstMaps* tmD = &op->d_maps[0].maps;  // not read by the kernel unless stage_out
+  {
+    int rc = src_map(op, p, src, n, &tmA);
+    if (rc) return rc;
+    if (p.stage_out) rc = dst_maps(op, p, dst, n, &tmD);
+    if (rc) return rc;
   }
   p.N = n;
   p.n_tiles = tiles_for(p, n);
   p.dst = dst;
   p.trace = op->trace;
   p.trace_cap = op->trace_cap;
+  auto set_tile_step = [&p](long tiles) {  // positions between successive tiles of one CTA
+    const long dq = tiles * kTileM, rows = dq / p.Wp;
+    p.ts_dw = (int)(dq % p.Wp);
+    p.ts_dn = (int)(rows / p.Hp);
+    p.ts_dh = (int)(rows % p.Hp);
+  };
   if (op->pair) {
     const int pair_tiles = (p.n_tiles + 1) / 2, clusters = pair_tiles < op->sms / 2 ? pair_tiles : op->sms / 2;
     p.tile_step_mod = 0;
-    DF_CUDA(op->pair_kernel.launch(2 * clusters, op->pair_smem, (cudaStream_t)stream, op->tmA, op->tmW0h, op->tmW1h, p,
-                                   op->epi_consts.data()));
+    set_tile_step(2L * clusters);
+    DF_CUDA(op->pair_kernel.launch(2 * clusters, op->pair_smem, (cudaStream_t)stream, *tmA, op->tmW0h, op->tmW1h, *tmD, p));
     return 0;
   }
   const int grid = p.n_tiles < op->sms ? p.n_tiles : op->sms;
   p.tile_step_mod = (kTileM * grid) % p.Wp;
-  DF_CUDA(op->kernel.launch(grid, op->smem_bytes, (cudaStream_t)stream, op->tmA, op->tmW0, op->tmW1, p,
-                            op->epi_consts.empty() ? nullptr : op->epi_consts.data()));
+  set_tile_step(grid);
+  DF_CUDA(op->kernel.launch(grid, op->smem_bytes, (cudaStream_t)stream, *tmA, op->tmW0, op->tmW1, *tmD, p));
   return 0;
 }
 

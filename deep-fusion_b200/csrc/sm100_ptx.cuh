@@ -73,12 +73,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// Warp-collective wait: ONE lane polls, the rest park at the warp barrier.  Hundreds of threads
-// spinning on try_wait saturate the SM's MIO/sync pipeline and slow down every other warp
+// Warp-collective wait.  Fast path: every lane tests the barrier once (the same instruction, the same
+// answer) and the warp goes on without diverging -- in steady state the phase is already complete, and a
+// divergent poll-then-__syncwarp costs ~300 cycles of reconvergence even then (profiles/
+// r01_trace_cfg3_v9b.log).  Slow path: ONE lane polls, the rest park at the warp barrier; hundreds of
+// threads spinning on try_wait saturate the SM's MIO/sync pipeline and slow down every other warp
 // (measured: 3-5x on both MMA issue and epilogue math, profiles/r01_trace_*.log).
 // kBackoffNs > 0 adds a sleep between polls for waits that are expected to be long.
 template <int kBackoffNs = 0>
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if (__all_sync(0xffffffffu, mbar_test_wait(bar, parity))) return;
   if ((threadIdx.x & 31) == 0) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
@@ -141,6 +145,30 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
           "r"(dst),
       "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
       : "memory");
+}
+
+// TMA tile store smem -> global (bulk async-group completion).  Elements of the box that fall
+// outside the tensor (negative or too large coordinates) are not written.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all bulk groups of this thread are complete (writes performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// named barrier among `n_threads` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 
 // ------------------------------------------------------------------------------ tcgen05
