@@ -92,6 +92,16 @@ struct Tracer {
   }
 };
 
+// kernel entry / exit wall-clock stamps (%globaltimer, ns; comparable across SMs) in the last two words of
+// the CTA's role-2 trace lane
+__device__ __forceinline__ void trace_wallclock(const Params& p, int slot) {
+  if (p.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[((size_t)blockIdx.x * 4 + 2) * p.trace_cap + p.trace_cap - 1 - slot] = t;
+  }
+}
+
 struct Barriers {
   uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
   uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
@@ -475,6 +485,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
   };
   Tracer tr(p, 3);
   if (threadIdx.x != kEpiWarp0 * 32) tr.base = nullptr;
+  if (!staged) griddep_wait();  // direct stores: earlier kernels may still be using the destination
 
   // ---- conv0 epilogue of local tile `it`
   auto unit_e0 = [&](int it) {
@@ -557,12 +568,10 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
     }
     const int cb = c & 1;
     tr.ev(36);
-    if (staged)  // chunk c - 2 must have left this staging buffer
-      mbar_wait_warp(smem_u32(&bar->stage_empty[cb]), ((c >> 1) & 1) ^ 1);
-    tr.ev(34);
     mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c >> 1) & 1);
     tc_fence_after_sync();
     tr.ev(32);
+    bool stage_checked = !staged;
     int ncols = g.OC1() - j * g.nc1();  // real columns in this chunk
     if (ncols > g.nc1()) ncols = g.nc1();
     const uint32_t t_base = lane_addr + kAcc1Col + cb * kAcc1Stride;
@@ -595,6 +604,10 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
           saddr[ri] = stage_col + ((uint32_t)rinfo[ri] ^ unit_x);
           asm volatile("" : "+r"(saddr[ri]));
         }
+      }
+      if (!stage_checked) {  // chunk c - 2 must have left this staging buffer (waited for under the TMEM loads)
+        mbar_wait_warp(smem_u32(&bar->stage_empty[cb]), ((c >> 1) & 1) ^ 1);
+        stage_checked = true;
       }
       tmem_ld_wait();
       if (last) {  // accumulator is in registers: the tensor pipe may overwrite it
@@ -673,6 +686,7 @@ __device__ __forceinline__ void store_role(const Params& p, const DstMaps& tmD, 
   const int q_first = 2 * p.Wp;
   Tracer tr(p, 2);
   uint32_t c = 0;
+  griddep_wait();  // earlier kernels in the stream may still be reading / writing the destination
   for (int it = 0; it < n_local; ++it) {
     const int q0 = q_first + (tile0 + it * tile_stride) * kTileM;
     const int f0 = valid_before(p, q0), V = valid_before(p, q0 + kTileM) - f0;
@@ -701,6 +715,10 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   Barriers* bar = reinterpret_cast<Barriers*>(smem);
   const uint32_t sbase = smem_u32(smem);
+  trace_wallclock(p, 0);
+  // PDL: the next launch may take over SMs as soon as this grid's CTAs leave them and run its prologue
+  // (barriers, TMEM, weights) under our tail; whatever depends on earlier kernels sits behind griddep_wait()
+  griddep_launch_dependents();
   const Geo<G> g{p};
 
   // shfl from lane 0 tells ptxas the warp index is warp-uniform (values derived from it can then
@@ -769,6 +787,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // =============================== TMA producer: halo rows ===============================
     if (elect_one()) {
       Tracer tr(p, 0);
+      griddep_wait();  // the source may have been written by the previous kernel in the stream
       for (int it = 0; it < n_local; ++it) {
         const int tile = blockIdx.x + it * gridDim.x;
         const int s = it % p.SA;
@@ -1038,6 +1057,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 3) tmem_dealloc<512>(tmem);
+  trace_wallclock(p, 1);
 }
 
 // =============================================================================== CTA-pair kernel
@@ -1073,6 +1093,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   PairBarriers* bar = reinterpret_cast<PairBarriers*>(smem);
   const uint32_t sbase = smem_u32(smem);
+  trace_wallclock(p, 0);
+  griddep_launch_dependents();  // PDL, see conv_fused_kernel
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
@@ -1135,6 +1157,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================ halo producer (both CTAs) ================================
     if (elect_one()) {
       Tracer tr(p, 0);
+      griddep_wait();  // the source may have been written by the previous kernel in the stream
       for (int it = 0; it < n_local; ++it) {
         const int tile = 2 * (cid + it * ncl) + (int)rank;
         const int s = it % p.SA;
@@ -1279,6 +1302,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still touch it
   if (warp == 3) tmem_dealloc_pair<512>(tmem);
+  trace_wallclock(p, 1);
 }
 
 // ================================================================================ host side
@@ -1308,11 +1332,28 @@ typedef cudaError_t (*LaunchFn)(int grid, uint32_t smem, cudaStream_t st, const 
                                 const CUtensorMap& w1, const DstMaps& d, const Params& p);
 typedef cudaError_t (*AttrFn)(uint32_t smem);
 
+// Launch with programmatic stream serialization: back-to-back launches on one stream overlap the next
+// launch's prologue with this launch's tail (see griddep_launch_dependents in the kernels).
+template <class Kernel>
+cudaError_t launch_pdl(Kernel kernel, int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
+                       const CUtensorMap& w1, const DstMaps& d, const Params& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = getenv("DF_NO_PDL") ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, a, w0, w1, d, p);
+}
+
 template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
 cudaError_t launch_conv(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
                         const CUtensorMap& w1, const DstMaps& d, const Params& p) {
-  conv_fused_kernel<G, kDst, kDown0, kDown1, kNanSafe><<<grid, kThreads, smem, st>>>(a, w0, w1, d, p);
-  return cudaGetLastError();
+  return launch_pdl(conv_fused_kernel<G, kDst, kDown0, kDown1, kNanSafe>, grid, smem, st, a, w0, w1, d, p);
 }
 template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
 cudaError_t attr_conv(uint32_t smem) {
@@ -1327,8 +1368,7 @@ struct KernelFn {
 template <class G, int kDst>
 cudaError_t launch_pair(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
                         const CUtensorMap& w1, const DstMaps& d, const Params& p) {
-  conv_pair_kernel<G, kDst><<<grid, kThreads, smem, st>>>(a, w0, w1, d, p);
-  return cudaGetLastError();
+  return launch_pdl(conv_pair_kernel<G, kDst>, grid, smem, st, a, w0, w1, d, p);
 }
 template <class G, int kDst>
 cudaError_t attr_pair(uint32_t smem) {
@@ -1711,7 +1751,7 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
       hi_max = hi[q] > hi_max ? hi[q] : hi_max;
     }
     // one K for every channel when a single lower bound keeps all ranges inside [0, 2^23)
-    bool uniform = hi_max - lo_min < (1ll << 23);
+    bool uniform = hi_max - lo_min < (1ll << 23) && !getenv("DF_NO_UNIFORM_K");  // (env: test hook, per-channel K path)
     for (int pass = 0; pass < 2; ++pass) {
       bool ok = finite;
       for (int q = 0; q < p.OC1 && ok; ++q) {

@@ -97,6 +97,13 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   __syncwarp();
 }
 
+// ------------------------------------------------------- programmatic dependent launch (PDL)
+// launch_dependents: the next kernel in the stream (if launched with the programmatic-stream-
+// serialization attribute) may start its CTAs as soon as every CTA of this grid has executed this or
+// exited; wait: blocks until all prerequisite grids have completed and their memory is visible.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------- fences
 // generic-proxy writes to smem -> visible to the async proxy (TMA / tcgen05.mma reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -23,6 +23,14 @@ def run(n, h, w, ic, oc, oc1, dst="u8", cta=0, cap=512, max_lines=120):
     df.check(df.lib().df_conv_debug_trace(op.handle, tb.ptr, cap))
     op.run(src, out); df.sync()
     t = tb.download((i.grid, 4, cap), np.uint64)
+    # kernel entry / exit wall-clock stamps (ns) of every CTA: last two words of role lane 2
+    t_in = t[:, 2, cap - 1].astype(np.int64); t_out = t[:, 2, cap - 2].astype(np.int64)
+    t[:, 2, cap - 2:] = 0
+    if t_in.min() > 0:
+        base = t_in.min()
+        print(f"wall clock (ns, relative to the first CTA's entry): entry min/median/max = {0}/{int(np.median(t_in - base))}/{int((t_in - base).max())}  "
+              f"exit min/median/max = {int((t_out - base).min())}/{int(np.median(t_out - base))}/{int((t_out - base).max())}  "
+              f"this CTA: in {int(t_in[cta] - base)} out {int(t_out[cta] - base)}")
     ev = []
     for role in range(4):
         for x in t[cta, role]:

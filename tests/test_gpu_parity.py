@@ -223,10 +223,43 @@ print("RES", i.w0_resident, i.w1_resident, "OK" if np.array_equal(got, want) els
     return r.stdout
 
 
-def test_conv_cta_pair_kernel(df):
-    """cta_group::2 variant (weight halves resident in a CTA pair), opt-in through DF_PAIR=1."""
-    out = _run_cfg3_in_subprocess({"DF_PAIR": "1"})
+def test_conv_cta_pair_kernel_is_the_default_for_cfg3(df):
+    """cta_group::2 kernel (weight halves resident in a CTA pair): the default for the cfg3 shape;
+    DF_PAIR=0 selects the single-CTA kernels (weights streamed), which must give the same bytes."""
+    out = _run_cfg3_in_subprocess({})
     assert "RES 2 2 OK" in out, out
+    out = _run_cfg3_in_subprocess({"DF_PAIR": "0"})
+    assert "RES 0 1 OK" in out, out
+
+
+def test_conv_store_and_launch_variants(df):
+    """Direct (unstaged) stores of 1-byte output, per-channel offset-magic constants, launches without
+    programmatic dependent launch: all bit-identical to the default path."""
+    for env in ({"DF_FORCE_DYNAMIC_GEOMETRY": "1", "DF_NO_STAGED_STORE": "1"}, {"DF_NO_UNIFORM_K": "1"},
+                {"DF_NO_UNIFORM_K": "1", "DF_NO_STAGED_STORE": "1"}, {"DF_NO_PDL": "1"}):
+        assert "OK" in _run_cfg3_in_subprocess(env), env
+
+
+def test_conv_back_to_back_launches_overlap_safely(df):
+    """Programmatic dependent launch lets launch k+1 start its prologue under the tail of launch k.  Chain
+    launches that reuse the same destination and feed on different sources: every result must be the one
+    of its own source (no early read, no late write)."""
+    c = cases.ConvCase("pdl", 16, 28, 28, 128, 128, 512, "u8", "s32", "s32")
+    src, w0, w1, b0, b1, s0, s1 = c.tensors()
+    wb, w1b = c.blocked(w0, w1)
+    op = df.Conv(c.n, c.h, c.w, c.ic, c.oc, c.oc1, cases.DT[c.dst], wb, w1b, b0, b1, s0, s1, cases.DT[c.b0], cases.DT[c.b1])
+    srcs = [src, np.ascontiguousarray(src[::-1]), (255 - src)]
+    want = [op(s) for s in srcs]                      # one launch at a time
+    sb = [df.DeviceBuffer.from_numpy(s) for s in srcs]
+    outs = [df.DeviceBuffer(want[0].size) for _ in range(2)]
+    for rep in range(20):                             # many launches in flight, two destinations reused
+        for k in range(3):
+            op.run(sb[k], outs[(rep * 3 + k) % 2])
+    last = (19 * 3 + 2) % 2
+    df.sync()
+    assert np.array_equal(outs[last].download(want[2].shape, np.uint8), want[2])
+    assert np.array_equal(outs[1 - last].download(want[1].shape, np.uint8), want[1])
+    op.close()
 
 
 def test_conv_generic_geometry_and_i2f_paths(df):
