@@ -237,17 +237,30 @@ def run_ours(args, rank, world, local_rank):
         sets.append((df.DeviceBuffer.from_numpy(np.roll(base.reshape(-1), 4099 * i)), df.DeviceBuffer(dst_bytes)))
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # The K timed steps are captured into one CUDA graph (K kernel nodes, programmatic-dependent-launch
+    # edges between them) and replayed with a single launch: at ~20 us per step a Python loop of ctypes
+    # calls is uncomfortably close to being the thing measured.  --no-graph times the plain loop.
+    st = df.Stream()
     for i in range(args.warmup):
-        op.run(*sets[i % n_sets])
-    df.sync()
+        op.run(*sets[i % n_sets], stream=st.ptr)
+    graph = None
+    if not args.no_graph:
+        with df.Graph(st) as graph:
+            for i in range(args.steps):
+                op.run(*sets[(args.warmup + i) % n_sets], stream=st.ptr)
+        graph.launch()  # untimed replay: graph upload, instruction caches
+    st.sync()
     barrier(dist)
     e0, e1 = df.Event(), df.Event()
     t_start = time.time()
-    e0.record()
-    for i in range(args.steps):
-        op.run(*sets[(args.warmup + i) % n_sets])
-    e1.record()
-    df.sync()
+    e0.record(st.ptr)
+    if graph is not None:
+        graph.launch()
+    else:
+        for i in range(args.steps):
+            op.run(*sets[(args.warmup + i) % n_sets], stream=st.ptr)
+    e1.record(st.ptr)
+    st.sync()
     ms_total = e0.elapsed_ms(e1)
     t_end = time.time()
     barrier(dist)
@@ -265,17 +278,27 @@ def run_ours(args, rank, world, local_rank):
     for i in range(c_sets):
         csets.append(([df.DeviceBuffer.from_numpy(a) for a in c_in], df.DeviceBuffer(c_bytes // 2)))
     npix = cn * chh * cww
-    ccalls = [df.ConcatCall(df.U8, True, [b.ptr for b in s[0]], list(cics), s[1].ptr, npix) for s in csets]
+    ccalls = [df.ConcatCall(df.U8, True, [b.ptr for b in s[0]], list(cics), s[1].ptr, npix, stream=st.ptr) for s in csets]
     crun = lambda i: ccalls[i]()  # noqa: E731
     for i in range(max(3, args.warmup)):
         crun(i % c_sets)
-    df.sync()
     c_steps = max(args.steps, 50)
+    cgraph = None
+    if not args.no_graph:  # a 2 us kernel: the host cannot issue launches that fast, the graph can
+        with df.Graph(st) as cgraph:
+            for i in range(c_steps):
+                crun(i % c_sets)
+        cgraph.launch()
+    st.sync()
     ce0, ce1 = df.Event(), df.Event()
-    ce0.record()
-    for i in range(c_steps):
-        crun(i % c_sets)
-    ce1.record()
+    ce0.record(st.ptr)
+    if cgraph is not None:
+        cgraph.launch()
+    else:
+        for i in range(c_steps):
+            crun(i % c_sets)
+    ce1.record(st.ptr)
+    st.sync()
     c_ms = barrier_and_max(dist, ce0.elapsed_ms(ce1) / c_steps)
     concat_gbs = c_bytes / (c_ms * 1e-3) / 1e9
 
@@ -325,13 +348,14 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "u8", "data": "synthetic", "images_per_s": total_images / (ms_step * 1e-3),
         "config": {"workload": WORKLOADS[args.workload][7], "images_per_gpu": n, "parallelism": f"batch-sharded x{world}, no collective",
                    "cache": f"rotating {n_sets} src/dst buffer sets ({n_sets * (src_bytes + dst_bytes) >> 20} MiB > 2x L2) so no step finds its data in L2",
+                   "launch": "plain loop of df_conv_run calls" if args.no_graph else f"{args.steps} steps captured in one CUDA graph, replayed once inside the timed region",
                    "tiles": info.tiles_per_launch, "grid": info.grid, "smem_bytes": info.smem_bytes,
                    "weights_resident": [info.w0_resident, info.w1_resident], "mma_row_efficiency": round(info.mma_efficiency, 4)},
         "roofline": {"bound": "tensor", "achieved": kernel_tops_this_rank, "peak": tensor_peak, "unit": "TOPS",
                      "frac": kernel_tops_this_rank / tensor_peak, "traffic": None,
                      "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({peaks['which']}); int8 dense rate = 2 x bf16",
                      "frac_of_i8_mma_probe": kernel_tops_this_rank / 4335.0,
-                     "i8_mma_probe_tops": 4335.0, "kernel": "conv_fused_kernel", "ops_per_launch": n * ops_per_image(p)},
+                     "i8_mma_probe_tops": 4335.0, "kernel": "conv_pair_kernel" if info.w0_resident == 2 else "conv_fused_kernel", "ops_per_launch": n * ops_per_image(p)},
         "concat": {"workload": "concat+ReLU u8, 28x28, C=64/128/32/32, batch 32 (BASELINE configs[1])", "value": concat_gbs,
                    "unit": "GB/s", "us_per_launch": c_ms * 1e3, "bytes_per_launch": c_bytes,
                    "roofline": {"bound": "hbm", "achieved": concat_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -356,6 +380,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time a plain loop of launches instead of a CUDA graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

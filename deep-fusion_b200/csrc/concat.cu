@@ -10,7 +10,10 @@
 //
 // ReLU is the reference's literal one (jit_concat_kernel.cc:43-51): vpmaxsb for s8 AND u8,
 // vpmaxsw for s32, vmaxps(0, x) for f32 -- see DESIGN.md (C6/D9).
+#include <stdlib.h>
+
 #include "df_common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace {
 
@@ -55,6 +58,9 @@ __device__ __forceinline__ uint32_t relu_word(uint32_t x) {
 template <int kMode>
 __global__ void __launch_bounds__(kThreads) concat_kernel_strided(const ConcatParams p, uint4* __restrict__ dst,
                                                                   uint32_t n_pixels) {
+  // PDL: back-to-back launches overlap this launch's scheduling and index setup with the previous
+  // kernel's tail; nothing is read or written before griddep_wait()
+  sm100::griddep_launch_dependents();
   const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;
   const uint32_t off = tid % p.group_vecs;
   uint32_t pixel = tid / p.group_vecs;
@@ -64,6 +70,7 @@ __global__ void __launch_bounds__(kThreads) concat_kernel_strided(const ConcatPa
   const uint32_t width = p.vec_begin[i + 1] - p.vec_begin[i];
   const uint4* src = p.src[i] + (off - p.vec_begin[i]);
   uint4* out = dst + p.dst_off + off;
+  sm100::griddep_wait();
   for (; pixel < n_pixels; pixel += pstride * kUnroll) {
     uint4 val[kUnroll];
 #pragma unroll
@@ -88,6 +95,8 @@ __global__ void __launch_bounds__(kThreads) concat_kernel_strided(const ConcatPa
 
 template <int kMode>
 __global__ void __launch_bounds__(kThreads) concat_kernel(const ConcatParams p, uint4* __restrict__ dst) {
+  sm100::griddep_launch_dependents();
+  sm100::griddep_wait();
   const uint32_t stride = gridDim.x * kThreads;
   for (uint32_t base = blockIdx.x * kThreads + threadIdx.x; base < p.total; base += stride * kUnroll) {
     uint4 val[kUnroll];
@@ -118,6 +127,22 @@ __global__ void __launch_bounds__(kThreads) concat_kernel(const ConcatParams p, 
       }
     }
   }
+}
+
+// launch with programmatic stream serialization (see the kernels)
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned blocks, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = getenv("DF_NO_PDL") ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 }  // namespace
@@ -180,22 +205,23 @@ extern "C" int df_concat_run(int dtype, int relu, int n_inputs, const void* cons
       unsigned want = (p.total + kThreads * kUnroll - 1) / (kThreads * kUnroll);
       if (want > cap) want = cap;
       unsigned sblocks = (want + block_multiple - 1) / block_multiple * block_multiple;
+      uint4* d4 = (uint4*)dst_dev;
+      const uint32_t npx = (uint32_t)n_pixels;
       switch (mode) {
-        case kCopy: concat_kernel_strided<kCopy><<<sblocks, kThreads, 0, st>>>(p, (uint4*)dst_dev, (uint32_t)n_pixels); break;
-        case kReluBytes: concat_kernel_strided<kReluBytes><<<sblocks, kThreads, 0, st>>>(p, (uint4*)dst_dev, (uint32_t)n_pixels); break;
-        case kReluHalves: concat_kernel_strided<kReluHalves><<<sblocks, kThreads, 0, st>>>(p, (uint4*)dst_dev, (uint32_t)n_pixels); break;
-        default: concat_kernel_strided<kReluF32><<<sblocks, kThreads, 0, st>>>(p, (uint4*)dst_dev, (uint32_t)n_pixels); break;
+        case kCopy: DF_CUDA(launch_pdl(concat_kernel_strided<kCopy>, sblocks, st, p, d4, npx)); break;
+        case kReluBytes: DF_CUDA(launch_pdl(concat_kernel_strided<kReluBytes>, sblocks, st, p, d4, npx)); break;
+        case kReluHalves: DF_CUDA(launch_pdl(concat_kernel_strided<kReluHalves>, sblocks, st, p, d4, npx)); break;
+        default: DF_CUDA(launch_pdl(concat_kernel_strided<kReluF32>, sblocks, st, p, d4, npx)); break;
       }
-      DF_CUDA(cudaGetLastError());
       continue;
     }
+    uint4* d4 = (uint4*)dst_dev;
     switch (mode) {
-      case kCopy: concat_kernel<kCopy><<<blocks, kThreads, 0, st>>>(p, (uint4*)dst_dev); break;
-      case kReluBytes: concat_kernel<kReluBytes><<<blocks, kThreads, 0, st>>>(p, (uint4*)dst_dev); break;
-      case kReluHalves: concat_kernel<kReluHalves><<<blocks, kThreads, 0, st>>>(p, (uint4*)dst_dev); break;
-      default: concat_kernel<kReluF32><<<blocks, kThreads, 0, st>>>(p, (uint4*)dst_dev); break;
+      case kCopy: DF_CUDA(launch_pdl(concat_kernel<kCopy>, blocks, st, p, d4)); break;
+      case kReluBytes: DF_CUDA(launch_pdl(concat_kernel<kReluBytes>, blocks, st, p, d4)); break;
+      case kReluHalves: DF_CUDA(launch_pdl(concat_kernel<kReluHalves>, blocks, st, p, d4)); break;
+      default: DF_CUDA(launch_pdl(concat_kernel<kReluF32>, blocks, st, p, d4)); break;
     }
-    DF_CUDA(cudaGetLastError());
   }
   return 0;
 }

@@ -91,6 +91,24 @@ struct Tracer {
     if (base && n < cap) base[n++] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
   }
 };
+// The epilogue warps are bound by instruction issue, and even a disabled trace point costs them ~10
+// instructions (ncu: 15 % of the epilogue's instructions with five points per unit).  Their trace points
+// exist only in builds with -DDF_EPI_TRACE=1 (make DF_NVFLAGS=-DDF_EPI_TRACE=1; scripts/trace_conv.py).
+#ifndef DF_EPI_TRACE
+#define DF_EPI_TRACE 0
+#endif
+struct EpiTracer {
+#if DF_EPI_TRACE
+  Tracer t;
+  __device__ EpiTracer(const Params& p, int role, bool on) : t(p, role) {
+    if (!on) t.base = nullptr;
+  }
+  __device__ __forceinline__ void ev(unsigned tag) { t.ev(tag); }
+#else
+  __device__ EpiTracer(const Params&, int, bool) {}
+  __device__ __forceinline__ void ev(unsigned) {}
+#endif
+};
 
 // kernel entry / exit wall-clock stamps (%globaltimer, ns; comparable across SMs) in the last two words of
 // the CTA's role-2 trace lane
@@ -483,8 +501,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
     if constexpr (kPair) mbar_arrive_cluster(a);
     else mbar_arrive(a);
   };
-  Tracer tr(p, 3);
-  if (threadIdx.x != kEpiWarp0 * 32) tr.base = nullptr;
+  EpiTracer tr(p, 3, threadIdx.x == kEpiWarp0 * 32);
   if (!staged) griddep_wait();  // direct stores: earlier kernels may still be using the destination
 
   // ---- conv0 epilogue of local tile `it`
@@ -596,7 +613,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
       // where the four rows go, computed while the TMEM loads are in flight and pinned in registers (left
       // to itself the compiler re-derives every address from the kernel parameters inside the row loop,
       // and the epilogue is bound by instruction issue)
-      uint32_t saddr[4];
+      [[maybe_unused]] uint32_t saddr[4];
       if constexpr (ts == 1) {
         const uint32_t unit_x = ((uint32_t)ccol >> 4) << 4, stage_col = stage_buf + ((uint32_t)ccol & 15);
 #pragma unroll

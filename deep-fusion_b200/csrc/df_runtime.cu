@@ -104,4 +104,31 @@ int df_event_destroy(void* e) {
   return 0;
 }
 
+// ---- CUDA graphs: replay a captured sequence of df_* calls with one launch (launch-bound loops)
+int df_graph_begin(void* s) {
+  if (!s) return df::fail(DF_E_INVALID, "graph capture needs an explicit stream (df_stream_create)");
+  DF_CUDA(cudaStreamBeginCapture((cudaStream_t)s, cudaStreamCaptureModeThreadLocal));
+  return 0;
+}
+int df_graph_end(void* s, void** graph_exec) {
+  if (!graph_exec) return df::fail(DF_E_INVALID, "graph: null out");
+  *graph_exec = nullptr;
+  cudaGraph_t g = nullptr;
+  DF_CUDA(cudaStreamEndCapture((cudaStream_t)s, &g));
+  cudaGraphExec_t ge = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return df::fail((int)e, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  *graph_exec = ge;
+  return 0;
+}
+int df_graph_launch(void* graph_exec, void* s) {
+  DF_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)s));
+  return 0;
+}
+int df_graph_destroy(void* graph_exec) {
+  if (graph_exec) DF_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+  return 0;
+}
+
 }  // extern "C"

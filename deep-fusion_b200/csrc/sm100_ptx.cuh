@@ -79,8 +79,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // r01_trace_cfg3_v9b.log).  Slow path: ONE lane polls, the rest park at the warp barrier; hundreds of
 // threads spinning on try_wait saturate the SM's MIO/sync pipeline and slow down every other warp
 // (measured: 3-5x on both MMA issue and epilogue math, profiles/r01_trace_*.log).
-// kBackoffNs > 0 adds a sleep between polls for waits that are expected to be long.
-template <int kBackoffNs = 0>
+// kBackoffNs > 0 adds a sleep between polls: a poller shares its scheduler with working warps (ncu: the
+// 16 pollers of the first accumulator wait alone executed 10 % of the kernel's instructions).
+template <int kBackoffNs = 32>
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   if (__all_sync(0xffffffffu, mbar_test_wait(bar, parity))) return;
   if ((threadIdx.x & 31) == 0) {

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "df_free", "df_memset", "df_host_register", "df_host_unregister", "df_h2d", "df_d2h", "df_stream_create",
     "df_stream_sync", "df_stream_destroy", "df_event_create", "df_event_record", "df_stream_wait_event", "df_event_elapsed_ms",
     "df_event_destroy", "df_concat_check", "df_concat_run", "df_conv_create", "df_conv_run", "df_conv_query",
-    "df_conv_destroy", "df_conv_debug_trace",
+    "df_conv_destroy", "df_conv_debug_trace", "df_graph_begin", "df_graph_end", "df_graph_launch", "df_graph_destroy",
 ]
 
 
@@ -77,6 +77,11 @@ def lib():
         l.df_event_record.argtypes = [C.c_void_p, C.c_void_p]
         l.df_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         l.df_event_destroy.argtypes = [C.c_void_p]
+        l.df_stream_wait_event.argtypes = [C.c_void_p, C.c_void_p]
+        l.df_graph_begin.argtypes = [C.c_void_p]
+        l.df_graph_end.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        l.df_graph_launch.argtypes = [C.c_void_p, C.c_void_p]
+        l.df_graph_destroy.argtypes = [C.c_void_p]
         l.df_concat_check.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
         l.df_concat_run.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_void_p,
                                     C.c_long, C.c_void_p]
@@ -176,6 +181,51 @@ class Event:
     def __del__(self):
         try:
             lib().df_event_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+class Stream:
+    def __init__(self):
+        p = C.c_void_p()
+        check(lib().df_stream_create(C.byref(p)))
+        self.ptr = p.value
+
+    def sync(self):
+        sync(self.ptr)
+
+    def __del__(self):
+        try:
+            lib().df_stream_destroy(self.ptr)
+        except Exception:
+            pass
+
+
+class Graph:
+    """Captured sequence of launches on a Stream (df_graph_*): `with Graph(stream) as g: ...` then g.launch()."""
+
+    def __init__(self, stream: Stream):
+        self.stream, self.exec = stream, None
+
+    def __enter__(self):
+        check(lib().df_graph_begin(self.stream.ptr))
+        return self
+
+    def __exit__(self, et, ev, tb):
+        p = C.c_void_p()
+        rc = lib().df_graph_end(self.stream.ptr, C.byref(p))
+        if et is None:
+            check(rc)
+        self.exec = p.value
+        return False
+
+    def launch(self):
+        check(lib().df_graph_launch(self.exec, self.stream.ptr))
+
+    def __del__(self):
+        try:
+            if self.exec:
+                lib().df_graph_destroy(self.exec)
         except Exception:
             pass
 

@@ -56,6 +56,12 @@ int df_event_record(void *event, void *stream);
 int df_stream_wait_event(void *stream, void *event);
 int df_event_elapsed_ms(void *start, void *stop, float *ms); /* synchronises on `stop` */
 int df_event_destroy(void *event);
+/* CUDA graphs (no reference counterpart; the reference's callers loop over submit() on the host): capture
+ * the df_* calls issued on `stream` between begin and end, then replay them with one launch each time. */
+int df_graph_begin(void *stream);                    /* stream from df_stream_create, not NULL */
+int df_graph_end(void *stream, void **graph_exec);
+int df_graph_launch(void *graph_exec, void *stream);
+int df_graph_destroy(void *graph_exec);
 
 /* ---- concat(+ReLU): replaces op_concat<T>::infer + jit_concat_kernel
  *      (src/op_concat.cc:22-72, src/jit_concat_kernel.cc:30-197) ---------------------------
