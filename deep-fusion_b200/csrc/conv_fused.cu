@@ -41,7 +41,8 @@ namespace {
 constexpr int kEpiWarp0 = 4;    // warps 0..3: TMA(A) | MMA | TMA(W) | TMEM alloc
 constexpr int kEpiWarps = 16;   // epilogue warps (four per TMEM lane quarter), all on the same work unit
 constexpr int kStageBufs = 2;   // output staging buffers (unit c uses buffer c & 1)
-constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);  // 640
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);  // 640: a 21st warp would round the register
+                                                        // allocation up to 24 warps (80 registers per thread)
 constexpr int kTileM = 128;
 constexpr int kMaxAStages = 4;
 constexpr int kMaxBStages = 8;
@@ -864,6 +865,36 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
       }
+      // ============================ GEMM2 issuer (all weights resident) ========================
+      if (g.w0_res() && g.w1_res()) {
+        const uint32_t idesc1 = make_idesc_i8(kTileM, g.nc1(), 0, 1);
+        const uint64_t desc1_hi = make_smem_desc(0, 16, 8 * g.swb1(), layout_of(g.swb1()));
+        const uint64_t w1_desc = desc1_hi | ((sbase + p.off_w1) >> 4);
+        const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid) >> 4);
+        const uint32_t w1_step = g.w1_block_bytes() >> 4, mid_step_kb = g.mid_kb_stride() >> 4;
+        const int nks1_full = g.swb1() >> 5;
+        mbar_wait(smem_u32(&bar->res_full), 0);
+        uint32_t c = 0;
+        for (int it = 0; it < n_local; ++it) {
+          mbar_wait(smem_u32(&bar->mid_full[0]), it & 1);
+          for (int j = 0; j < g.n_chunks(); ++j, ++c) {
+            const uint32_t cb = c & 1;
+            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
+#pragma unroll
+            for (int kb = 0; kb < g.nkb1(); ++kb) {
+              const uint64_t b_desc = w1_desc + (uint64_t)((j * g.nkb1() + kb) * w1_step);
+              const uint64_t a_desc = mid_desc + kb * mid_step_kb;
+              const int nks = (kb == g.nkb1() - 1) ? g.ks1_last() : nks1_full;
+#pragma unroll
+              for (int ks = 0; ks < nks; ++ks) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, (kb | ks) != 0);
+            }
+            umma_commit(smem_u32(&bar->acc1_full[cb]));
+          }
+          umma_commit(smem_u32(&bar->mid_empty[0]));
+        }
+      }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ======================================
@@ -944,14 +975,35 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       };
 
-      if (g.w1_res()) {
-        // Readiness-driven issue.  With W1 resident only GEMM1 consumes the weight ring, so the two
-        // GEMM streams are independent: issue a GEMM2 chunk whenever its accumulator is free and the
-        // intermediate tile is there (it unblocks the epilogue, the longer path), otherwise the next
-        // TAP of the next GEMM1 (a whole tap row queued in front of a chunk leaves the epilogue idle for
-        // longer than the chunk takes).  A fixed order suffers head-of-line blocking in both directions
-        // (profiles/r01_trace_cfg3_v4.log).
-        int g1_it = 0, g1_kh = 0, g1_kw = 0, g2_it = 0, g2_j = 0;
+      if (g.w1_res() && g.w0_res()) {
+        // All weights resident: the two GEMM streams are independent and each has its own issuing
+        // thread: this one runs GEMM1 as far ahead as accumulators and halo stages allow, warp 2 (done
+        // with the weight loads) issues every conv1 chunk the moment its accumulator is free.  One
+        // thread polling for both spent ~110 cycles per MMA on issue and left the epilogue waiting behind
+        // whatever GEMM1 work was queued (profiles/r01_trace_cfg3_v8.log).
+        for (int it = 0; it < n_local; ++it) {
+          const int ab = it % g.n_acc0();
+          mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / g.n_acc0()) & 1) ^ 1);
+          mbar_wait(smem_u32(&bar->a_full[sa]), a_par);
+          tc_fence_after_sync();
+          tr.ev(10);
+          const uint32_t d_tmem = tmem + ab * g.OC();
+          const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swb()) >> 4);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) gemm1_taps(kh, 0, 3, d_tmem, a_tile);
+          umma_commit(smem_u32(&bar->a_empty[sa]));
+          umma_commit(smem_u32(&bar->acc0_full[ab]));
+          tr.ev(11);
+          if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
+          a_off_px += p.tile_step_mod;
+          if (a_off_px >= p.Wp) a_off_px -= p.Wp;
+        }
+      } else if (g.w1_res() && !g.w0_res()) {
+        // W1 resident, W0 streamed by warp 2: one thread issues both GEMMs, readiness-driven -- a GEMM2
+        // chunk whenever its accumulator is free and the intermediate tile is there (it unblocks the
+        // epilogue, the longer path), otherwise the next tap row of the next GEMM1.  A fixed order
+        // suffers head-of-line blocking in both directions (profiles/r01_trace_cfg3_v4.log).
+        int g1_it = 0, g1_kh = 0, g2_it = 0, g2_j = 0;
         bool g2_open = false;
         uint64_t a_tile = 0;
         uint32_t d0 = 0;
@@ -990,7 +1042,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (!did && g1_it < n_local) {
             bool ok = true;
-            if (g1_kh == 0 && g1_kw == 0) {
+            if (g1_kh == 0) {
               const int ab = g1_it % g.n_acc0();
               ok = mbar_test_wait(smem_u32(&bar->acc0_empty[ab]), ((g1_it / g.n_acc0()) & 1) ^ 1) &&
                    mbar_test_wait(smem_u32(&bar->a_full[sa]), a_par);
@@ -1002,14 +1054,10 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             }
             if (ok) {
-              gemm1_taps(g1_kh, g1_kw, g1_kw + 1, d0, a_tile);
+              gemm1_taps(g1_kh, 0, 3, d0, a_tile);
               did = true;
               idle = 0;
-              if (++g1_kw == 3) {
-                g1_kw = 0;
-                ++g1_kh;
-              }
-              if (g1_kh == 3) {
+              if (++g1_kh == 3) {
                 umma_commit(smem_u32(&bar->a_empty[sa]));
                 umma_commit(smem_u32(&bar->acc0_full[g1_it % g.n_acc0()]));
                 tr.ev(11);
@@ -1352,11 +1400,11 @@ typedef cudaError_t (*AttrFn)(uint32_t smem);
 // Launch with programmatic stream serialization: back-to-back launches on one stream overlap the next
 // launch's prologue with this launch's tail (see griddep_launch_dependents in the kernels).
 template <class Kernel>
-cudaError_t launch_pdl(Kernel kernel, int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
-                       const CUtensorMap& w1, const DstMaps& d, const Params& p) {
+cudaError_t launch_pdl(Kernel kernel, int grid, int threads, uint32_t smem, cudaStream_t st, const CUtensorMap& a,
+                       const CUtensorMap& w0, const CUtensorMap& w1, const DstMaps& d, const Params& p) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1370,7 +1418,7 @@ cudaError_t launch_pdl(Kernel kernel, int grid, uint32_t smem, cudaStream_t st, 
 template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
 cudaError_t launch_conv(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
                         const CUtensorMap& w1, const DstMaps& d, const Params& p) {
-  return launch_pdl(conv_fused_kernel<G, kDst, kDown0, kDown1, kNanSafe>, grid, smem, st, a, w0, w1, d, p);
+  return launch_pdl(conv_fused_kernel<G, kDst, kDown0, kDown1, kNanSafe>, grid, kThreads, smem, st, a, w0, w1, d, p);
 }
 template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
 cudaError_t attr_conv(uint32_t smem) {
@@ -1385,7 +1433,7 @@ struct KernelFn {
 template <class G, int kDst>
 cudaError_t launch_pair(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
                         const CUtensorMap& w1, const DstMaps& d, const Params& p) {
-  return launch_pdl(conv_pair_kernel<G, kDst>, grid, smem, st, a, w0, w1, d, p);
+  return launch_pdl(conv_pair_kernel<G, kDst>, grid, kThreads, smem, st, a, w0, w1, d, p);
 }
 template <class G, int kDst>
 cudaError_t attr_pair(uint32_t smem) {
