@@ -532,9 +532,8 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
       const uint32_t off0 = (uint32_t)m_row0 * g.swb1() + (uint32_t)(ch0 - kb * g.swb1());
       const uint32_t mid_kb = mid + kb * g.mid_kb_stride();
       tmem_ld_wait();
-      if (last) {  // accumulator is in registers: the tensor pipe may overwrite it
+      if (last) {  // accumulator is in registers (tcgen05.wait::ld is warp-wide): the tensor pipe may overwrite it
         tc_fence_before_sync();
-        __syncwarp();
         if (lane == 0) arrive(a_acc0_empty + 8 * ab);
       }
 #pragma unroll
@@ -628,32 +627,32 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
         stage_checked = true;
       }
       tmem_ld_wait();
-      if (last) {  // accumulator is in registers: the tensor pipe may overwrite it
+      if (last) {  // accumulator is in registers (tcgen05.wait::ld is warp-wide): the tensor pipe may overwrite it
         tc_fence_before_sync();
-        __syncwarp();
         if (lane == 0) arrive(a_acc1_empty + 8 * cb);
       }
+      // Padding rows are computed like any other and only their store is predicated off: a branch around
+      // the row costs three control instructions and a branch-resolve stall per row, the wasted arithmetic
+      // (6..8 % of the rows for the BASELINE shapes) is cheaper.
 #pragma unroll
       for (int ri = 0; ri < 4; ++ri) {
         const int rr = rinfo[ri];
-        if (rr >= 0) {
-          uint32_t v[CH], w[ts == 1 ? CH / 4 : CH];
+        uint32_t v[CH], w[ts == 1 ? CH / 4 : CH];
 #pragma unroll
-          for (int i = 0; i < CH; ++i) v[i] = acc[ri >> 1][4 * (i / 2) + 2 * (ri & 1) + (i & 1)];
-          finish_conv1<kDst, kDown1, kNanSafe, CH, kUniK>(v, c4, s4, k4, k_uni, fast1, relu1, w);
-          if constexpr (ts == 1) {
-            if (staged) {  // 16-byte unit XOR row-inside-the-1024-B-atom, as SWIZZLE_128B wants
-              sts_bytes<CH>(saddr[ri], w);
-            } else {
-              uint8_t* out = static_cast<uint8_t*>(p.dst) + (size_t)rr * g.OC1() + ch0;
-              if constexpr (CH == 8) *reinterpret_cast<uint2*>(out) = make_uint2(w[0], w[1]);
-              else *reinterpret_cast<uint32_t*>(out) = w[0];
-            }
-          } else {
-            uint4* out = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.dst) + ((size_t)rr * g.OC1() + ch0) * 4);
-#pragma unroll
-            for (int i = 0; i < CH / 4; ++i) out[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        for (int i = 0; i < CH; ++i) v[i] = acc[ri >> 1][4 * (i / 2) + 2 * (ri & 1) + (i & 1)];
+        finish_conv1<kDst, kDown1, kNanSafe, CH, kUniK>(v, c4, s4, k4, k_uni, fast1, relu1, w);
+        if constexpr (ts == 1) {
+          if (staged) {  // 16-byte unit XOR row-inside-the-1024-B-atom, as SWIZZLE_128B wants
+            if (rr >= 0) sts_bytes<CH>(saddr[ri], w);
+          } else if (rr >= 0) {
+            uint8_t* out = static_cast<uint8_t*>(p.dst) + (size_t)rr * g.OC1() + ch0;
+            if constexpr (CH == 8) *reinterpret_cast<uint2*>(out) = make_uint2(w[0], w[1]);
+            else *reinterpret_cast<uint32_t*>(out) = w[0];
           }
+        } else if (rr >= 0) {
+          uint4* out = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.dst) + ((size_t)rr * g.OC1() + ch0) * 4);
+#pragma unroll
+          for (int i = 0; i < CH / 4; ++i) out[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
         }
       }
     };
