@@ -71,6 +71,9 @@ struct Params {
   uint32_t off_w0, w0_block_bytes, off_w1, w1_block_bytes;
   uint32_t off_b, b_stage_bytes;
   int relu1, round0, round1, nan_safe;
+  int conv0_only;      // conv() without the 1x1 stage (include/deepfusion.h:121-129): the 3x3 accumulator goes
+                       // through the conv1 finish (bias1 / scale1 / relu1 / round1 hold the conv0 values,
+                       // OC1 == OC, chunks of 128 accumulator columns); run-time geometry only
   int stage_out;       // 1-byte destinations: conv1 chunks are staged in smem and leave by TMA store
   uint32_t off_stage;  // kStageBufs staging buffers of kTileM x 128 B (128 B-swizzled rows)
   const float *bias0, *scale0, *bias1, *scale1;
@@ -477,6 +480,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
   const bool relu1 = p.relu1 != 0;
   const bool fast1 = G::is_static ? true : (p.fast1 != 0);
   const int k_uni = p.k1_uniform;  // static geometries: never 0 (df_conv_create)
+  const bool c0_only = !G::is_static && p.conv0_only != 0;
   const int q_first = 2 * p.Wp;
   // staged output (1-byte destinations, see store_staged_chunk): always for the static geometries
   constexpr bool kCanStage = (kDst == DF_U8 || kDst == DF_S8);
@@ -585,13 +589,19 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
     }
     const int cb = c & 1;
     tr.ev(36);
-    mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c >> 1) & 1);
+    // conv0-only operator: the chunk is 128 columns of the 3x3 accumulator of this tile
+    const int ab0 = it % g.n_acc0();
+    if (!c0_only) mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c >> 1) & 1);
+    else if (j == 0) mbar_wait_warp(smem_u32(&bar->acc0_full[ab0]), (it / g.n_acc0()) & 1);
     tc_fence_after_sync();
     tr.ev(32);
     bool stage_checked = !staged;
+    // which barrier tells the tensor pipe that the accumulator may be overwritten, and is it this chunk's turn
+    const uint32_t a_release = c0_only ? a_acc0_empty + 8 * ab0 : a_acc1_empty + 8 * cb;
+    const bool releases = !c0_only || j == g.n_chunks() - 1;
     int ncols = g.OC1() - j * g.nc1();  // real columns in this chunk
     if (ncols > g.nc1()) ncols = g.nc1();
-    const uint32_t t_base = lane_addr + kAcc1Col + cb * kAcc1Stride;
+    const uint32_t t_base = c0_only ? lane_addr + ab0 * g.OC() + j * g.nc1() : lane_addr + kAcc1Col + cb * kAcc1Stride;
     const uint32_t stage_buf = sbase + p.off_stage + cb * kStageBytes;
     const int nb32 = ncols / 32, nblk = nb32 + (ncols - nb32 * 32) / 16;
     auto block = [&](auto ch_c, auto unik_c, int col0, bool last) {
@@ -627,9 +637,9 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
         stage_checked = true;
       }
       tmem_ld_wait();
-      if (last) {  // accumulator is in registers (tcgen05.wait::ld is warp-wide): the tensor pipe may overwrite it
+      if (last && releases) {  // accumulator is in registers (tcgen05.wait::ld is warp-wide): the tensor pipe may overwrite it
         tc_fence_before_sync();
-        if (lane == 0) arrive(a_acc1_empty + 8 * cb);
+        if (lane == 0) arrive(a_release);
       }
       // Padding rows are computed like any other and only their store is predicated off: a branch around
       // the row costs three control instructions and a branch-resolve stall per row, the wasted arithmetic
@@ -668,10 +678,10 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
         else block(std::integral_constant<int, 4>{}, std::false_type{}, nb32 * 32, last);
       }
     }
-    if (!released) {
+    if (!released && releases) {
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) arrive(a_acc1_empty + 8 * cb);
+      if (lane == 0) arrive(a_release);
     }
     tr.ev(35);
     if (staged) {
@@ -685,6 +695,11 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
   // ---- the unit stream (see above), identical in every epilogue warp
   const int nch = g.n_chunks();
   uint32_t c = 0;
+  if (c0_only) {  // conv0-only operator: no intermediate tile, every unit finishes accumulator columns
+    for (int it = 0; it < n_local; ++it)
+      for (int j = 0; j < nch; ++j, ++c) unit_c(it, j, c);
+    return;
+  }
   if (n_local > 0) unit_e0(0);
   for (int it = 0; it < n_local; ++it) {
     for (int j = 0; j < nch; ++j, ++c) {
@@ -836,7 +851,8 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 2) {
     // =============================== TMA producer: weights =================================
     if (elect_one()) {
-      const int n_w0 = 9 * g.nkb(), n_w1 = g.n_chunks() * g.nkb1();
+      const bool c0_only = !G::is_static && p.conv0_only != 0;
+      const int n_w0 = 9 * g.nkb(), n_w1 = c0_only ? 0 : g.n_chunks() * g.nkb1();
       if (g.w0_res() || g.w1_res()) {
         const uint32_t full = smem_u32(&bar->res_full);
         mbar_expect_tx(full, (g.w0_res() ? n_w0 * g.w0_block_bytes() : 0) + (g.w1_res() ? n_w1 * g.w1_block_bytes() : 0));
@@ -865,7 +881,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       // ============================ GEMM2 issuer (all weights resident) ========================
-      if (g.w0_res() && g.w1_res()) {
+      if (g.w0_res() && g.w1_res() && !c0_only) {
         const uint32_t idesc1 = make_idesc_i8(kTileM, g.nc1(), 0, 1);
         const uint64_t desc1_hi = make_smem_desc(0, 16, 8 * g.swb1(), layout_of(g.swb1()));
         const uint64_t w1_desc = desc1_hi | ((sbase + p.off_w1) >> 4);
@@ -974,7 +990,8 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       };
 
-      if (g.w1_res() && g.w0_res()) {
+      if ((g.w1_res() && g.w0_res()) || (!G::is_static && p.conv0_only)) {
+        // (conv0-only operator: there is no GEMM2 at all.)
         // All weights resident: the two GEMM streams are independent and each has its own issuing
         // thread: this one runs GEMM1 as far ahead as accumulators and halo stages allow, warp 2 (done
         // with the weight loads) issues every conv1 chunk the moment its accumulator is free.  One
@@ -1634,11 +1651,11 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   int rc = validate(d);
   if (rc) return rc;
   if (!wei || !scale0) return df::fail(DF_E_INVALID, "conv: null weights / scales");
-  if ((d->bia0_dt != DF_UNDEF && !bia0) || (d->bia1_dt != DF_UNDEF && !bia1))
+  if ((d->bia0_dt != DF_UNDEF && !bia0) || (d->oc1 != 0 && d->bia1_dt != DF_UNDEF && !bia1))
     return df::fail(DF_E_INVALID, "conv: bias dtype given but pointer is null");
   // ---- the B200 path: fused 3x3 s1 p1 + 1x1
-  if (d->oc1 == 0) return df::fail(DF_E_UNSUPPORTED, "conv0-only operator is not on the B200 path yet");
-  if (!wei1 || !scale1) return df::fail(DF_E_INVALID, "conv: null 1x1 weights / scales");
+  const bool conv0_only = d->oc1 == 0;  // conv() without the 1x1 stage (include/deepfusion.h:121-129)
+  if (!conv0_only && (!wei1 || !scale1)) return df::fail(DF_E_INVALID, "conv: null 1x1 weights / scales");
   if (d->kh != 3 || d->kw != 3 || d->sh != 1 || d->sw != 1 || d->ph != 1 || d->pw != 1)
     return df::fail(DF_E_UNSUPPORTED, "B200 path supports k3 s1 p1 only");
   if (d->oc > 256) return df::fail(DF_E_UNSUPPORTED, "B200 path supports conv0 oc <= 256 (got %d)", d->oc);
@@ -1651,7 +1668,8 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   p.W = d->iw;
   p.IC = d->ic;
   p.OC = d->oc;
-  p.OC1 = d->oc1;
+  p.OC1 = conv0_only ? d->oc : d->oc1;  // destination channels
+  p.conv0_only = conv0_only ? 1 : 0;
   p.swb = pick_swb(d->ic);
   p.nkb = (d->ic + p.swb - 1) / p.swb;
   p.ks_last = (d->ic - (p.nkb - 1) * p.swb + 31) / 32;
@@ -1665,12 +1683,12 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   p.r8_dw = 8 % p.Wp;
   p.r8_dn = (8 / p.Wp) / p.Hp;
   p.r8_dh = (8 / p.Wp) % p.Hp;
-  p.nc1 = d->oc1 < 128 ? d->oc1 : 128;
-  p.n_chunks = (d->oc1 + p.nc1 - 1) / p.nc1;
+  p.nc1 = p.OC1 < 128 ? p.OC1 : 128;
+  p.n_chunks = (p.OC1 + p.nc1 - 1) / p.nc1;
   p.n_acc0 = d->oc <= 128 ? 2 : 1;
-  p.relu1 = d->relu1;
+  p.relu1 = conv0_only ? d->relu0 : d->relu1;
   p.round0 = d->round0;
-  p.round1 = d->round1;
+  p.round1 = conv0_only ? d->round0 : d->round1;
 
   // ---- shared memory plan
   const int oc1_pad = p.n_chunks * p.nc1;
@@ -1696,7 +1714,7 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   p.w0_block_bytes = (uint32_t)p.OC * p.swb;
   p.w1_block_bytes = (uint32_t)p.nc1 * p.swb1;
   const uint32_t w0_bytes = align_up(9 * p.nkb * p.w0_block_bytes, 1024);
-  const uint32_t w1_bytes = align_up(p.n_chunks * p.nkb1 * p.w1_block_bytes, 1024);
+  const uint32_t w1_bytes = conv0_only ? 0 : align_up(p.n_chunks * p.nkb1 * p.w1_block_bytes, 1024);
   const uint32_t avail = kSmemLimit - 1024;  // base alignment slack
   const uint32_t fixed = off;
   if (fixed + 2 * p.a_stage_bytes + w0_bytes + w1_bytes <= avail) {
@@ -1770,8 +1788,8 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
             wei[blocked_off(o, i, tap / 3, tap % 3, p.IC, 3, 3)];
       }
     }
-  std::vector<int8_t> w1((size_t)p.n_chunks * p.nkb1 * p.nc1 * p.swb1, 0);
-  for (int j = 0; j < p.n_chunks; ++j) {
+  std::vector<int8_t> w1((size_t)p.n_chunks * p.nkb1 * p.nc1 * p.swb1, 0);  // stays zero (and unused) for conv0-only
+  for (int j = 0; j < (conv0_only ? 0 : p.n_chunks); ++j) {
     const int ncols = p.OC1 - j * p.nc1 < p.nc1 ? p.OC1 - j * p.nc1 : p.nc1;  // real columns of this chunk
     for (int r = 0; r < ncols; ++r) {
       const int q = j * p.nc1 + col_to_channel(r, ncols);
@@ -1789,6 +1807,11 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
     finite = finite && isfinite(b0[o]) && isfinite(s0[o]);
   }
   for (int q = 0; q < p.OC1; ++q) {
+    if (conv0_only) {  // the final stage of the conv0-only operator uses the conv0 bias / scales
+      b1[q] = b0[q];
+      s1[q] = s0[q];
+      continue;
+    }
     b1[q] = d->bia1_dt != DF_UNDEF ? bias_to_f32(d->bia1_dt, bia1, q) : 0.f;
     s1[q] = scale1[d->nscale1 > 1 ? q : 0];
     finite = finite && isfinite(b1[q]) && isfinite(s1[q]);
@@ -1799,8 +1822,8 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   // channel is narrower than 2^23 and C[q] = bias + lo - 2^23 is exactly representable.
   std::vector<int> k1(p.OC1, 0);
   std::vector<float> c1(p.OC1, 0.f);
-  bool fast1 = finite;
-  {
+  bool fast1 = finite && !conv0_only;  // (the 3x3 accumulator's range is far wider than 2^23)
+  if (!conv0_only) {
     std::vector<long long> lo(p.OC1), hi(p.OC1);
     long long lo_min = 0, hi_max = 0;
     for (int q = 0; q < p.OC1; ++q) {
@@ -1830,6 +1853,8 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
       uniform = false;  // retry with per-channel offsets
     }
     p.k1_uniform = (fast1 && uniform) ? k1[0] : 0;
+  } else {
+    p.k1_uniform = 0;
   }
   if (getenv("DF_NO_FAST_CONV1")) fast1 = false;  // test hook: exercise the I2F path
   if (!fast1) p.k1_uniform = 0;
@@ -1880,10 +1905,10 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   // conversion with ONE constant K, and (1-byte destinations) staged output; anything else runs the
   // run-time-geometry kernel.
   const bool one_byte = d->dst_dt == DF_U8 || d->dst_dt == DF_S8;
-  const bool static_ok = p.fast1 && p.k1_uniform != 0 && d->round0 == DF_ROUND_NEAREST && d->round1 == DF_ROUND_NEAREST &&
+  const bool static_ok = !conv0_only && p.fast1 && p.k1_uniform != 0 && d->round0 == DF_ROUND_NEAREST && d->round1 == DF_ROUND_NEAREST &&
                          !p.nan_safe && !getenv("DF_FORCE_DYNAMIC_GEOMETRY");  // (env: test hook for the generic path)
   if (!static_ok || (one_byte && !p.stage_out)) op->geom_id = 0;
-  op->kernel = pick_kernel(op->geom_id, d->dst_dt, d->round0 == DF_ROUND_DOWN, d->round1 == DF_ROUND_DOWN, p.nan_safe != 0);
+  op->kernel = pick_kernel(op->geom_id, d->dst_dt, p.round0 == DF_ROUND_DOWN, p.round1 == DF_ROUND_DOWN, p.nan_safe != 0);
   DF_TRY_CUDA(op->kernel.attr(op->smem_bytes));
 
   // ---- CTA-pair variant: BASELINE cfg3 with everything resident once the weights are split in two.
@@ -2048,7 +2073,7 @@ extern "C" int df_conv_query(const df_conv* op, df_conv_info* info) {
   info->b_stages = op->pair ? 0 : p.SB;
   info->padded_w = p.Wp;
   info->padded_h = p.Hp;
-  info->macs_per_image = (double)p.H * p.W * (9.0 * p.IC * p.OC + (double)p.OC * p.OC1);
+  info->macs_per_image = (double)p.H * p.W * (9.0 * p.IC * p.OC + (p.conv0_only ? 0.0 : (double)p.OC * p.OC1));
   info->mma_efficiency = (double)op->desc.n * p.H * p.W / ((double)info->tiles_per_launch * kTileM);
   return 0;
 }

@@ -69,6 +69,30 @@ def test_conv_submit(H, name):
     assert op.launches() in (1, 4)
 
 
+@pytest.mark.parametrize("dst_dt", ["u8", "f32"])
+def test_conv0_only_submit(H, dst_dt):
+    """The reference's 9-argument conv(): 3x3 stage only (include/deepfusion.h:121-129)."""
+    from dfb200 import layout, synth
+    n, h, w, ic, oc = 2, 9, 7, 32, 48
+    src_a = synth.src_u8(1, (n, h, w, ic))
+    w0 = synth.wei_s8(2, (oc, ic, 3, 3))
+    b0 = synth.bias(4, oc, "s32")
+    s0 = synth.channel_scales(oc, 10)
+    wb = layout.oihw_to_blocked(w0)
+    src = H.Memory((n, ic, h, w), "nhwc", "u8")
+    src.set(src_a)
+    wei = H.Memory((oc, ic, 3, 3), "OIhw4i16o4i", "s8")
+    wei.array().reshape(-1)[...] = wb
+    bia = H.Memory((oc,), "x", "s32", nchw=False)
+    bia.set(b0)
+    dst = H.Memory((n, oc, h, w), "nhwc", dst_dt)
+    op = H.conv(src, wei, bia, (1, 1), (1, 1), dst, conv0_relu=True, conv0_scales=s0)
+    op.submit()
+    d = O.make_desc(n, h, w, ic, oc, 0, cases.DT[dst_dt], O.S32, 0, relu0=1, nscale0=oc)
+    want = O.conv(d, src_a, wb, b0, s0)
+    assert np.array_equal(dst.array().view(np.uint8), want.view(np.uint8))
+
+
 def test_concat_feeds_conv_on_device(H):
     """concat+ReLU output consumed by the fused conv without leaving HBM (ext API)."""
     from dfb200 import synth

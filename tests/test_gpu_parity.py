@@ -109,6 +109,36 @@ def test_conv_batch_properties_at_full_size(df):
     op.close()
 
 
+# conv() without the 1x1 stage (reference 9-argument overload, include/deepfusion.h:121-129)
+CONV0_ONLY = [  # (n, h, w, ic, oc, bias dtype, scale exponent)
+    (2, 7, 6, 32, 48, "s32", 10),     # ragged, one block of 32 columns + one of 16
+    (3, 9, 11, 64, 64, "s8", 12),
+    (2, 14, 14, 128, 128, None, 13),  # two accumulators, one chunk
+    (2, 5, 9, 64, 256, "f32", 12),    # OC = 256: one accumulator, two chunks of 128 columns
+    (1, 28, 28, 256, 144, "u8", 14),  # weights streamed, partial second chunk
+]
+
+
+@pytest.mark.parametrize("shape", CONV0_ONLY, ids=lambda s: f"{s[3]}to{s[4]}_{s[1]}x{s[2]}")
+@pytest.mark.parametrize("dst", ["u8", "s8", "s32", "f32"])
+def test_conv0_only_operator(df, shape, dst):
+    n, h, w, ic, oc, bdt, k0 = shape
+    from dfb200 import layout, synth
+    src = synth.src_u8(1, (n, h, w, ic))
+    w0 = synth.wei_s8(2, (oc, ic, 3, 3))
+    b0 = synth.bias(4, oc, bdt) if bdt else None
+    s0 = synth.channel_scales(oc, k0)
+    wb = layout.oihw_to_blocked(w0)
+    for relu0, r0 in ((0, 0), (1, 1)):
+        op = df.Conv(n, h, w, ic, oc, 0, cases.DT[dst], wb, None, b0, None, s0, (1.0,), cases.DT[bdt], 0, relu0=bool(relu0), round0=r0)
+        got = op(src)
+        op.close()
+        d = O.make_desc(n, h, w, ic, oc, 0, cases.DT[dst], cases.DT[bdt], 0, relu0=relu0, round0=r0, nscale0=oc)
+        want = O.conv(d, src, wb, b0, s0)
+        assert got.shape == want.shape == (n, h, w, oc)
+        _assert_same(got, want, dst)
+
+
 def test_conv_zero_input_gives_bias_only(df):
     c = cases.ConvCase("zero", 2, 10, 10, 64, 64, 128, "s32", "s32", "s32")
     src, w0, w1, b0, b1, s0, s1 = c.tensors()
