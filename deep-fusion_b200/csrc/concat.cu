@@ -18,7 +18,10 @@
 namespace {
 
 constexpr int kMaxInputs = 16;  // per launch; longer lists are processed in groups
-constexpr int kThreads = 256;
+#ifndef DF_CONCAT_THREADS
+#define DF_CONCAT_THREADS 256
+#endif
+constexpr int kThreads = DF_CONCAT_THREADS;
 constexpr int kUnroll = 4;
 
 struct ConcatParams {
@@ -194,7 +197,7 @@ extern "C" int df_concat_run(int dtype, int relu, int n_inputs, const void* cons
     done_vecs += p.group_vecs;
     const unsigned per_block = kThreads * kUnroll;
     unsigned blocks = (p.total + per_block - 1) / per_block;
-    const unsigned cap = (unsigned)sms * 8;  // a multiple of the SM count, 8 resident CTAs each
+    const unsigned cap = (unsigned)sms * (2048 / kThreads);  // a multiple of the SM count, all CTAs resident
     if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
     // strided fast path when a block-count with (blocks * 256) % vectors-per-pixel == 0 exists nearby
