@@ -39,7 +39,14 @@ using namespace sm100;
 namespace {
 
 constexpr int kEpiWarp0 = 4;    // warps 0..3: TMA(A) | MMA | TMA(W) | TMEM alloc
-constexpr int kEpiWarps = 16;   // epilogue warps (four per TMEM lane quarter), all on the same work unit
+constexpr int kEpiWarps = 16;   // epilogue warps (four per TMEM lane quarter)
+// 1 (default): all 16 warps on one unit.  2: two groups of 8 on alternate units -- measured slower on cfg3 /
+// cfg4 (19.4 vs 18.2 us, 98 vs 89 us), slightly faster on cfg1 (32.7 vs 35.2 us); kept as a build knob.
+#ifndef DF_EPI_GROUPS
+#define DF_EPI_GROUPS 1
+#endif
+constexpr int kEpiGroups = DF_EPI_GROUPS;             // groups of epilogue warps; group u % kEpiGroups runs unit u
+constexpr int kUnitWarps = kEpiWarps / kEpiGroups;    // warps that share one work unit (= arrivals per hand-off)
 constexpr int kStageBufs = 2;   // output staging buffers (unit c uses buffer c & 1)
 constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);  // 640: a 21st warp would round the register
                                                         // allocation up to 24 warps (80 registers per thread)
@@ -448,8 +455,10 @@ __device__ __forceinline__ void finish_conv1(const uint32_t* v, const float4* c4
 
 // ------------------------------------------------------------------------------ epilogue role
 // Work units: E0(t) = conv0 epilogue of tile t (TMEM acc0 -> u8 tile in smem) and C_j(t) = conv1 chunk j
-// of tile t (TMEM acc1 -> destination).  ALL 16 epilogue warps work on the same unit: warp w reads TMEM
-// lane quarter w % 4 and every fourth column block.  Units run in ONE fixed order,
+// of tile t (TMEM acc1 -> destination).  The 16 epilogue warps form kEpiGroups groups; the warps of a group
+// work on the same unit (warp w reads TMEM lane quarter w % 4 and every kBlockStride-th column block) and
+// unit u of the stream belongs to group u % kEpiGroups, each group taking its units in stream order
+// (kEpiGroups = 1 by default: see DF_EPI_GROUPS).  The stream order is fixed,
 //     E0(0) | C_0(t) .. C_{n-2}(t)  E0(t+1)  C_{n-1}(t) | ...
 // which keeps the single intermediate buffer and the two conv1 accumulators busy without ever making
 // the tensor pipe wait for the epilogue it feeds: E0(t+1) starts when GEMM2(t) has read the intermediate
@@ -467,7 +476,9 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
   const Geo<G> g{p};
   const uint32_t sbase = smem_u32(smem);
   const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-  const int cbi = (warp - kEpiWarp0) >> 2;      // this warp takes column blocks cbi, cbi + 4, ...
+  const int group = (warp - kEpiWarp0) / kUnitWarps;            // which units this warp works on
+  constexpr int kBlockStride = kUnitWarps / 4;                   // warps per lane quarter inside a group
+  const int cbi = ((warp - kEpiWarp0) % kUnitWarps) >> 2;       // this warp takes column blocks cbi, cbi + kBlockStride, ...
   const int m4 = lane & 3, r8 = lane >> 2;      // position inside the row-pair fragment
   const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
   const float* sb0 = reinterpret_cast<const float*>(smem + p.off_bias0);
@@ -487,7 +498,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
   const bool staged = kCanStage && (G::is_static || p.stage_out != 0);
   // where this thread's four rows (ri = 2 * h16 + hl -> tile row quarter * 32 + 8 * ri + r8) of the
   // current tile go: staging row (staged) or NHW pixel index (direct); -1 for padding positions
-  int row_it = -1, rinfo[4];
+  int row_it = -1, pos_it = 0, rinfo[4];  // rinfo is valid for tile row_it; the PosStates are at tile pos_it
   const int m_row0 = quarter * 32 + r8;
   // position bookkeeping is spread over the warp: lane l tracks tile row quarter * 32 + l and the four
   // rows a thread needs come by shuffle from lanes r8, r8 + 8, r8 + 16, r8 + 24
@@ -552,8 +563,8 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
       }
     };
     bool released = false;
-    for (int b = cbi; b < nblk; b += 4) {
-      const bool last = b + 4 >= nblk;
+    for (int b = cbi; b < nblk; b += kBlockStride) {
+      const bool last = b + kBlockStride >= nblk;
       released |= last;
       if (b < nb32) block(std::integral_constant<int, 8>{}, b * 32, last);
       else block(std::integral_constant<int, 4>{}, nb32 * 32, last);
@@ -571,8 +582,8 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
 
   // ---- conv1 chunk j of local tile `it` (c = global chunk counter of this CTA)
   auto unit_c = [&](int it, int j, uint32_t c) {
-    if (row_it != it) {  // tiles come in order: it == row_it + 1
-      if (row_it >= 0) {
+    if (row_it != it) {  // tiles come in increasing order (a group may have no conv1 unit in some tile)
+      for (; pos_it < it; ++pos_it) {
         pos_step(p, pos_tile, p.ts_dw, p.ts_dn, p.ts_dh);
         pos_step(p, pos_lane, p.ts_dw, p.ts_dn, p.ts_dh);
       }
@@ -667,8 +678,8 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
       }
     };
     bool released = false;
-    for (int b = cbi; b < nblk; b += 4) {
-      const bool last = b + 4 >= nblk;
+    for (int b = cbi; b < nblk; b += kBlockStride) {
+      const bool last = b + kBlockStride >= nblk;
       released |= last;
       if (G::is_static || k_uni != 0) {
         if (b < nb32) block(std::integral_constant<int, 8>{}, std::true_type{}, b * 32, last);
@@ -692,19 +703,22 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
     tr.ev(33);
   };
 
-  // ---- the unit stream (see above), identical in every epilogue warp
+  // ---- the unit stream (see above): every warp walks it, a group executes its own units
   const int nch = g.n_chunks();
-  uint32_t c = 0;
-  if (c0_only) {  // conv0-only operator: no intermediate tile, every unit finishes accumulator columns
+  uint32_t c = 0, u = 0;
+  auto mine = [&]() { return (u++ % kEpiGroups) == (uint32_t)group; };  // unit u belongs to group u % kEpiGroups
+  if (c0_only) {  // conv0-only operator: no intermediate tile, every unit finishes accumulator columns;
+                  // all chunks of a tile stay with one group (they share the tile's accumulator hand-off)
     for (int it = 0; it < n_local; ++it)
-      for (int j = 0; j < nch; ++j, ++c) unit_c(it, j, c);
+      for (int j = 0; j < nch; ++j, ++c)
+        if ((it % kEpiGroups) == group) unit_c(it, j, c);
     return;
   }
-  if (n_local > 0) unit_e0(0);
+  if (n_local > 0 && mine()) unit_e0(0);
   for (int it = 0; it < n_local; ++it) {
     for (int j = 0; j < nch; ++j, ++c) {
-      if (j == nch - 1 && it + 1 < n_local) unit_e0(it + 1);
-      unit_c(it, j, c);
+      if (j == nch - 1 && it + 1 < n_local && mine()) unit_e0(it + 1);
+      if (mine()) unit_c(it, j, c);
     }
   }
 }
@@ -771,12 +785,12 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(smem_u32(&bar->res_full), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar->acc0_full[i]), 1);
-      mbar_init(smem_u32(&bar->acc0_empty[i]), kEpiWarps);
-      mbar_init(smem_u32(&bar->mid_full[i]), kEpiWarps);
+      mbar_init(smem_u32(&bar->acc0_empty[i]), kUnitWarps);
+      mbar_init(smem_u32(&bar->mid_full[i]), kUnitWarps);
       mbar_init(smem_u32(&bar->mid_empty[i]), 1);
       mbar_init(smem_u32(&bar->acc1_full[i]), 1);
-      mbar_init(smem_u32(&bar->acc1_empty[i]), kEpiWarps);
-      mbar_init(smem_u32(&bar->stage_full[i]), kEpiWarps);
+      mbar_init(smem_u32(&bar->acc1_empty[i]), kUnitWarps);
+      mbar_init(smem_u32(&bar->stage_full[i]), kUnitWarps);
       mbar_init(smem_u32(&bar->stage_empty[i]), 1);
     }
     fence_mbar_init();
@@ -1196,12 +1210,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar->acc0_full[i]), 1);
-      mbar_init(smem_u32(&bar->acc0_empty[i]), 2 * kEpiWarps);
-      mbar_init(smem_u32(&bar->mid_full[i]), 2 * kEpiWarps);
+      mbar_init(smem_u32(&bar->acc0_empty[i]), 2 * kUnitWarps);
+      mbar_init(smem_u32(&bar->mid_full[i]), 2 * kUnitWarps);
       mbar_init(smem_u32(&bar->mid_empty[i]), 1);
       mbar_init(smem_u32(&bar->acc1_full[i]), 1);
-      mbar_init(smem_u32(&bar->acc1_empty[i]), 2 * kEpiWarps);
-      mbar_init(smem_u32(&bar->stage_full[i]), kEpiWarps);
+      mbar_init(smem_u32(&bar->acc1_empty[i]), 2 * kUnitWarps);
+      mbar_init(smem_u32(&bar->stage_full[i]), kUnitWarps);
       mbar_init(smem_u32(&bar->stage_empty[i]), 1);
     }
     fence_mbar_init();
