@@ -103,7 +103,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((time.time(), sm, rs, util))
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.0005)  # the timed region of a graph replay is only a few ms long
 
     def summary(self, t0, t1):
         if not self.ok or not self.samples:
