@@ -78,6 +78,7 @@ struct Params {
   uint32_t off_w0, w0_block_bytes, off_w1, w1_block_bytes;
   uint32_t off_b, b_stage_bytes;
   int relu1, round0, round1, nan_safe;
+  int dbg_no_mma;      // diagnostic (DF_DEBUG_NO_MMA=1): skip every tcgen05.mma, keep the hand-offs; results are garbage
   int conv0_only;      // conv() without the 1x1 stage (include/deepfusion.h:121-129): the 3x3 accumulator goes
                        // through the conv1 finish (bias1 / scale1 / relu1 / round1 hold the conv0 values,
                        // OC1 == OC, chunks of 128 accumulator columns); run-time geometry only
@@ -664,7 +665,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
         finish_conv1<kDst, kDown1, kNanSafe, CH, kUniK>(v, c4, s4, k4, k_uni, fast1, relu1, w);
         if constexpr (ts == 1) {
           if (staged) {  // 16-byte unit XOR row-inside-the-1024-B-atom, as SWIZZLE_128B wants
-            if (rr >= 0) sts_bytes<CH>(saddr[ri], w);
+            if (rr >= 0 && !(p.dbg_no_mma & 4)) sts_bytes<CH>(saddr[ri], w);
           } else if (rr >= 0) {
             uint8_t* out = static_cast<uint8_t*>(p.dst) + (size_t)rr * g.OC1() + ch0;
             if constexpr (CH == 8) *reinterpret_cast<uint2*>(out) = make_uint2(w[0], w[1]);
@@ -740,7 +741,7 @@ __device__ __forceinline__ void store_role(const Params& p, const DstMaps& tmD, 
       const uint32_t cb = c & 1;
       mbar_wait(smem_u32(&bar->stage_full[cb]), (c >> 1) & 1);
       tr.ev(40);
-      store_staged_chunk(tmD, sbase + p.off_stage + cb * kStageBytes, f0, V, j * g.nc1());
+      if (!(p.dbg_no_mma & 2)) store_staged_chunk(tmD, sbase + p.off_stage + cb * kStageBytes, f0, V, j * g.nc1());
       tr.ev(41);
       bulk_wait_read_all();
       tr.ev(42);
@@ -1330,7 +1331,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               constexpr int nks_full = G::swb1 >> 5;
               const int nks = (kb == G::nkb1 - 1) ? G::ks1_last : nks_full;
 #pragma unroll
-              for (int ks = 0; ks < nks; ++ks) umma_i8_pair(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, (kb | ks) != 0);
+              for (int ks = 0; ks < nks; ++ks)
+                if (!(p.dbg_no_mma & 1)) umma_i8_pair(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, (kb | ks) != 0);
             }
             umma_commit_pair(smem_u32(&bar->acc1_full[cb]));
             tr.ev(13);
@@ -1374,7 +1376,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               constexpr int nks_full = G::swb >> 5;
               const int nks = (kb == G::nkb - 1) ? G::ks_last : nks_full;
 #pragma unroll
-              for (int ks = 0; ks < nks; ++ks) umma_i8_pair(d0, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+              for (int ks = 0; ks < nks; ++ks)
+                if (!(p.dbg_no_mma & 1)) umma_i8_pair(d0, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
             }
           }
         }
@@ -1684,6 +1687,7 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   p.OC = d->oc;
   p.OC1 = conv0_only ? d->oc : d->oc1;  // destination channels
   p.conv0_only = conv0_only ? 1 : 0;
+  p.dbg_no_mma = getenv("DF_DEBUG_NO_MMA") ? atoi(getenv("DF_DEBUG_NO_MMA")) : 0;  // bit 0: no MMA, 1: no TMA stores, 2: no staging writes
   p.swb = pick_swb(d->ic);
   p.nkb = (d->ic + p.swb - 1) / p.swb;
   p.ks_last = (d->ic - (p.nkb - 1) * p.swb + 31) / 32;
