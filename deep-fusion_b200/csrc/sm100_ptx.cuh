@@ -62,14 +62,16 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
 #ifndef DF_MBAR_SPIN_LIMIT
 #define DF_MBAR_SPIN_LIMIT (1u << 26)
 #endif
+// out of line: the report-and-trap path would otherwise be expanded (printf marshalling, ~30 instructions)
+// into every wait site, in the middle of the hot code
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("mbar_wait timeout: block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > DF_MBAR_SPIN_LIMIT) {
-      printf("mbar_wait timeout: block %d thread %d bar 0x%x parity %u\n", blockIdx.x,
-             threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (++spins > DF_MBAR_SPIN_LIMIT) mbar_timeout(bar, parity);
   }
 }
 
@@ -88,11 +90,7 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
       if (kBackoffNs > 0) __nanosleep(kBackoffNs);
-      if (++spins > DF_MBAR_SPIN_LIMIT) {
-        printf("mbar_wait timeout: block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar,
-               parity);
-        __trap();
-      }
+      if (++spins > DF_MBAR_SPIN_LIMIT) mbar_timeout(bar, parity);
     }
   }
   __syncwarp();
