@@ -751,6 +751,31 @@ __device__ __forceinline__ void store_role(const Params& p, const DstMaps& tmD, 
   bulk_wait_all();  // the staging buffers must outlive the last TMA stores
 }
 
+// Per-channel f32 bias / scale (and offset-magic K) vectors -> shared memory, by the epilogue warps only and
+// AFTER the CTA-wide start barrier: the global loads' latency (~1 us) then overlaps the first halo / weight
+// loads and the first GEMM1 instead of delaying every role.
+template <class G>
+__device__ __forceinline__ void load_epilogue_constants(const Params& p, uint8_t* smem) {
+  const Geo<G> g{p};
+  float* sb0 = reinterpret_cast<float*>(smem + p.off_bias0);
+  float* ss0 = reinterpret_cast<float*>(smem + p.off_scale0);
+  float* sb1 = reinterpret_cast<float*>(smem + p.off_bias1);
+  float* ss1 = reinterpret_cast<float*>(smem + p.off_scale1);
+  int* sk1 = reinterpret_cast<int*>(smem + p.off_k1);
+  const int t = (int)threadIdx.x - kEpiWarp0 * 32, nt = kEpiWarps * 32;
+  for (int i = t; i < g.OC(); i += nt) {
+    sb0[i] = p.bias0[i];
+    ss0[i] = p.scale0[i];
+  }
+  const int oc1_pad = g.n_chunks() * g.nc1();
+  for (int i = t; i < oc1_pad; i += nt) {
+    sb1[i] = i < g.OC1() ? p.bias1[i] : 0.f;
+    ss1[i] = i < g.OC1() ? p.scale1[i] : 0.f;
+    sk1[i] = i < g.OC1() ? p.k1[i] : 0;
+  }
+  named_bar_sync(1, nt);  // epilogue warps only
+}
+
 // ------------------------------------------------------------------------------- the kernel
 template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -800,24 +825,6 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmW1);
   }
   if (warp == 3) tmem_alloc<512>(smem_u32(&bar->tmem_base));
-  {
-    // per-channel f32 bias / scale vectors -> smem (read by every epilogue thread)
-    float* sb0 = reinterpret_cast<float*>(smem + p.off_bias0);
-    float* ss0 = reinterpret_cast<float*>(smem + p.off_scale0);
-    float* sb1 = reinterpret_cast<float*>(smem + p.off_bias1);
-    float* ss1 = reinterpret_cast<float*>(smem + p.off_scale1);
-    for (int i = threadIdx.x; i < g.OC(); i += kThreads) {
-      sb0[i] = p.bias0[i];
-      ss0[i] = p.scale0[i];
-    }
-    const int oc1_pad = g.n_chunks() * g.nc1();
-    int* sk1 = reinterpret_cast<int*>(smem + p.off_k1);
-    for (int i = threadIdx.x; i < oc1_pad; i += kThreads) {
-      sb1[i] = i < g.OC1() ? p.bias1[i] : 0.f;
-      ss1[i] = i < g.OC1() ? p.scale1[i] : 0.f;
-      sk1[i] = i < g.OC1() ? p.k1[i] : 0;
-    }
-  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -1142,6 +1149,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp >= kEpiWarp0) {
     // ====================================== epilogue =======================================
+    load_epilogue_constants<G>(p, smem);
     epilogue_role<G, kDst, kDown0, kDown1, kNanSafe, false>(p, smem, bar, tmem, warp, lane, n_local, (int)blockIdx.x,
                                                             (int)gridDim.x);
   } else if (warp == 3) {
@@ -1225,22 +1233,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmW1);
   }
   if (warp == 3) tmem_alloc_pair<512>(smem_u32(&bar->tmem_base));
-  {
-    float* sb0 = reinterpret_cast<float*>(smem + p.off_bias0);
-    float* ss0 = reinterpret_cast<float*>(smem + p.off_scale0);
-    float* sb1 = reinterpret_cast<float*>(smem + p.off_bias1);
-    float* ss1 = reinterpret_cast<float*>(smem + p.off_scale1);
-    int* sk1 = reinterpret_cast<int*>(smem + p.off_k1);
-    for (int i = threadIdx.x; i < G::OC; i += kThreads) {
-      sb0[i] = p.bias0[i];
-      ss0[i] = p.scale0[i];
-    }
-    for (int i = threadIdx.x; i < G::OC1; i += kThreads) {
-      sb1[i] = p.bias1[i];
-      ss1[i] = p.scale1[i];
-      sk1[i] = p.k1[i];
-    }
-  }
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();  // both CTAs' barriers exist before anyone arrives remotely
@@ -1389,6 +1381,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= kEpiWarp0) {
     // ================================== epilogue (both CTAs) ===================================
+    load_epilogue_constants<G>(p, smem);
     epilogue_role<G, kDst, false, false, false, true>(p, smem, bar, tmem, warp, lane, n_local, 2 * cid + (int)rank, 2 * ncl);
   } else if (warp == 3) {
     // ================================ store thread (staged output) ==========================
