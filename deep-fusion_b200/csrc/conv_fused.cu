@@ -15,15 +15,21 @@
 //    profiles/r01_probe.log).
 //  * halo rows come in by TMA (4-D NHWC tensor map, box = {K-block, Wp, 1, 1}); out-of-image
 //    rows / columns / images are zero-filled by the TMA unit -- that IS the padding.
-//  * conv0 accumulates in TMEM; 8 epilogue warps apply (float(acc)+bias)*scale -> ReLU -> round
+//  * conv0 accumulates in TMEM; the 16 epilogue warps apply (float(acc)+bias)*scale -> ReLU -> round
 //    -> u8 and write the tile straight into shared memory in the swizzled K-major layout the
 //    second GEMM wants, so the intermediate never leaves the SM.
 //  * conv1x1 runs as N-chunks of <=128 output channels through two TMEM accumulators, so the
 //    epilogue of chunk j overlaps the MMA of chunk j+1 and the conv0 MMAs of the next tile.
-//  * warp roles: w0 TMA(A) | w1 MMA issue | w2 TMA(weights) | w3 TMEM alloc | w4-11 epilogue.
-//    All hand-offs are mbarriers; tcgen05.commit releases stages.
-//  * weights live in shared memory for the whole (persistent) kernel when they fit; otherwise
-//    they stream through a ring of stages in exactly the order the MMA thread consumes them.
+//  * the epilogue reads row-pair TMEM fragments of channel-permuted accumulators (one set of
+//    per-channel constants serves four rows), stages 1-byte output in shared memory and sends it
+//    out with two TMA stores per chunk (see DstMaps / store_staged_chunk).
+//  * warp roles: w0 TMA(A) | w1 GEMM1 issue | w2 TMA(weights), then GEMM2 issue | w3 TMEM alloc,
+//    then TMA stores | w4-19 epilogue.  All hand-offs are mbarriers; tcgen05.commit releases stages.
+//  * weights live in shared memory for the whole (persistent) kernel when they fit -- for the
+//    cfg3 shape split across a CTA pair (conv_pair_kernel, cta_group::2); otherwise they stream
+//    through a ring of stages in exactly the order the MMA thread consumes them.
+//  * launches use programmatic dependent launch: the next launch's prologue runs under this
+//    launch's tail (griddep_launch_dependents / griddep_wait).
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
