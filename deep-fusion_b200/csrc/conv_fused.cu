@@ -220,7 +220,11 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   p.OC = d->oc;
   p.OC1 = conv0_only ? d->oc : d->oc1;  // destination channels
   p.conv0_only = conv0_only ? 1 : 0;
+#if DF_DIAG
   p.dbg_no_mma = getenv("DF_DEBUG_NO_MMA") ? atoi(getenv("DF_DEBUG_NO_MMA")) : 0;  // bit 0: no MMA, 1: no TMA stores, 2: no staging writes
+#else
+  p.dbg_no_mma = 0;
+#endif
   p.swb = pick_swb(d->ic);
   p.nkb = (d->ic + p.swb - 1) / p.swb;
   p.ks_last = (d->ic - (p.nkb - 1) * p.swb + 31) / 32;
@@ -240,91 +244,6 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   p.relu1 = conv0_only ? d->relu0 : d->relu1;
   p.round0 = d->round0;
   p.round1 = conv0_only ? d->round0 : d->round1;
-
-  // ---- shared memory plan
-  const int oc1_pad = p.n_chunks * p.nc1;
-  uint32_t off = 1024;  // barriers
-  p.off_bias0 = off;
-  off += align_up(p.OC * 4, 128);
-  p.off_scale0 = off;
-  off += align_up(p.OC * 4, 128);
-  p.off_bias1 = off;
-  off += align_up(oc1_pad * 4, 128);
-  p.off_scale1 = off;
-  off += align_up(oc1_pad * 4, 128);
-  p.off_k1 = off;
-  off += align_up(oc1_pad * 4, 128);
-  off = align_up(off, 1024);
-  p.mid_kb_stride = kTileM * p.swb1;
-  p.mid_bytes = align_up(p.nkb1 * p.mid_kb_stride, 1024);
-  p.off_mid = off;
-  off += p.mid_bytes;
-  p.NM = 1;  // one intermediate buffer is enough with the epilogue's unit order (see epilogue_role)
-  p.a_kb_stride = (uint32_t)p.NR * p.Wp * p.swb;
-  p.a_stage_bytes = align_up(p.nkb * p.a_kb_stride, 1024);
-  p.w0_block_bytes = (uint32_t)p.OC * p.swb;
-  p.w1_block_bytes = (uint32_t)p.nc1 * p.swb1;
-  const uint32_t w0_bytes = align_up(9 * p.nkb * p.w0_block_bytes, 1024);
-  const uint32_t w1_bytes = conv0_only ? 0 : align_up(p.n_chunks * p.nkb1 * p.w1_block_bytes, 1024);
-  const uint32_t avail = kSmemLimit - 1024;  // base alignment slack
-  const uint32_t fixed = off;
-  if (fixed + 2 * p.a_stage_bytes + w0_bytes + w1_bytes <= avail) {
-    p.w0_res = p.w1_res = 1;
-    p.off_w0 = fixed;
-    p.off_w1 = fixed + w0_bytes;
-    p.off_a = fixed + w0_bytes + w1_bytes;
-    int sa = (int)((avail - p.off_a) / p.a_stage_bytes);
-    p.SA = sa > kMaxAStages ? kMaxAStages : sa;
-    p.SB = 1;
-    p.b_stage_bytes = 0;
-    p.off_b = p.off_a + p.SA * p.a_stage_bytes;
-  } else {
-    const uint32_t stage_w0 = align_up(p.w0_block_bytes, 1024);
-    const uint32_t stage_both = align_up(p.w0_block_bytes > p.w1_block_bytes ? p.w0_block_bytes : p.w1_block_bytes, 1024);
-    p.SA = 2;
-    if (fixed + 2 * p.a_stage_bytes + w1_bytes + 3 * stage_w0 <= avail) {
-      p.w0_res = 0;
-      p.w1_res = 1;
-      p.off_w1 = fixed;
-      p.off_a = fixed + w1_bytes;
-      p.b_stage_bytes = stage_w0;
-    } else {
-      p.w0_res = p.w1_res = 0;
-      p.off_a = fixed;
-      p.b_stage_bytes = stage_both;
-    }
-    p.off_b = p.off_a + p.SA * p.a_stage_bytes;
-    if (p.off_b + 2 * p.b_stage_bytes > avail) {
-      delete op;
-      return df::fail(DF_E_UNSUPPORTED, "conv: shape does not fit the shared-memory plan");
-    }
-    int sb = (int)((avail - p.off_b) / p.b_stage_bytes);
-    p.SB = sb > kMaxBStages ? kMaxBStages : sb;
-  }
-  // compile-time geometry when the shape and the plan are one of the BASELINE configurations
-  op->geom_id = 0;
-  if (geom_matches<GeoCfg1>(p)) { op->geom_id = 1; p.SB = GeoCfg1::SB; }
-  else if (geom_matches<GeoCfg3>(p)) { op->geom_id = 3; p.SB = GeoCfg3::SB; }
-  else if (geom_matches<GeoCfg4>(p)) { op->geom_id = 4; p.SB = GeoCfg4::SB; }
-  const int shape_id = op->geom_id;  // which BASELINE shape this is (0: none), whatever kernel ends up running it
-  // Staged output (store_staged_chunk): two 16 KB buffers behind the weight stages.  The run-time
-  // geometry gives weight stages beyond four up for it; the static plans keep their stage counts.
-  const bool can_stage = (d->dst_dt == DF_U8 || d->dst_dt == DF_S8) && p.nc1 == 128 &&
-                         !(getenv("DF_NO_STAGED_STORE") && atoi(getenv("DF_NO_STAGED_STORE")) != 0);
-  p.stage_out = 0;
-  p.off_stage = 0;
-  {
-    const uint32_t need = kStageBufs * kStageBytes;
-    if (can_stage && !shape_id)
-      while (p.SB > 4 && p.off_b + p.SB * p.b_stage_bytes + need > avail) --p.SB;
-    uint32_t end = p.off_b + p.SB * p.b_stage_bytes;
-    if (can_stage && end + need <= avail) {
-      p.stage_out = 1;
-      p.off_stage = end;
-      end += need;
-    }
-    op->smem_bytes = end + 1024;
-  }
 
   // ---- parameters: weights re-laid out K-major per (tap, K-block); bias -> f32; scales expanded
   // Row r of a weight block (= MMA N index = accumulator column r) holds output channel
@@ -411,6 +330,111 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   if (!fast1) p.k1_uniform = 0;
   p.fast1 = fast1;
 
+  // ---- shared memory plan.  plan(nm, stage): nm intermediate tiles; stage = staged 1-byte output wanted
+  const int oc1_pad = p.n_chunks * p.nc1;
+  const uint32_t avail = kSmemLimit - 1024;  // base alignment slack
+  auto plan = [&](int nm, bool stage) -> bool {
+    uint32_t off = 1024;  // barriers
+    p.off_bias0 = off;
+    off += align_up(p.OC * 4, 128);
+    p.off_scale0 = off;
+    off += align_up(p.OC * 4, 128);
+    p.off_bias1 = off;
+    off += align_up(oc1_pad * 4, 128);
+    p.off_scale1 = off;
+    off += align_up(oc1_pad * 4, 128);
+    p.off_k1 = off;
+    off += align_up(oc1_pad * 4, 128);
+    off = align_up(off, 1024);
+    p.mid_kb_stride = kTileM * p.swb1;
+    p.mid_bytes = align_up(p.nkb1 * p.mid_kb_stride, 1024);
+    p.off_mid = off;
+    p.NM = nm;
+    off += nm * p.mid_bytes;
+    p.a_kb_stride = (uint32_t)p.NR * p.Wp * p.swb;
+    p.a_stage_bytes = align_up(p.nkb * p.a_kb_stride, 1024);
+    p.w0_block_bytes = (uint32_t)p.OC * p.swb;
+    p.w1_block_bytes = (uint32_t)p.nc1 * p.swb1;
+    const uint32_t w0_bytes = align_up(9 * p.nkb * p.w0_block_bytes, 1024);
+    const uint32_t w1_bytes = conv0_only ? 0 : align_up(p.n_chunks * p.nkb1 * p.w1_block_bytes, 1024);
+    const uint32_t fixed = off;
+    if (fixed + 2 * p.a_stage_bytes + w0_bytes + w1_bytes <= avail) {
+      p.w0_res = p.w1_res = 1;
+      p.off_w0 = fixed;
+      p.off_w1 = fixed + w0_bytes;
+      p.off_a = fixed + w0_bytes + w1_bytes;
+      int sa = (int)((avail - p.off_a) / p.a_stage_bytes);
+      p.SA = sa > kMaxAStages ? kMaxAStages : sa;
+      p.SB = 1;
+      p.b_stage_bytes = 0;
+      p.off_b = p.off_a + p.SA * p.a_stage_bytes;
+    } else {
+      const uint32_t stage_w0 = align_up(p.w0_block_bytes, 1024);
+      const uint32_t stage_both = align_up(p.w0_block_bytes > p.w1_block_bytes ? p.w0_block_bytes : p.w1_block_bytes, 1024);
+      p.SA = 2;
+      if (fixed + 2 * p.a_stage_bytes + w1_bytes + 3 * stage_w0 <= avail) {
+        p.w0_res = 0;
+        p.w1_res = 1;
+        p.off_w1 = fixed;
+        p.off_a = fixed + w1_bytes;
+        p.b_stage_bytes = stage_w0;
+      } else {
+        p.w0_res = p.w1_res = 0;
+        p.off_a = fixed;
+        p.b_stage_bytes = stage_both;
+      }
+      p.off_b = p.off_a + p.SA * p.a_stage_bytes;
+      if (p.off_b + 2 * p.b_stage_bytes > avail) return false;
+      int sb = (int)((avail - p.off_b) / p.b_stage_bytes);
+      p.SB = sb > kMaxBStages ? kMaxBStages : sb;
+    }
+    // Staged output (store_staged_chunk, run-time geometry only): two 16 KB buffers behind the weight
+    // stages; weight stages beyond four are given up for it.
+    p.stage_out = 0;
+    p.off_stage = 0;
+    const uint32_t need = kStageBufs * kStageBytes;
+    if (stage)
+      while (p.SB > 4 && p.off_b + p.SB * p.b_stage_bytes + need > avail) --p.SB;
+    uint32_t end = p.off_b + p.SB * p.b_stage_bytes;
+    if (stage && end + need <= avail) {
+      p.stage_out = 1;
+      p.off_stage = end;
+      end += need;
+    }
+    op->smem_bytes = end + 1024;
+    return true;
+  };
+  // The static kernels (BASELINE shapes) are built for round-to-nearest, finite constants and the
+  // offset-magic conv1 conversion with ONE constant K; they store 1-byte output straight from registers
+  // and -- when it fits -- keep TWO intermediate tiles, so that the conv0 epilogue of tile t+1 does not have
+  // to wait for GEMM2 of tile t (profiles/r02_knockout.log: with one tile the two strictly alternate and
+  // their hand-offs alone cost ~3000 cycles per tile).  Anything else runs the run-time-geometry kernel.
+  const bool static_ok = !conv0_only && p.fast1 && p.k1_uniform != 0 && d->round0 == DF_ROUND_NEAREST && d->round1 == DF_ROUND_NEAREST &&
+                         !p.nan_safe && !getenv("DF_FORCE_DYNAMIC_GEOMETRY");  // (env: test hook for the generic path)
+  auto match_static = [&]() {
+    if (geom_matches<GeoCfg1>(p)) { p.SB = GeoCfg1::SB; return 1; }
+    if (geom_matches<GeoCfg3>(p)) { p.SB = GeoCfg3::SB; return 3; }
+    if (geom_matches<GeoCfg4>(p)) { p.SB = GeoCfg4::SB; return 4; }
+    return 0;
+  };
+  op->geom_id = 0;
+  if (static_ok) {
+    for (int nm = 2; nm >= 1 && !op->geom_id; --nm)
+      if (plan(nm, false)) {
+        op->geom_id = match_static();
+        if (op->geom_id) op->smem_bytes = p.off_b + p.SB * p.b_stage_bytes + 1024;
+      }
+  }
+  const int shape_id = op->geom_id;  // which BASELINE shape this is (0: none)
+  if (!op->geom_id) {
+    const bool can_stage = (d->dst_dt == DF_U8 || d->dst_dt == DF_S8) && p.nc1 == 128 &&
+                           !(getenv("DF_NO_STAGED_STORE") && atoi(getenv("DF_NO_STAGED_STORE")) != 0);
+    if (!plan(1, can_stage)) {
+      delete op;
+      return df::fail(DF_E_UNSUPPORTED, "conv: shape does not fit the shared-memory plan");
+    }
+  }
+
 #define DF_TRY(expr)                          \
   do {                                        \
     int rc_ = (expr);                         \
@@ -441,6 +465,7 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   DF_TRY_CUDA(cudaMemcpy(op->d_bias0, b0.data(), p.OC * 4, cudaMemcpyHostToDevice));
   DF_TRY_CUDA(cudaMemcpy(op->d_scale0, s0.data(), p.OC * 4, cudaMemcpyHostToDevice));
   DF_TRY_CUDA(cudaMalloc(&op->d_k1, p.OC1 * 4));
+
   DF_TRY_CUDA(cudaMemcpy(op->d_k1, k1.data(), p.OC1 * 4, cudaMemcpyHostToDevice));
   DF_TRY_CUDA(cudaMemcpy(op->d_bias1, fast1 ? c1.data() : b1.data(), p.OC1 * 4, cudaMemcpyHostToDevice));
   DF_TRY_CUDA(cudaMemcpy(op->d_scale1, s1.data(), p.OC1 * 4, cudaMemcpyHostToDevice));
@@ -452,14 +477,11 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   DF_TRY(encode_2d(&op->tmW0, op->d_w0, p.swb, (long)9 * p.nkb * p.OC, p.OC));
   DF_TRY(encode_2d(&op->tmW1, op->d_w1, p.swb1, (long)p.n_chunks * p.nkb1 * p.nc1, p.nc1));
 
-  // The static kernels are built for round-to-nearest, finite constants, the offset-magic conv1
-  // conversion with ONE constant K, and (1-byte destinations) staged output; anything else runs the
-  // run-time-geometry kernel.
-  const bool one_byte = d->dst_dt == DF_U8 || d->dst_dt == DF_S8;
-  const bool static_ok = !conv0_only && p.fast1 && p.k1_uniform != 0 && d->round0 == DF_ROUND_NEAREST && d->round1 == DF_ROUND_NEAREST &&
-                         !p.nan_safe && !getenv("DF_FORCE_DYNAMIC_GEOMETRY");  // (env: test hook for the generic path)
-  if (!static_ok || (one_byte && !p.stage_out)) op->geom_id = 0;
   op->kernel = pick_kernel(op->geom_id, d->dst_dt, p.round0 == DF_ROUND_DOWN, p.round1 == DF_ROUND_DOWN, p.nan_safe != 0);
+  if (!op->kernel.launch) {
+    df_conv_destroy(op);
+    return df::fail(DF_E_UNSUPPORTED, "conv: no kernel for this configuration in this build");
+  }
   DF_TRY_CUDA(op->kernel.attr(op->smem_bytes));
 
   // ---- CTA-pair variant: BASELINE cfg3 with everything resident once the weights are split in two.
@@ -469,14 +491,14 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
     Params q = p;
     q.w0_res = q.w1_res = 1;
     q.SB = 1;
-    q.stage_out = one_byte ? 1 : 0;
-    uint32_t off2 = p.off_mid + q.mid_bytes;
+    q.stage_out = 0;
+    q.off_stage = 0;
+    q.NM = 2;
+    uint32_t off2 = p.off_mid + q.NM * q.mid_bytes;
     q.off_w0 = off2;
     off2 += align_up(9 * q.nkb * (q.w0_block_bytes / 2), 1024);
     q.off_w1 = off2;
     off2 += align_up(q.n_chunks * q.nkb1 * (q.w1_block_bytes / 2), 1024);
-    q.off_stage = off2;
-    if (q.stage_out) off2 += kStageBufs * kStageBytes;
     q.off_a = off2;
     q.a_kb_stride = (uint32_t)(q.NR + 1) * q.Wp * q.swb;  // one extra row of slack before the tile origin
     q.a_stage_bytes = align_up(q.nkb * q.a_kb_stride, 1024);
@@ -532,7 +554,9 @@ static int src_map(df_conv* op, const Params& p, const void* ptr, int n, const C
 
 // Destination maps of the staged output path: the 1-byte NHWC destination as 2-D [n*H*W pixels][OC1],
 // boxes {128 channels, 128 >> i pixels}, SWIZZLE_128B (store_staged_chunk).
+// (The static-geometry kernels store per warp, 16 rows at most: they use m[3 ..].)
 static int dst_maps(df_conv* op, const Params& p, const void* ptr, int n, const DstMaps** out) {
+  const bool per_warp = false;
   for (int i = 0; i < df_conv::kMapSlots; ++i)
     if (op->d_maps[i].ptr == ptr && op->d_maps[i].n == n) {
       *out = &op->d_maps[i].maps;
@@ -544,14 +568,14 @@ static int dst_maps(df_conv* op, const Params& p, const void* ptr, int n, const 
   op->d_next = (op->d_next + 1) % df_conv::kMapSlots;
   s.ptr = nullptr;
   const cuuint64_t pixels = (cuuint64_t)n * p.H * p.W;
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < (per_warp ? 6 : 8); ++i) {
     cuuint64_t gd[2] = {(cuuint64_t)p.OC1, pixels};
     cuuint64_t gs[1] = {(cuuint64_t)p.OC1};
-    cuuint32_t box[2] = {128, (cuuint32_t)(128 >> i)};
+    cuuint32_t box[2] = {per_warp ? 64u : 128u, (cuuint32_t)((per_warp ? 32 : 128) >> i)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&s.maps.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gd, gs, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, per_warp ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return df::fail(DF_E_INTERNAL, "cuTensorMapEncodeTiled(dst) failed: %d", (int)r);
   }
   s.ptr = ptr;

@@ -97,6 +97,20 @@ struct Params {
   int trace_cap;
 };
 
+// Diagnostic switches that produce garbage results (skip the MMAs / the TMA stores / the staging writes to
+// time what is left) exist only in builds with -DDF_DIAG=1; in production builds they fold to nothing.
+#ifndef DF_DIAG
+#define DF_DIAG 0
+#endif
+__device__ __forceinline__ bool dbg_flag(const Params& p, int bit) {
+#if DF_DIAG
+  return (p.dbg_no_mma & bit) != 0;
+#else
+  (void)p; (void)bit;
+  return false;
+#endif
+}
+
 // Diagnostic timeline: role r of CTA b appends (tag << 48 | clock) words to its own lane of the
 // buffer.  One predictable branch per event when disabled.
 struct Tracer {
@@ -138,6 +152,34 @@ __device__ __forceinline__ void trace_wallclock(const Params& p, int slot) {
   }
 }
 
+// GEMM1 issue throttle.  The tensor pipe executes MMAs in the order they were issued, whichever thread issued
+// them.  GEMM1 of the next tile (36 MMAs, 2304 cycles for cfg3) can be issued long before the conv1 chunks of the
+// current tile are (they wait for the conv0 epilogue), and a chunk issued behind it is not computed until all of
+// it has run -- the epilogue then sits idle for a whole GEMM1 and the two phases serialise (profiles/
+// r02_trace_cfg3_seed.log: acc1 chunks ready 1500 cycles after their issue).  So the GEMM1 thread keeps at most
+// kG1Ahead tap groups (one tap = K-blocks x K-steps MMAs, 256 cycles for cfg3) in the queue beyond the completed
+// ones: after each tap it commits to g1_prog[tap % kG1Ahead] and before issuing tap i it waits for tap
+// i - kG1Ahead.  A chunk that becomes ready is then at most kG1Ahead taps away from the tensor pipe.
+#ifndef DF_G1_AHEAD
+#define DF_G1_AHEAD 2
+#endif
+constexpr int kG1Ahead = DF_G1_AHEAD;
+
+// Build knobs for A/B measurements (defaults = the production configuration):
+//   DF_SEED        1: the static kernels keep the conv1 accumulators pre-seeded with the offset-magic constant
+//   DF_STATIC_EPI  1: the static kernels run epilogue_static (two groups, per-warp TMA stores); 0: epilogue_role
+#ifndef DF_SEED
+#define DF_SEED 1
+#endif
+#ifndef DF_STATIC_EPI
+#define DF_STATIC_EPI 1
+#endif
+
+template <class G>
+constexpr bool seeded_acc1() { return G::is_static && DF_SEED != 0; }
+template <class G>
+constexpr bool static_epilogue() { return G::is_static && DF_STATIC_EPI != 0; }
+
 struct Barriers {
   uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
   uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
@@ -146,6 +188,7 @@ struct Barriers {
   uint64_t mid_full[2], mid_empty[2];
   uint64_t acc1_full[2], acc1_empty[2];
   uint64_t stage_full[2], stage_empty[2];  // staged output: epilogue group <-> store thread (warp 3)
+  uint64_t g1_prog[kG1Ahead];              // GEMM1 issue throttle (see G1Throttle)
   uint32_t tmem_base;
 };
 
@@ -317,6 +360,11 @@ __device__ __forceinline__ void scale4_fast(const uint32_t* acc, const int4 k, c
   asm("mov.b64 {%0, %1}, %2;" : "=f"(t[2]), "=f"(t[3]) : "l"(b));
 }
 __device__ __forceinline__ float4 load_scale4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {  // 16-byte shared-memory load from a 32-bit shared address
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 // vmaxps(zero, t): second source when NaN or both zero
 __device__ __forceinline__ float relu_x86(float t) { return (0.0f > t) ? 0.0f : t; }
 
@@ -410,6 +458,20 @@ __device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, uint32_t* r) {
   else tmem_ld_16x256b_x2(taddr, r);
 }
 
+// registers -> TMEM, 32 lanes x 8 columns (thread = lane); used to pre-seed the conv1 accumulators
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// registers -> TMEM, 16 lanes x 16 columns (row-pair fragment layout, see tmem_ld_16x256b_x2)
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void sts128(uint32_t addr, const uint32_t* w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
 }
@@ -418,6 +480,25 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t w) {
 }
 __device__ __forceinline__ void sts64(uint32_t addr, const uint32_t* w) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(w[0]), "r"(w[1]) : "memory");
+}
+// 8-byte store executed only when flag >= 0
+__device__ __forceinline__ void sts64_if(uint32_t addr, const uint32_t* w, int flag) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %3, 0;\n\t@p st.shared.v2.b32 [%0], {%1, %2};\n\t}\n" ::"r"(addr), "r"(w[0]), "r"(w[1]),
+               "r"(flag)
+               : "memory");
+}
+// global stores executed only when `on`: predicated in the asm so that the compiler cannot sink the arithmetic
+// that feeds them into a divergent branch
+__device__ __forceinline__ void stg64_if(void* ptr, const uint32_t* w, bool on) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p st.global.v2.b32 [%0], {%1, %2};\n\t}\n" ::"l"(ptr), "r"(w[0]), "r"(w[1]),
+               "r"((int)on)
+               : "memory");
+}
+__device__ __forceinline__ void stg256_if(void* ptr, const uint32_t* w, bool on) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %9, 0;\n\t@p st.global.v4.b32 [%0], {%1, %2, %3, %4};\n\t@p st.global.v4.b32 [%0+16], {%5, %6, %7, %8};\n\t}\n" ::"l"(ptr),
+      "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"((int)on)
+      : "memory");
 }
 // CH packed bytes (CH / 4 words) -> shared memory
 template <int CH>
@@ -502,7 +583,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
   const int q_first = 2 * p.Wp;
   // staged output (1-byte destinations, see store_staged_chunk): always for the static geometries
   constexpr bool kCanStage = (kDst == DF_U8 || kDst == DF_S8);
-  const bool staged = kCanStage && (G::is_static || p.stage_out != 0);
+  const bool staged = kCanStage && !G::is_static && p.stage_out != 0;  // static geometries store straight from registers
   // where this thread's four rows (ri = 2 * h16 + hl -> tile row quarter * 32 + 8 * ri + r8) of the
   // current tile go: staging row (staged) or NHW pixel index (direct); -1 for padding positions
   int row_it = -1, pos_it = 0, rinfo[4];  // rinfo is valid for tile row_it; the PosStates are at tile pos_it
@@ -527,14 +608,44 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
   EpiTracer tr(p, 3, threadIdx.x == kEpiWarp0 * 32);
   if (!staged) griddep_wait();  // direct stores: earlier kernels may still be using the destination
 
+  // Pre-seeded conv1 accumulators (static geometries: one offset-magic constant K for all channels).  The
+  // epilogue warps keep the conv1 accumulators initialised to K and GEMM2 ACCUMULATES on top of it, so the
+  // accumulator the epilogue reads already is the bit pattern of 2^23 + (acc - lo) -- the per-element
+  // integer add of scale4_fast disappears (a third of the conv1 arithmetic instructions).  Every warp
+  // (re)seeds the columns it reads, right after its tcgen05.ld has landed and before it hands the
+  // accumulator back: tcgen05.st -> tcgen05.wait::st -> fence -> arrive on acc1_empty.  TMEM writes run at
+  // four times the read rate (B300_MICROARCH.md), the eight registers holding K stay live for the whole role.
+  constexpr bool kSeed = seeded_acc1<G>();
+  [[maybe_unused]] uint32_t kseed[8];
+  auto seed_block = [&](uint32_t taddr32) {  // 32 lanes (this warp's quarter) x 32 columns at taddr32
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tmem_st_32x32b_x8(taddr32 + 8 * i, kseed);
+  };
+  if constexpr (kSeed) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)  // volatile loads: ptxas must keep eight live registers instead of re-creating them per store
+      asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(kseed[i]) : "r"(smem_u32(sk1) + 4 * i));
+    for (int cb = 0; cb < 2; ++cb)
+      for (int b = cbi; b < kAcc1Stride / 32; b += kBlockStride) seed_block(lane_addr + kAcc1Col + cb * kAcc1Stride + b * 32);
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) {
+      arrive(a_acc1_empty);
+      arrive(a_acc1_empty + 8);
+    }
+  }
+  const int k_add = kSeed ? 0 : k_uni;  // what the epilogue still has to add to the accumulator
+
   // ---- conv0 epilogue of local tile `it`
   auto unit_e0 = [&](int it) {
     const int ab = it % g.n_acc0();
-    mbar_wait_warp(smem_u32(&bar->mid_empty[0]), (it & 1) ^ 1);
+    const int mb = it % p.NM;  // intermediate tile buffer
+    mbar_wait_warp(smem_u32(&bar->mid_empty[mb]), ((it / p.NM) & 1) ^ 1);
     mbar_wait_warp(smem_u32(&bar->acc0_full[ab]), (it / g.n_acc0()) & 1);
     tc_fence_after_sync();
     tr.ev(30);
-    const uint32_t mid = sbase + p.off_mid;
+    const uint32_t mid = sbase + p.off_mid + mb * p.mid_bytes;
     const uint32_t t_base = lane_addr + ab * g.OC();
     const int nb32 = g.OC() / 32, nblk = nb32 + (g.OC() - nb32 * 32) / 16;
     auto block = [&](auto ch_c, int col0, bool last) {
@@ -558,6 +669,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
         tc_fence_before_sync();
         if (lane == 0) arrive(a_acc0_empty + 8 * ab);
       }
+      if (!dbg_flag(p, 128))
 #pragma unroll
       for (int ri = 0; ri < 4; ++ri) {
         uint32_t v[CH], packed[CH / 4];
@@ -583,7 +695,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
     }
     fence_proxy_async_smem();  // intermediate tile -> visible to the tensor pipe (async proxy)
     __syncwarp();
-    if (lane == 0) arrive(a_mid_full);
+    if (lane == 0) arrive(a_mid_full + 8 * mb);
     tr.ev(31);
   };
 
@@ -609,7 +721,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
     tr.ev(36);
     // conv0-only operator: the chunk is 128 columns of the 3x3 accumulator of this tile
     const int ab0 = it % g.n_acc0();
-    if (!c0_only) mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c >> 1) & 1);
+    if (!c0_only) { if (!dbg_flag(p, 32)) mbar_wait_warp(smem_u32(&bar->acc1_full[cb]), (c >> 1) & 1); }
     else if (j == 0) mbar_wait_warp(smem_u32(&bar->acc0_full[ab0]), (it / g.n_acc0()) & 1);
     tc_fence_after_sync();
     tr.ev(32);
@@ -628,8 +740,13 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
       const int ccol = col0 + CH * m4;      // first of this thread's CH channels inside the chunk
       const int ch0 = j * g.nc1() + ccol;   // ... and as conv1 output channel
       uint32_t acc[2][2 * CH];
-      tmem_ld_frag<CH>(t_base + col0, acc[0]);
-      tmem_ld_frag<CH>(t_base + (16u << 16) + col0, acc[1]);
+      if (!dbg_flag(p, 8)) {
+        tmem_ld_frag<CH>(t_base + col0, acc[0]);
+        tmem_ld_frag<CH>(t_base + (16u << 16) + col0, acc[1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 2 * CH; ++i) acc[0][i] = acc[1][i] = (uint32_t)(lane + i);
+      }
       float4 c4[CH / 4], s4[CH / 4];
       int4 k4[kUniK ? 1 : CH / 4];
 #pragma unroll
@@ -654,25 +771,31 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
         mbar_wait_warp(smem_u32(&bar->stage_empty[cb]), ((c >> 1) & 1) ^ 1);
         stage_checked = true;
       }
+      tr.ev(37);
       tmem_ld_wait();
+      tr.ev(38);
+      if constexpr (kSeed) seed_block(t_base + col0);  // the columns just read are K again for the chunk after next
       if (last && releases) {  // accumulator is in registers (tcgen05.wait::ld is warp-wide): the tensor pipe may overwrite it
+        if constexpr (kSeed) tmem_st_wait();
         tc_fence_before_sync();
         if (lane == 0) arrive(a_release);
       }
+      tr.ev(39);
       // Padding rows are computed like any other and only their store is predicated off: a branch around
       // the row costs three control instructions and a branch-resolve stall per row, the wasted arithmetic
       // (6..8 % of the rows for the BASELINE shapes) is cheaper.
+      if (!dbg_flag(p, 16))
 #pragma unroll
       for (int ri = 0; ri < 4; ++ri) {
         const int rr = rinfo[ri];
         uint32_t v[CH], w[ts == 1 ? CH / 4 : CH];
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = acc[ri >> 1][4 * (i / 2) + 2 * (ri & 1) + (i & 1)];
-        finish_conv1<kDst, kDown1, kNanSafe, CH, kUniK>(v, c4, s4, k4, k_uni, fast1, relu1, w);
+        finish_conv1<kDst, kDown1, kNanSafe, CH, kUniK>(v, c4, s4, k4, k_add, fast1, relu1, w);
         if constexpr (ts == 1) {
           if (staged) {  // 16-byte unit XOR row-inside-the-1024-B-atom, as SWIZZLE_128B wants
-            if (rr >= 0 && !(p.dbg_no_mma & 4)) sts_bytes<CH>(saddr[ri], w);
-          } else if (rr >= 0) {
+            if (rr >= 0 && !dbg_flag(p, 4)) sts_bytes<CH>(saddr[ri], w);
+          } else if (rr >= 0 && !dbg_flag(p, 4)) {
             uint8_t* out = static_cast<uint8_t*>(p.dst) + (size_t)rr * g.OC1() + ch0;
             if constexpr (CH == 8) *reinterpret_cast<uint2*>(out) = make_uint2(w[0], w[1]);
             else *reinterpret_cast<uint32_t*>(out) = w[0];
@@ -702,6 +825,9 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
       if (lane == 0) arrive(a_release);
     }
     tr.ev(35);
+    // warps without a block in this chunk (ragged last chunk) must not report the staging buffer full
+    // before chunk c - 2 has left it either: their arrival completes the phase the store thread waits for
+    if (!stage_checked) mbar_wait_warp(smem_u32(&bar->stage_empty[cb]), ((c >> 1) & 1) ^ 1);
     if (staged) {
       fence_proxy_async_smem();  // this thread's staging writes -> visible to the TMA unit
       __syncwarp();
@@ -730,6 +856,221 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
   }
 }
 
+template <int N, class F, int I = 0>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<N, F, I + 1>(static_cast<F&&>(f));
+  }
+}
+
+// ------------------------------------------------------------------ epilogue role, static geometries
+// The BASELINE shapes (StaticGeom: OC a multiple of 32, conv1 chunks of 128 channels, finite constants,
+// round-to-nearest, one offset-magic constant K) run this epilogue instead of epilogue_role.  Same unit
+// stream, same hand-offs, but written for the one thing that bounds it: instruction issue.  The 16 epilogue
+// warps share four schedulers with the single-thread roles, and profiles/r02_skeleton_ncu.txt shows that of
+// the ~17.6 k warp instructions epilogue_role executes per 128-position tile only ~5 k are arithmetic: the rest
+// is per-unit bookkeeping (addresses re-derived from kernel parameters, staging hand-offs, polling loops), and
+// with every unit knocked down to its skeleton the kernel is only half as fast again as the real one.  Here
+//   * output goes straight from registers to global memory: a thread owns 8 consecutive channels of a row,
+//     a quad 32 contiguous bytes (128 for 4-byte types) -- no staging buffers, store thread, proxy fences
+//     or staging barriers (measured faster than both TMA-store variants, profiles/r02_variants.log);
+//   * everything a conv1 unit needs besides its accumulator is computed once per tile (row -> pixel index
+//     from one ballot over the warp's 32 rows: valid positions are a contiguous pixel range) or once per
+//     kernel (shared-memory addresses), and the chunk index only moves constant offsets;
+//   * optionally (DF_SEED) the conv1 accumulators are kept pre-seeded with K so that GEMM2 accumulates on
+//     top of it and the per-element integer add of the offset-magic conversion disappears.
+template <class G, int kDst, bool kPair, class Bar>
+__device__ __forceinline__ void epilogue_static(const Params& p, const DstMaps&, uint8_t* smem, Bar* bar, uint32_t tmem,
+                                                int warp, int lane, int n_local, int tile0, int tile_stride) {
+  static_assert(G::is_static && G::nc1 == 128 && G::OC % 32 == 0, "epilogue_static: unsupported geometry");
+  const uint32_t sbase = smem_u32(smem);
+  const int e = warp - kEpiWarp0;               // 0 .. 15
+  const int quarter = e & 3;                    // TMEM lane quarter (= warp & 3)
+  const int cbi = e >> 2;                       // 32-column block of a 128-column chunk / of the conv0 accumulator
+  const int m4 = lane & 3, r8 = lane >> 2;
+  const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+  constexpr int ts = (kDst == DF_F32 || kDst == DF_S32) ? 4 : 1;
+  const bool relu1 = p.relu1 != 0;
+  const int q_first = 2 * p.Wp;
+  // this thread's 8 channels inside a chunk / a conv0 block row, and where their constants live
+  const int chl = cbi * 32 + 8 * m4;
+  const uint32_t sb1 = sbase + p.off_bias1 + 4 * chl, ss1 = sbase + p.off_scale1 + 4 * chl;
+  const uint32_t bar_acc1_full = smem_u32(&bar->acc1_full[0]), bar_acc0_full = smem_u32(&bar->acc0_full[0]);
+  const uint32_t bar_mid_empty = smem_u32(&bar->mid_empty[0]);
+  uint32_t a_acc0_empty = smem_u32(&bar->acc0_empty[0]), a_acc1_empty = smem_u32(&bar->acc1_empty[0]);
+  uint32_t a_mid_full = smem_u32(&bar->mid_full[0]);
+  if constexpr (kPair) {
+    a_acc0_empty = mapa_u32(a_acc0_empty, 0);
+    a_acc1_empty = mapa_u32(a_acc1_empty, 0);
+    a_mid_full = mapa_u32(a_mid_full, 0);
+  }
+  auto arrive = [&](uint32_t a) {
+    if constexpr (kPair) mbar_arrive_cluster(a);
+    else mbar_arrive(a);
+  };
+  EpiTracer tr(p, 3, threadIdx.x == kEpiWarp0 * 32);
+  griddep_wait();  // earlier kernels in the stream may still be using the destination
+
+  // ---- pre-seeded conv1 accumulators: this warp's 32 lanes x 32 columns of both buffers
+  constexpr bool kSeed = seeded_acc1<G>();
+  const int k_add = kSeed ? 0 : p.k1_uniform;
+  [[maybe_unused]] uint32_t kseed[8];
+  const uint32_t t_acc1 = lane_addr + kAcc1Col + cbi * 32;  // buffer 0; buffer 1: + kAcc1Stride
+  auto seed_block = [&](uint32_t taddr32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tmem_st_32x32b_x8(taddr32 + 8 * i, kseed);
+  };
+  if constexpr (kSeed) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)  // volatile loads: ptxas must keep eight live registers instead of re-creating them per store
+      asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(kseed[i]) : "r"(sbase + p.off_k1 + 4 * i));
+    seed_block(t_acc1);
+    seed_block(t_acc1 + kAcc1Stride);
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) {
+      arrive(a_acc1_empty);
+      arrive(a_acc1_empty + 8);
+    }
+  }
+
+  // ---- position bookkeeping: lane l tracks tile row quarter * 32 + l (see PosState); the valid rows of the
+  //      warp's 32 are the contiguous pixel range [f0, f0 + popc(mask)), row r is pixel f0 + popc(mask below r)
+  PosState pos_lane = pos_of(p, q_first + tile0 * kTileM + quarter * 32 + lane);
+  int pos_it = 0;
+  uint8_t* rptr[4];  // where the thread's rows r8 + 8 ri go (its 8 channels of chunk 0)
+  uint32_t rvalid = 0;  // bit ri: row is a real pixel.  (Sending padding rows to a scratch area instead of predicating
+                        // the stores was 3.5x slower: every SM hammering the same few L2 lines.)
+  auto tile_rows = [&](int it) {
+    for (; pos_it < it; ++pos_it) pos_step(p, pos_lane, p.ts_dw, p.ts_dn, p.ts_dh);
+    const int pix = pos_pixel(p, pos_lane);
+    const uint32_t mask = __ballot_sync(0xffffffffu, pix >= 0);
+    const int f0 = __shfl_sync(0xffffffffu, pix, mask ? __ffs(mask) - 1 : 0);
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+      const int r = r8 + 8 * ri;
+      const int rho = __popc(mask & ((1u << r) - 1u));
+      rptr[ri] = static_cast<uint8_t*>(p.dst) + ((size_t)(f0 + rho) * G::OC1 + chl) * ts;
+      rvalid = (rvalid & ~(1u << ri)) | (((mask >> r) & 1u) << ri);
+    }
+  };
+
+  // ---- conv0 epilogue of local tile `it`: acc0 -> u8 -> intermediate tile in smem (K-major, swizzled);
+  //      warp e takes 32 rows (its lane quarter) x the 32-column blocks cbi, cbi + 4, ...
+  constexpr uint32_t swz_mask1 = (uint32_t)(G::swb1 / 16 - 1);
+  constexpr int nb0 = G::OC / 32;
+  constexpr int kbw = G::swb1;
+  auto unit_e0 = [&](int it) {
+    const int ab = it % G::n_acc0;
+    const int mb = it % p.NM;  // intermediate tile buffer
+    mbar_wait_warp(bar_mid_empty + 8 * mb, ((it / p.NM) & 1) ^ 1);
+    mbar_wait_warp(bar_acc0_full + 8 * ab, (it / G::n_acc0) & 1);
+    tc_fence_after_sync();
+    tr.ev(30);
+    const uint32_t mid = sbase + p.off_mid + mb * p.mid_bytes;
+    const uint32_t t_base = lane_addr + ab * G::OC;
+    bool released = false;
+#pragma unroll
+    for (int b = cbi; b < nb0; b += 4) {
+      const int ch0 = b * 32 + 8 * m4;
+      uint32_t acc[2][16];
+      tmem_ld_frag<8>(t_base + b * 32, acc[0]);
+      tmem_ld_frag<8>(t_base + (16u << 16) + b * 32, acc[1]);
+      float4 b4[2], s4[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        b4[i] = lds128f(sbase + p.off_bias0 + 4 * (ch0 + 4 * i));
+        s4[i] = lds128f(sbase + p.off_scale0 + 4 * (ch0 + 4 * i));
+      }
+      const int kb = ch0 / kbw;
+      const uint32_t off0 = (uint32_t)(quarter * 32 + r8) * kbw + (uint32_t)(ch0 - kb * kbw);
+      const uint32_t mid_kb = mid + kb * (uint32_t)(kTileM * kbw);
+      tmem_ld_wait();
+      if (b + 4 >= nb0) {  // last block of this warp: the accumulator is in registers
+        tc_fence_before_sync();
+        if (lane == 0) arrive(a_acc0_empty + 8 * ab);
+        released = true;
+      }
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri) {
+        uint32_t v[8], packed[2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = acc[ri >> 1][4 * (i / 2) + 2 * (ri & 1) + (i & 1)];
+        uint32_t off = off0 + (uint32_t)(ri * 8) * kbw;
+        off ^= ((off >> 7) & swz_mask1) << 4;
+        finish_conv0<false, false, 8>(v, b4, s4, packed);
+        sts_bytes<8>(mid_kb + off, packed);
+      }
+    }
+    if (!released) {  // warps without a conv0 block (OC < 128)
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) arrive(a_acc0_empty + 8 * ab);
+    }
+    fence_proxy_async_smem();  // intermediate tile -> visible to the tensor pipe (async proxy)
+    __syncwarp();
+    if (lane == 0) arrive(a_mid_full + 8 * mb);
+    tr.ev(31);
+  };
+
+  // ---- conv1 chunk j of the current tile (c = chunk counter of this CTA): this warp's 32 rows x 32 channels
+  auto unit_c = [&](auto j_c, uint32_t c) {
+    constexpr int j = decltype(j_c)::value;  // compile-time chunk index: constant offsets everywhere
+    const uint32_t cb = c & 1;
+    tr.ev(36);
+    mbar_wait_warp(bar_acc1_full + 8 * cb, (c >> 1) & 1);
+    tc_fence_after_sync();
+    tr.ev(32);
+    uint32_t acc[2][16];
+    const uint32_t t_blk = t_acc1 + cb * kAcc1Stride;
+    tmem_ld_frag<8>(t_blk, acc[0]);
+    tmem_ld_frag<8>(t_blk + (16u << 16), acc[1]);
+    float4 c4[2], s4[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      c4[i] = lds128f(sb1 + 4 * (j * 128 + 4 * i));
+      s4[i] = lds128f(ss1 + 4 * (j * 128 + 4 * i));
+    }
+    tmem_ld_wait();
+    tr.ev(38);
+    if constexpr (kSeed) {
+      seed_block(t_blk);  // the columns just read are K again for the chunk after next
+      tmem_st_wait();
+    }
+    tc_fence_before_sync();
+    if (lane == 0) arrive(a_acc1_empty + 8 * cb);  // accumulator is in registers: the tensor pipe may overwrite it
+    tr.ev(39);
+    // Padding rows are computed like any other and only their store is predicated off (a branch around a
+    // row costs more than the wasted arithmetic: 6..8 % of the rows for the BASELINE shapes).
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+      uint32_t v[8], w[ts == 1 ? 2 : 8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = acc[ri >> 1][4 * (i / 2) + 2 * (ri & 1) + (i & 1)];
+      finish_conv1<kDst, false, false, 8, true>(v, c4, s4, nullptr, k_add, true, relu1, w);
+      uint8_t* out = rptr[ri] + j * (128 * ts);
+      if constexpr (ts == 1) stg64_if(out, w, (rvalid >> ri) & 1u);
+      else stg256_if(out, w, (rvalid >> ri) & 1u);
+    }
+    tr.ev(33);
+  };
+
+  // ---- the unit stream:  E0(0) | C_0(t) .. C_{n-2}(t)  E0(t+1)  C_{n-1}(t) | ...
+  uint32_t c = 0;
+  if (n_local > 0) unit_e0(0);
+  for (int it = 0; it < n_local; ++it) {
+    tile_rows(it);
+    static_for<G::n_chunks>([&](auto j_c) {
+      constexpr int j = decltype(j_c)::value;
+      if (j == G::n_chunks - 1 && it + 1 < n_local) unit_e0(it + 1);
+      unit_c(j_c, c);
+      ++c;
+    });
+  }
+}
+
 // ---- store thread of the staged output path (one elected thread of warp 3): sends every staged conv1
 // chunk to the destination (store_staged_chunk) in the order the epilogue produces them
 template <class G, class Bar>
@@ -747,7 +1088,7 @@ __device__ __forceinline__ void store_role(const Params& p, const DstMaps& tmD, 
       const uint32_t cb = c & 1;
       mbar_wait(smem_u32(&bar->stage_full[cb]), (c >> 1) & 1);
       tr.ev(40);
-      if (!(p.dbg_no_mma & 2)) store_staged_chunk(tmD, sbase + p.off_stage + cb * kStageBytes, f0, V, j * g.nc1());
+      if (!dbg_flag(p, 2)) store_staged_chunk(tmD, sbase + p.off_stage + cb * kStageBytes, f0, V, j * g.nc1());
       tr.ev(41);
       bulk_wait_read_all();
       tr.ev(42);
@@ -825,6 +1166,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(smem_u32(&bar->stage_full[i]), kUnitWarps);
       mbar_init(smem_u32(&bar->stage_empty[i]), 1);
     }
+    for (int i = 0; i < kG1Ahead; ++i) mbar_init(smem_u32(&bar->g1_prog[i]), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW0);
@@ -919,23 +1261,25 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(smem_u32(&bar->res_full), 0);
         uint32_t c = 0;
         for (int it = 0; it < n_local; ++it) {
-          mbar_wait(smem_u32(&bar->mid_full[0]), it & 1);
+          const int mb = it % p.NM;
+          mbar_wait(smem_u32(&bar->mid_full[mb]), (it / p.NM) & 1);
+          const uint64_t mid_it = mid_desc + (uint64_t)((mb * p.mid_bytes) >> 4);
           for (int j = 0; j < g.n_chunks(); ++j, ++c) {
             const uint32_t cb = c & 1;
-            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c >> 1) & 1) ^ 1);
+            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c >> 1) & 1) ^ (seeded_acc1<G>() ? 0 : 1));  // seeded: handed over by the epilogue first
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
 #pragma unroll
             for (int kb = 0; kb < g.nkb1(); ++kb) {
               const uint64_t b_desc = w1_desc + (uint64_t)((j * g.nkb1() + kb) * w1_step);
-              const uint64_t a_desc = mid_desc + kb * mid_step_kb;
+              const uint64_t a_desc = mid_it + kb * mid_step_kb;
               const int nks = (kb == g.nkb1() - 1) ? g.ks1_last() : nks1_full;
 #pragma unroll
-              for (int ks = 0; ks < nks; ++ks) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, (kb | ks) != 0);
+              for (int ks = 0; ks < nks; ++ks) if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, seeded_acc1<G>() || (kb | ks) != 0);
             }
             umma_commit(smem_u32(&bar->acc1_full[cb]));
           }
-          umma_commit(smem_u32(&bar->mid_empty[0]));
+          umma_commit(smem_u32(&bar->mid_empty[mb]));
         }
       }
     }
@@ -966,8 +1310,12 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       // ---- taps [kw0, kw1) of tap row kh of GEMM1: K-blocks x K-steps each, descriptors by addition,
       //      weights in order
+      uint32_t tap_i = 0;  // taps issued so far (GEMM1 throttle, all-resident plan only: see kG1Ahead)
+      const bool throttle = g.w0_res() && g.w1_res();
       auto gemm1_taps = [&](int kh, int kw0, int kw1, uint32_t d_tmem, uint64_t a_tile) {
         for (int kw = kw0; kw < kw1; ++kw) {
+          if (throttle && tap_i >= (uint32_t)kG1Ahead)
+            mbar_wait(smem_u32(&bar->g1_prog[tap_i % kG1Ahead]), ((tap_i / kG1Ahead) - 1) & 1);
 #pragma unroll
           for (int kb = 0; kb < g.nkb(); ++kb) {
             const int blk = (kh * 3 + kw) * g.nkb() + kb;  // block index inside the tile
@@ -984,11 +1332,15 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t a_desc = a_tile + kh * a_step_kh + kw * a_step_kw + kb * a_step_kb;
             const int nks = (kb == g.nkb() - 1) ? g.ks_last() : nks_full;
 #pragma unroll
-            for (int ks = 0; ks < nks; ++ks) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+            for (int ks = 0; ks < nks; ++ks) if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
             if (!g.w0_res()) {
               umma_commit(smem_u32(&bar->b_empty[st]));
               if (++bs == (uint32_t)g.SB()) { bs = 0; bph ^= 1; }
             }
+          }
+          if (throttle) {
+            umma_commit(smem_u32(&bar->g1_prog[tap_i % kG1Ahead]));
+            ++tap_i;
           }
         }
       };
@@ -1010,7 +1362,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint64_t a_desc = mid_desc + kb * mid_step_kb;
           const int nks = (kb == g.nkb1() - 1) ? g.ks1_last() : nks1_full;
 #pragma unroll
-          for (int ks = 0; ks < nks; ++ks) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, (kb | ks) != 0);
+          for (int ks = 0; ks < nks; ++ks) if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, seeded_acc1<G>() || (kb | ks) != 0);
           if (!g.w1_res()) {
             umma_commit(smem_u32(&bar->b_empty[st]));
             if (++bs == (uint32_t)g.SB()) { bs = 0; bph ^= 1; }
@@ -1066,7 +1418,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             if (g2_open) {
               const int cb = c1count & 1;
-              if (mbar_test_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ 1)) {
+              if (mbar_test_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ (seeded_acc1<G>() ? 0 : 1))) {
                 tc_fence_after_sync();
                 const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid + mb * p.mid_bytes) >> 4);
                 gemm2_chunk(g2_j, tmem + kAcc1Col + cb * kAcc1Stride, mid_desc);
@@ -1142,7 +1494,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid + mb * p.mid_bytes) >> 4);
             for (int j = 0; j < g.n_chunks(); ++j, ++c1count) {
               const int cb = c1count & 1;
-              mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ 1);
+              mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ (seeded_acc1<G>() ? 0 : 1));
               tc_fence_after_sync();
               gemm2_chunk(j, tmem + kAcc1Col + cb * kAcc1Stride, mid_desc);
               umma_commit(smem_u32(&bar->acc1_full[cb]));
@@ -1156,12 +1508,17 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp >= kEpiWarp0) {
     // ====================================== epilogue =======================================
     load_epilogue_constants<G>(p, smem);
-    epilogue_role<G, kDst, kDown0, kDown1, kNanSafe, false>(p, smem, bar, tmem, warp, lane, n_local, (int)blockIdx.x,
-                                                            (int)gridDim.x);
+    if constexpr (static_epilogue<G>())
+      epilogue_static<G, kDst, false>(p, tmD, smem, bar, tmem, warp, lane, n_local, (int)blockIdx.x, (int)gridDim.x);
+    else
+      epilogue_role<G, kDst, kDown0, kDown1, kNanSafe, false>(p, smem, bar, tmem, warp, lane, n_local, (int)blockIdx.x,
+                                                              (int)gridDim.x);
   } else if (warp == 3) {
-    // ================================ store thread (staged output) ==========================
-    if ((kDst == DF_U8 || kDst == DF_S8) && p.stage_out && elect_one())
-      store_role<G>(p, tmD, bar, sbase, n_local, (int)blockIdx.x, (int)gridDim.x);
+    // ====================== store thread (staged output, run-time geometry only) ================
+    if constexpr (!G::is_static) {
+      if ((kDst == DF_U8 || kDst == DF_S8) && p.stage_out && elect_one())
+        store_role<G>(p, tmD, bar, sbase, n_local, (int)blockIdx.x, (int)gridDim.x);
+    }
   }
 
   tc_fence_before_sync();
@@ -1190,6 +1547,7 @@ struct PairBarriers {
   uint64_t mid_full[2], mid_empty[2];
   uint64_t acc1_full[2], acc1_empty[2];
   uint64_t stage_full[2], stage_empty[2];
+  uint64_t g1_prog[kG1Ahead];  // GEMM1 issue throttle (see G1Throttle)
   uint32_t tmem_base;
 };
 
@@ -1233,6 +1591,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&bar->stage_full[i]), kUnitWarps);
       mbar_init(smem_u32(&bar->stage_empty[i]), 1);
     }
+    for (int i = 0; i < kG1Ahead; ++i) mbar_init(smem_u32(&bar->g1_prog[i]), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW0);
@@ -1314,28 +1673,30 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(smem_u32(&bar->peer_ready[3]), 0);
         uint32_t c = 0;
         for (int it = 0; it < n_local; ++it) {
-          mbar_wait(smem_u32(&bar->mid_full[0]), it & 1);
+          const int mb = it % p.NM;
+          mbar_wait(smem_u32(&bar->mid_full[mb]), (it / p.NM) & 1);
+          const uint64_t mid_it = mid_desc + (uint64_t)((mb * p.mid_bytes) >> 4);
           tr.ev(12);
 #pragma unroll
           for (int j = 0; j < G::n_chunks; ++j, ++c) {
             const uint32_t cb = c & 1;
-            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c >> 1) & 1) ^ 1);
+            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c >> 1) & 1) ^ (seeded_acc1<G>() ? 0 : 1));  // seeded: handed over by the epilogue first
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
 #pragma unroll
             for (int kb = 0; kb < G::nkb1; ++kb) {
               const uint64_t b_desc = w1_desc + (uint64_t)((j * G::nkb1 + kb) * (kW1Half >> 4));
-              const uint64_t a_desc = mid_desc + kb * ((kTileM * G::swb1) >> 4);
+              const uint64_t a_desc = mid_it + kb * ((kTileM * G::swb1) >> 4);
               constexpr int nks_full = G::swb1 >> 5;
               const int nks = (kb == G::nkb1 - 1) ? G::ks1_last : nks_full;
 #pragma unroll
               for (int ks = 0; ks < nks; ++ks)
-                if (!(p.dbg_no_mma & 1)) umma_i8_pair(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, (kb | ks) != 0);
+                if (!dbg_flag(p, 1)) umma_i8_pair(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, seeded_acc1<G>() || (kb | ks) != 0);
             }
             umma_commit_pair(smem_u32(&bar->acc1_full[cb]));
             tr.ev(13);
           }
-          umma_commit_pair(smem_u32(&bar->mid_empty[0]));
+          umma_commit_pair(smem_u32(&bar->mid_empty[mb]));
         }
       }
     }
@@ -1348,7 +1709,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint64_t w0_desc = desc0_hi | ((sbase + p.off_w0) >> 4);
       Tracer tr(p, 1);
       tr.ev(9);
-      uint32_t sa = 0, a_par = 0;
+      uint32_t sa = 0, a_par = 0, tap_i = 0;
       for (int it = 0; it < n_local; ++it) {
         const int ab = it & 1;
         mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it >> 1) & 1) ^ 1);
@@ -1366,6 +1727,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
+            if (tap_i >= (uint32_t)kG1Ahead)  // throttle, see kG1Ahead
+              mbar_wait(smem_u32(&bar->g1_prog[tap_i % kG1Ahead]), ((tap_i / kG1Ahead) - 1) & 1);
 #pragma unroll
             for (int kb = 0; kb < G::nkb; ++kb) {
               const int blk = (kh * 3 + kw) * G::nkb + kb;
@@ -1375,8 +1738,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int nks = (kb == G::nkb - 1) ? G::ks_last : nks_full;
 #pragma unroll
               for (int ks = 0; ks < nks; ++ks)
-                if (!(p.dbg_no_mma & 1)) umma_i8_pair(d0, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+                if (!dbg_flag(p, 1)) umma_i8_pair(d0, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
             }
+            umma_commit_pair_local(smem_u32(&bar->g1_prog[tap_i % kG1Ahead]));
+            ++tap_i;
           }
         }
         umma_commit_pair(smem_u32(&bar->a_empty[sa]));
@@ -1388,11 +1753,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= kEpiWarp0) {
     // ================================== epilogue (both CTAs) ===================================
     load_epilogue_constants<G>(p, smem);
-    epilogue_role<G, kDst, false, false, false, true>(p, smem, bar, tmem, warp, lane, n_local, 2 * cid + (int)rank, 2 * ncl);
+    if constexpr (static_epilogue<G>())
+      epilogue_static<G, kDst, true>(p, tmD, smem, bar, tmem, warp, lane, n_local, 2 * cid + (int)rank, 2 * ncl);
+    else
+      epilogue_role<G, kDst, false, false, false, true>(p, smem, bar, tmem, warp, lane, n_local, 2 * cid + (int)rank, 2 * ncl);
   } else if (warp == 3) {
-    // ================================ store thread (staged output) ==========================
-    if ((kDst == DF_U8 || kDst == DF_S8) && p.stage_out && elect_one())
-      store_role<G>(p, tmD, bar, sbase, n_local, 2 * cid + (int)rank, 2 * ncl);
+    if constexpr (!G::is_static) {
+      if ((kDst == DF_U8 || kDst == DF_S8) && p.stage_out && elect_one())
+        store_role<G>(p, tmD, bar, sbase, n_local, 2 * cid + (int)rank, 2 * ncl);
+    }
   }
 
   tc_fence_before_sync();

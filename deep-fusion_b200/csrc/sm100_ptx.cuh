@@ -262,6 +262,10 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       "h"((uint16_t)3)
       : "memory");
 }
+// arrive on a barrier of the ISSUING CTA only when the leader's prior MMAs have completed
+__device__ __forceinline__ void umma_commit_pair_local(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 // TMA tile load executed by either CTA of a pair; completion bytes go to the LEADER's mbarrier
 __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1,
                                                  int c2, int c3) {

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(os.path.dirname(_HERE), "lib")
+LIB_DIR = os.environ.get("DFB200_LIB_DIR") or os.path.join(os.path.dirname(_HERE), "lib")  # (override: development builds, e.g. lib_trace)
 LIB_PATH = os.path.join(LIB_DIR, "libdfcuda.so")
 
 UNDEF, F32, S32, S8, U8 = 0, 1, 2, 3, 4

@@ -7,10 +7,10 @@ import dfb200 as df
 from dfb200 import synth, layout
 
 TAGS = {1: "A.issue", 8: "M.begin", 9: "M.start", 10: "M.g1_go", 11: "M.g1_issued", 12: "M.g2_go", 13: "M.g2_chunk", 14: "M.tap", 20: "B.iter",
-        30: "E.acc0_ready", 31: "E.epi0_done", 32: "E.acc1_ready", 33: "E.chunk_done", 36: "E.unit_begin", 34: "E.stage_free", 35: "E.math_done",
+        30: "E.acc0_ready", 31: "E.epi0_done", 32: "E.acc1_ready", 33: "E.chunk_done", 36: "E.unit_begin", 34: "E.stage_free", 35: "E.math_done", 37: "E.ld_issued", 38: "E.ld_landed", 39: "E.released",
         40: "S.full", 41: "S.issued", 42: "S.read_done"}
 
-def run(n, h, w, ic, oc, oc1, dst="u8", cta=0, cap=512, max_lines=120):
+def run(n, h, w, ic, oc, oc1, dst="u8", cta=0, cap=512, max_lines=120, skip=0):
     w0 = synth.wei_s8(2, (oc, ic, 3, 3)); w1 = synth.wei_s8(3, (oc1, oc))
     op = df.Conv(n, h, w, ic, oc, oc1, df.DT_OF[dst], layout.oihw_to_blocked(w0), layout.oihw_to_blocked(w1.reshape(oc1, oc, 1, 1)),
                  synth.bias(4, oc, "s32"), synth.bias(5, oc1, "s32"), synth.channel_scales(oc, 13), synth.channel_scales(oc1, 12), df.S32, df.S32)
@@ -40,7 +40,7 @@ def run(n, h, w, ic, oc, oc1, dst="u8", cta=0, cap=512, max_lines=120):
     t0 = ev[0][0]
     print(f"--- {h}x{w} {ic}->{oc}->{oc1} n={n} dst={dst} tiles={i.tiles_per_launch} grid={i.grid} cta={cta} events={len(ev)} span={ev[-1][0]-t0} cycles")
     prev = t0
-    for k, (c, tag, role) in enumerate(ev[:max_lines]):
+    for k, (c, tag, role) in enumerate(ev[skip:skip + max_lines]):
         print(f"{c - t0:8d} (+{c - prev:6d}) {'  ' * role}{TAGS.get(tag, tag)}")
         prev = c
     # per-tile steady state estimate from epilogue chunk-done events
@@ -51,6 +51,8 @@ def run(n, h, w, ic, oc, oc1, dst="u8", cta=0, cap=512, max_lines=120):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "cfg1"
-    if which == "cfg1": run(64, 56, 56, 64, 64, 256)
-    elif which == "cfg3": run(64, 28, 28, 128, 128, 512)
+    nb = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    skip = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    if which == "cfg1": run(nb, 56, 56, 64, 64, 256)
+    elif which == "cfg3": run(nb, 28, 28, 128, 128, 512, skip=skip)
     elif which == "cfg4": run(256, 14, 14, 256, 256, 1024)
