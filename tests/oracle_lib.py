@@ -110,3 +110,40 @@ def replay_concat(dt, relu, srcs):
 
 def replay_supported():
     return bool(lib().dfr_supported())
+
+
+# ---- oracle/_ref/libdfref.so: the reference's own kernel generators (unmodified sources) executed through
+#      the recording Xbyak stand-in (oracle/ref_driver.cc).  Built only where /root/reference exists; the
+#      built .so travels to the GPU box with the snapshot.
+_REF_SO = os.path.join(ROOT, "oracle", "_ref", "libdfref.so")
+_ref = None
+
+
+def ref_lib():
+    """The reference-executing library, or None when it was never built / the host lacks AVX-512 VNNI."""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(_REF_SO) and os.path.exists("/root/reference/src/jit_conv_kernel.cc"):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "_ref"])
+        if not os.path.exists(_REF_SO):
+            return None
+        l = C.CDLL(_REF_SO)
+        l.dfref_last_kernel_instructions.restype = C.c_long
+        if not l.dfref_supported():
+            return None
+        _ref = l
+    return _ref
+
+
+def ref_conv(d, src, wei, bia0, scale0, wei1=None, bia1=None, scale1=None):
+    return _conv(ref_lib().dfref_conv, d, src, wei, bia0, scale0, wei1, bia1, scale1)
+
+
+def ref_concat(dt, relu, srcs):
+    return _concat(ref_lib().dfref_concat, dt, relu, srcs)
+
+
+def ref_blocking():
+    out = (C.c_int * 5)()
+    ref_lib().dfref_last_blocking(out)
+    return list(out)
