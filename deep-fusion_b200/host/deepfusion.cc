@@ -14,6 +14,9 @@
 #include <string.h>
 #include <sys/time.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "df_host.h"
 
 namespace deepfusion {
@@ -54,8 +57,71 @@ static void cuda_or_exit(int rc, const char *what) {
   if (rc != 0) error_and_exit("%s failed (%d): %s", what, rc, df_last_error());
 }
 
+// include/deepfusion.h is the reference's header, byte for byte: `memory` has no member for the device mirror
+// and `op` has no virtual destructor.  What the B200 layer adds to both lives in side tables keyed by the
+// object's address.
+static std::mutex g_mu;
+static std::unordered_map<const memory *, memory_state> &memory_states() {
+  static std::unordered_map<const memory *, memory_state> *t = new std::unordered_map<const memory *, memory_state>();
+  return *t;  // (never destroyed: memories with static storage may outlive any table destructor)
+}
+memory_state *state_of(memory &m) {
+  std::lock_guard<std::mutex> g(g_mu);
+  return &memory_states()[&m];  // node-based map: the address stays valid until erased
+}
+static void drop_state(memory &m) {
+  memory_state st;
+  {
+    std::lock_guard<std::mutex> g(g_mu);
+    auto it = memory_states().find(&m);
+    if (it == memory_states().end()) return;
+    st = it->second;
+    memory_states().erase(it);
+  }
+  if (st.pinned) df_host_unregister(m.data());
+  if (st.dev) df_free(st.dev);
+}
+
+// An op created by the factories is destroyed through `std::unique_ptr<op>` -- i.e. through a base class
+// WITHOUT a virtual destructor (reference include/deepfusion.h:105-114), so a derived destructor never
+// runs.  Everything an op owns therefore sits in an op_resources object in this table; it is released
+//   * explicitly by ext::release(op), or
+//   * when a new op is created at the same address (the old one can only be gone), or
+//   * at process exit.
+// The reference's own op_conv / op_concat leak their workspaces in exactly this situation.
+static std::unordered_map<const op *, op_resources *> &op_table() {
+  static std::unordered_map<const op *, op_resources *> *t = new std::unordered_map<const op *, op_resources *>();
+  return *t;
+}
+void adopt_resources(const op *o, op_resources *r) {
+  op_resources *stale = nullptr;
+  {
+    std::lock_guard<std::mutex> g(g_mu);
+    auto it = op_table().find(o);
+    if (it != op_table().end()) {
+      stale = it->second;
+      it->second = r;
+    } else {
+      op_table()[o] = r;
+    }
+  }
+  delete stale;
+}
+bool release_resources(const op *o) {
+  op_resources *r = nullptr;
+  {
+    std::lock_guard<std::mutex> g(g_mu);
+    auto it = op_table().find(o);
+    if (it == op_table().end()) return false;
+    r = it->second;
+    op_table().erase(it);
+  }
+  delete r;
+  return true;
+}
+
 static void *mirror(memory &m) {
-  memory_state *st = m.state();
+  memory_state *st = state_of(m);
   if (!st->dev) cuda_or_exit(df_malloc(m.buffer_size(), &st->dev), "device allocation");
   return st->dev;
 }
@@ -90,24 +156,20 @@ static memory::dims nchw2format(const memory::nchw_dims &dm, const memory::forma
 }
 
 memory::memory(const nchw_dims &dm, const format fmt, const dtype dt, int alignment)
-    : data_(nullptr), std_dims_(dm), fmt_(fmt), dt_(dt), state_(new detail::memory_state()) {
+    : data_(nullptr), std_dims_(dm), fmt_(fmt), dt_(dt) {
   dims_ = nchw2format(dm, fmt);
   allocate_buffer(alignment);
 }
 
 memory::memory(const dims &dm, const format fmt, const dtype dt, int alignment)
-    : data_(nullptr), dims_(dm), fmt_(fmt), dt_(dt), state_(new detail::memory_state()) {
+    : data_(nullptr), dims_(dm), fmt_(fmt), dt_(dt) {
   // the reference leaves std_dims_ uninitialised here although op_conv reads it (defect D5)
   for (size_t i = 0; i < 4; ++i) std_dims_[i] = i < dm.size() ? dm[i] : 1;
   allocate_buffer(alignment);
 }
 
 memory::~memory() {
-  if (state_) {
-    if (state_->pinned) df_host_unregister(data_);
-    if (state_->dev) df_free(state_->dev);
-    delete state_;
-  }
+  detail::drop_state(*this);
   free(data_);
 }
 
@@ -142,7 +204,8 @@ namespace {
 class concat_op : public detail::device_op {
 public:
   concat_op(const std::vector<std::unique_ptr<memory>> &srcs, std::unique_ptr<memory> &dst, bool post_relu)
-      : relu_(post_relu), dst_(dst.get()) {
+      : relu_(post_relu), dst_(dst.get()), res_(new resources()), srcs_(res_->srcs), ic_(res_->ic) {
+    detail::adopt_resources(this, res_);
     if (!init_conf(srcs, dst)) error_and_exit("Init Concat op failed!");
     for (size_t i = 0; i < srcs.size(); ++i) srcs_.push_back(srcs[i].get());
   }
@@ -196,10 +259,15 @@ protected:
   const char *name() override { return "concat"; }
 
 private:
+  struct resources : detail::op_resources {  // heap state of the op (see detail::adopt_resources)
+    std::vector<memory *> srcs;
+    std::vector<int> ic;
+  };
   bool relu_;
   memory *dst_;
-  std::vector<memory *> srcs_;
-  std::vector<int> ic_;
+  resources *res_;
+  std::vector<memory *> &srcs_;
+  std::vector<int> &ic_;
   long n_pixels_ = 0;
 };
 
@@ -227,11 +295,9 @@ public:
       info("%s", df_last_error());
       error_and_exit("Init Conv op failed!");
     }
-  }
-  ~conv_op() override {
-    df_conv_destroy(handle_);
-    for (void *e : events_) df_event_destroy(e);
-    for (void *st : streams_) df_stream_destroy(st);
+    res_ = new resources();
+    res_->handle = handle_;
+    detail::adopt_resources(this, res_);
   }
 
   void launch(void *stream) override {
@@ -358,8 +424,9 @@ protected:
       cuda_or_exit(df_stream_sync(nullptr), "conv sync");
       return;
     }
+    std::vector<void *> &streams_ = res_->streams, &events_ = res_->events;
     if (streams_.empty()) {
-      detail::memory_state *ss = src_->state(), *ds = dst_->state();  // pinned buffers make the copies truly asynchronous
+      detail::memory_state *ss = detail::state_of(*src_), *ds = detail::state_of(*dst_);  // pinned buffers make the copies truly asynchronous
       if (!ss->pinned && df_host_register(src_->data(), src_->buffer_size()) == 0) ss->pinned = true;
       if (!ds->pinned && df_host_register(dst_->data(), dst_->buffer_size()) == 0) ds->pinned = true;
       streams_.resize(3);
@@ -384,10 +451,20 @@ protected:
   const char *name() override { return "conv"; }
 
 private:
+  // what the op owns (see detail::adopt_resources: `op` has no virtual destructor)
+  struct resources : detail::op_resources {
+    df_conv *handle = nullptr;
+    std::vector<void *> streams, events;  // created on the first pipelined submit()
+    ~resources() override {
+      df_conv_destroy(handle);
+      for (void *e : events) df_event_destroy(e);
+      for (void *st : streams) df_stream_destroy(st);
+    }
+  };
   memory *src_, *dst_;
   df_conv_desc desc_;
   df_conv *handle_ = nullptr;
-  std::vector<void *> streams_, events_;  // created on the first pipelined submit()
+  resources *res_ = nullptr;
 };
 
 }  // namespace
@@ -451,8 +528,12 @@ int launches_per_submit(op &o) {
   return d ? d->launches() : 0;
 }
 void pin(memory &m) {
-  detail::memory_state *st = m.state();
+  detail::memory_state *st = detail::state_of(m);
   if (!st->pinned && df_host_register(m.data(), m.buffer_size()) == 0) st->pinned = true;
+}
+void release(std::unique_ptr<op> &o) {
+  if (o) detail::release_resources(o.get());
+  o.reset();
 }
 
 }  // namespace ext

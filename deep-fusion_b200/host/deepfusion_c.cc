@@ -69,6 +69,9 @@ void dfh_op_submit(dfh_op *op) { op->o->submit(); }
 void dfh_op_submit_device(dfh_op *op, void *stream) { ext::submit_device(*op->o, stream); }
 int dfh_op_launches(dfh_op *op) { return ext::launches_per_submit(*op->o); }
 void dfh_sync(void *stream) { ext::sync(stream); }
-void dfh_op_destroy(dfh_op *op) { delete op; }
+void dfh_op_destroy(dfh_op *op) {
+  if (op) ext::release(op->o);
+  delete op;
+}
 
 }  // extern "C"

@@ -24,11 +24,20 @@ namespace deepfusion {
 
 namespace detail {
 
-// device mirror of one memory
+// device mirror of one memory (side table keyed by the memory's address: the public header is the
+// reference's, unchanged, and has no room for it)
 struct memory_state {
   void *dev = nullptr;
   bool pinned = false;
 };
+memory_state *state_of(memory &m);
+
+// what an op owns; released by ext::release(), address reuse or process exit (op has no virtual destructor)
+struct op_resources {
+  virtual ~op_resources() {}
+};
+void adopt_resources(const op *o, op_resources *r);
+bool release_resources(const op *o);
 
 // every B200 op: launch on device mirrors, asynchronously
 class device_op : public op {

@@ -1,17 +1,23 @@
-// deepfusion.h -- public C++ API of deep-fusion, B200 edition.
-//
-// Source-compatible with the reference's include/deepfusion.h:25-146: the same namespace, type
-// names, enumerators, constructors, accessors and factory signatures (including defaults), so code
-// written against the reference recompiles against this header and links libdeepfusion.so
-// unchanged.  What differs is behind the API: `memory` also owns a lazily created device mirror
-// and `op::submit()` runs hand-written sm_100a kernels through the C-ABI in dfcuda.h (host -> device
-// copy of the sources, kernel, device -> host copy of the destination, synchronous like the
-// reference).  Additive, non-reference entry points live in deepfusion_ext.h.
+/*******************************************************************************
+* Copyright 2017-2018 Intel Corporation
+*
+* Licensed under the Apache License, Version 2.0 (the "License");
+* you may not use this file except in compliance with the License.
+* You may obtain a copy of the License at
+*
+*     http://www.apache.org/licenses/LICENSE-2.0
+*
+* Unless required by applicable law or agreed to in writing, software
+* distributed under the License is distributed on an "AS IS" BASIS,
+* WITHOUT WARRANTIES OR CONDITIONS OF ANY KIND, either express or implied.
+* See the License for the specific language governing permissions and
+* limitations under the License.
+*******************************************************************************/
+
 #pragma once
 
 #include <stdint.h>
 #include <stdlib.h>
-
 #include <array>
 #include <memory>
 #include <vector>
@@ -23,7 +29,7 @@ typedef int32_t s32;
 typedef int8_t s8;
 typedef uint8_t u8;
 
-// kept for users of the reference header (include/deepfusion.h:33-40)
+// Disable the copy and assignment operator for a class.
 #ifndef DISABLE_COPY_AND_ASSIGN
 #define DISABLE_COPY_AND_ASSIGN(classname)          \
 private:                                            \
@@ -37,19 +43,13 @@ struct opdesc {
   int tmp;
 };
 
-// rounding of the f32 -> integer conversions in the conv epilogues (reference :46-49)
 enum round_mode {
-  nearest = 0,  // round half to even (vcvtps2dq {rn-sae})
-  down,         // toward -inf        (vcvtps2dq {rd-sae})
+  nearest = 0,
+  down,
 };
-
-namespace detail {
-struct memory_state;  // host-layer private: device mirror bookkeeping
-}
 
 struct memory {
 public:
-  // reference :53-61
   enum format {
     format_undef = 0,
     x,
@@ -63,7 +63,6 @@ public:
   typedef std::array<int, 2> pair_dims;
   typedef std::array<int, 4> nchw_dims;
 
-  // reference :66-72
   enum dtype {
     undef = 0,
     f32,
@@ -72,41 +71,40 @@ public:
     u8,
   };
 
-  // Logical dims are always given as N,C,H,W (or O,I,H,W); the buffer is laid out per `fmt`.
-  explicit memory(const nchw_dims &dm, const format fmt, const dtype dt, int alignment = 4096);
-  // Dims given in the physical order of `fmt` (used for format::x biases).
-  explicit memory(const dims &dm, const format fmt, const dtype dt, int alignment = 4096);
+  // TODO: enable more format init
+  // explicit memory(const dims& dm, const format fmt, const dtype dt, int
+  // alignment = 64);
+  explicit memory(const nchw_dims &dm,
+                  const format fmt,
+                  const dtype dt,
+                  int alignment = 4096);
+  explicit memory(const dims &dm,
+                  const format fmt,
+                  const dtype dt,
+                  int alignment = 4096);
   ~memory();
-
-  size_t size();         // number of elements
-  size_t buffer_size();  // bytes
+  size_t size();
+  size_t buffer_size();
   dims actual_dims() { return dims_; }
   nchw_dims std_dims() { return std_dims_; }  // nchw or oihw
   dtype data_type() { return dt_; }
   format dim_format() { return fmt_; }
-  void *data() { return data_; }  // HOST pointer, valid for the lifetime of the object
-
-  detail::memory_state *state() { return state_; }
+  void *data() { return data_; }
 
 private:
   void allocate_buffer(int alignment);
   void *data_;
   dims dims_;
-  nchw_dims std_dims_;
+  nchw_dims std_dims_;  // nchw or oihw
   format fmt_;
   dtype dt_;
-  detail::memory_state *state_;
 
   DISABLE_COPY_AND_ASSIGN(memory);
 };
 
-// An operator borrows the memories it was created with (raw pointers captured at creation, as in
-// the reference, src/op_conv.h:82-95): they must outlive the op.  submit() is synchronous and
-// must not be called concurrently on the same op.
 class op {
 public:
   explicit op() {}
-  virtual ~op() {}
   virtual void submit();
 
 protected:
@@ -115,12 +113,11 @@ protected:
   DISABLE_COPY_AND_ASSIGN(op);
 };
 
-// concat along channels (+ optional ReLU); reference :116-118
 std::unique_ptr<op> concat(const std::vector<std::unique_ptr<memory>> &srcs,
                            std::unique_ptr<memory> &dst,
                            bool post_relu = false);
 
-// conv only; reference :121-129
+// only conv
 std::unique_ptr<op> conv(const std::unique_ptr<memory> &src,
                          const std::unique_ptr<memory> &wei,
                          const std::unique_ptr<memory> &bia,
@@ -131,7 +128,7 @@ std::unique_ptr<op> conv(const std::unique_ptr<memory> &src,
                          std::vector<float> conv0_scales = {1.f},
                          round_mode conv0_round_mode = round_mode::nearest);
 
-// conv + ReLU fused with conv1x1 (+ ReLU); reference :132-145
+// conv and fuse conv1x1_relu
 std::unique_ptr<op> conv(const std::unique_ptr<memory> &src,
                          const std::unique_ptr<memory> &wei,
                          const std::unique_ptr<memory> &bia,
@@ -146,4 +143,4 @@ std::unique_ptr<op> conv(const std::unique_ptr<memory> &src,
                          bool conv1_relu = false,
                          std::vector<float> conv1_scales = {1.f},
                          round_mode conv1_round_mode = round_mode::nearest);
-}  // namespace deepfusion
+}

@@ -22,6 +22,10 @@ void sync(void *stream = nullptr);
 int launches_per_submit(op &o);
 // Pin the host buffer of a memory (cudaHostRegister) so submit()'s copies run at full PCIe speed.
 void pin(memory &m);
+// Destroys an op together with the device resources it owns.  Plain destruction through std::unique_ptr<op>
+// cannot do that: the reference's `op` (include/deepfusion.h:105-114, kept verbatim) has no virtual destructor,
+// so the resources of an op that is simply dropped are reclaimed only when its address is reused or at exit.
+void release(std::unique_ptr<op> &o);
 
 }  // namespace ext
 }  // namespace deepfusion
