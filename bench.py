@@ -12,8 +12,13 @@ sharded over GPUs by batch (weak scaling: 64 images per GPU), with no data-path 
                pinned HOST buffers: H2D of the batch + kernel + D2H of the result inside the timed region
  roofline      the fused conv kernel against the tensor roofline
  concat        the concat+ReLU op (BASELINE configs[1]) against the HBM roofline, reported beside it
- cpu_baseline  the AVX-512-VNNI + OpenMP port of the reference's CPU path on this box's host cores
-`--impl reference` times that CPU port alone (the reference itself cannot be built: DESIGN.md §2).
+ other_shapes  the other BASELINE conv shapes (cfg1 batch 1 / 64, cfg4 u8 / s32 / f32) and a >= 1 s sustained run of
+               the headline shape, each against its own roofline (HBM where the arithmetic intensity is below the ridge)
+ cpu_baseline  the AVX-512-VNNI + OpenMP port of the reference's CPU path on this box's host cores (hot and
+               cold cache, destination pre-allocated, warmed up by time)
+`--impl reference` times that CPU port alone.  The port is bit-identical to the reference's own kernel
+generators executed through oracle/_ref (tests/test_ref_pin.py); that interpreter is a checker, far slower
+than the JIT code it stands for, so it is not what is timed.
 """
 from __future__ import annotations
 
@@ -42,14 +47,18 @@ WORKLOADS = {
     "cfg4f32": (256, 14, 14, 256, 256, 1024, "f32", "conv3x3+ReLU+conv1x1+ReLU 14x14 256->256->1024, batch 256/GPU, f32 out (BASELINE configs[3])"),
 }
 CONCAT_CFG2 = (32, 28, 28, (64, 128, 32, 32))  # BASELINE configs[1]
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of the dominant
-# kernel (profiles/r01_conv_cfg3_v18_summary.txt, r01_concat_v15_summary.txt).  Both kernels read exactly
-# their algorithmic input from DRAM (conv: 6.42 MB of activations + 0.21 MB of weights; concat: 6.42 MB);
-# the output (conv 25.69 MB, concat 6.42 MB) is still in the 126 MB write-back L2 when the launch ends, so
-# the per-launch capture shows no DRAM writes -- in the rotating-buffer loop bench.py times they are
-# evicted later at the same rate, i.e. steady-state traffic = algorithmic bytes, no re-reads.
-NCU_TRAFFIC = {"cfg3": 6703616 + 0, "concat_cfg2": 6429184 + 0}
 K0 = {64: 12, 128: 13, 256: 14}
+
+
+def ncu_constants():
+    """Numbers that come from profiler captures / probes rather than from this run, read from
+    profiles/ncu_constants.json (written by scripts/ncu_constants.py from the .ncu-rep files; every entry
+    names its source).  Absent file or key -> None: nothing here is hard-coded."""
+    p = os.path.join(ROOT, "profiles", "ncu_constants.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def measured_peaks():
@@ -150,24 +159,56 @@ def barrier(dist):
 
 
 # ----------------------------------------------------------------------------------- CPU port
-def cpu_port_time(p, budget_s, min_runs=2):
-    """Times the AVX-512-VNNI + OpenMP port of the reference's CPU path (oracle/, checker-side code
-    used here only as the reported baseline).  Returns (images/s, runs, images per run, kind)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    n = p["n"]
-    fn, kind = (O.replay_conv, "port (AVX-512-VNNI replay, OpenMP)") if O.replay_supported() else (O.conv, "port (scalar C)")
-    if not O.replay_supported():
-        n = min(n, 2)
-    src = synth.src_u8(1, (n, p["h"], p["w"], p["ic"]))
-    d = O.make_desc(n, p["h"], p["w"], p["ic"], p["oc"], p["oc1"], O.DT_OF[p["dst"]], O.S32, O.S32, nscale0=p["oc"], nscale1=p["oc1"])
-    fn(d, src, p["w0b"], p["b0"], p["s0"], p["w1b"], p["b1"], p["s1"])  # warm-up
-    t0, runs = time.time(), 0
-    while runs < min_runs or (time.time() - t0) < budget_s:
-        fn(d, src, p["w0b"], p["b0"], p["s0"], p["w1b"], p["b1"], p["s1"])
-        runs += 1
-    dt = time.time() - t0
-    return n * runs / dt, runs, n, kind, int(O.lib().dfr_num_threads())
+class CpuArm:
+    """The AVX-512-VNNI + OpenMP port of the reference's CPU path (oracle/df_replay_avx512.c; checker-side code,
+    used here only as the reported baseline) on one batch of the workload.  The destination is allocated
+    ONCE (the reference's ops also own theirs), the arm is warmed up by time, and besides the hot-cache rate
+    it measures the reference's cold-cache protocol: every thread scrubs 2 MB between iterations
+    (test/test_utils.cc:23-49, benchmark/bench_concat.cc:86-110)."""
+
+    def __init__(self, p):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        self.O, self.p = O, p
+        self.fast = O.replay_supported()
+        self.n = p["n"] if self.fast else min(p["n"], 2)
+        self.fn = O.replay_conv if self.fast else O.conv
+        self.cores = int(O.lib().dfr_num_threads()) if self.fast else 1
+        self.src = synth.src_u8(1, (self.n, p["h"], p["w"], p["ic"]))
+        self.d = O.make_desc(self.n, p["h"], p["w"], p["ic"], p["oc"], p["oc1"], O.DT_OF[p["dst"]], O.S32, O.S32,
+                             nscale0=p["oc"], nscale1=p["oc1"])
+        self.dst = np.zeros((self.n, p["h"], p["w"], p["oc1"]), dtype=O.NP_OF[O.DT_OF[p["dst"]]])
+        self.scrub = np.zeros(max(1, self.cores) * (2 << 20), np.uint8)
+        self.kind = ("AVX-512-VNNI intrinsics replay of the reference's emitted instruction sequence + OpenMP, bit-identical to the "
+                     "reference generators run through oracle/_ref" if self.fast else "scalar C oracle (host lacks AVX-512 VNNI)")
+
+    def call(self):
+        p = self.p
+        self.fn(self.d, self.src, p["w0b"], p["b0"], p["s0"], p["w1b"], p["b1"], p["s1"], out=self.dst)
+
+    def warm(self, seconds, min_calls):
+        t0, k = time.time(), 0
+        while k < min_calls or time.time() - t0 < seconds:
+            self.call()
+            k += 1
+        return k
+
+    def timed(self, steps, cold=False):
+        """seconds per step (mean over `steps`), each step timed on its own"""
+        tot = 0.0
+        for _ in range(steps):
+            if cold:
+                self.scrub += 1  # evicts what the previous iteration left in the caches
+            t = time.perf_counter()
+            self.call()
+            tot += time.perf_counter() - t
+        return tot / steps
+
+    def budget_steps(self, seconds, lo=3):
+        t = time.perf_counter()
+        self.call()
+        one = time.perf_counter() - t
+        return max(lo, int(seconds / max(one, 1e-6)))
 
 
 def use_all_host_threads():
@@ -179,43 +220,33 @@ def use_all_host_threads():
     return n
 
 
+def shared_config(wl, n, world):
+    """`config` is the same object in both arms (the driver compares them)."""
+    return {"workload": WORKLOADS[wl][7], "images_per_gpu": n, "parallelism": f"batch-sharded x{world}, no collective"}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path on the host cores."""
     if rank != 0:
         return
     use_all_host_threads()
     p = conv_params(args.workload)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    fast = O.replay_supported()
-    n = p["n"] if fast else min(p["n"], 2)
-    fn = O.replay_conv if fast else O.conv
-    src = synth.src_u8(1, (n, p["h"], p["w"], p["ic"]))
-    d = O.make_desc(n, p["h"], p["w"], p["ic"], p["oc"], p["oc1"], O.DT_OF[p["dst"]], O.S32, O.S32, nscale0=p["oc"], nscale1=p["oc1"])
-    call = lambda: fn(d, src, p["w0b"], p["b0"], p["s0"], p["w1b"], p["b1"], p["s1"])  # noqa: E731
-    t = time.time()
-    call()
-    one = time.time() - t
-    steps = args.steps
-    if one * (args.steps + args.warmup) > 150.0:  # keep the whole run within a few minutes
-        steps = max(1, int(150.0 / one) - args.warmup)
-    for _ in range(args.warmup):
-        call()
-    t0 = time.time()
-    for _ in range(steps):
-        call()
-    dt = (time.time() - t0) / steps
+    arm = CpuArm(p)
+    n = arm.n
+    steps = min(args.steps, arm.budget_steps(120.0))  # keep the whole run within a few minutes
+    arm.warm(2.0, args.warmup)                         # by time: clocks, page tables, OpenMP team
+    dt = arm.timed(steps)
+    dt_cold = arm.timed(max(3, min(steps, 20)), cold=True)
     tops = n * ops_per_image(p) / dt / 1e12
-    cores = int(O.lib().dfr_num_threads()) if fast else 1
     line = {
         "impl": "reference", "metric": "fused conv3x3+1x1 int8 TOPS", "value": tops, "unit": "TOPS", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic", "images_per_s": n / dt,
-        "config": {"workload": WORKLOADS[args.workload][7], "images_per_step": n},
-        "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": cores,
-                         "kind": "port", "sample": f"{n} images per step x {steps} steps; "
-                         + ("AVX-512-VNNI intrinsics replay of the reference's emitted instruction sequence + OpenMP" if fast else "scalar C oracle (host lacks AVX-512 VNNI)")
-                         + "; the reference binary itself needs Xbyak and cannot be built offline"},
+        "config": shared_config(args.workload, p["n"], args.gpus),
+        "cpu_baseline": {"value": tops, "unit": "TOPS", "cores": arm.cores, "kind": "port",
+                         "sample": f"{n} images per step x {steps} steps after a 2 s warm-up, destination pre-allocated; {arm.kind}",
+                         "cold_cache_value": n * ops_per_image(p) / dt_cold / 1e12,
+                         "cold_cache_protocol": "2 MB per thread scrubbed between iterations (reference test/test_utils.cc:23-49)"},
         "e2e": {"value": tops, "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -223,6 +254,55 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------- GPU arm
+def shape_roofline(p, peaks, tops):
+    """Per-shape ceiling = min(tensor peak, arithmetic intensity x HBM bandwidth): shapes whose
+    intensity is below the ridge are reported against the HBM roofline in GB/s."""
+    ts_out = 4 if p["dst"] in ("f32", "s32") else 1
+    bytes_img = p["h"] * p["w"] * (p["ic"] + p["oc1"] * ts_out)
+    ai = ops_per_image(p) / bytes_img
+    tensor_peak = 2.0 * peaks["bf16_tflops"]
+    hbm_ceiling_tops = ai * peaks["hbm_gbs"] / 1e3
+    if hbm_ceiling_tops < tensor_peak:
+        gbs = tops * 1e3 / ai
+        return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                "ops_per_byte": ai, "ceiling_tops": hbm_ceiling_tops}
+    return {"bound": "tensor", "achieved": tops, "peak": tensor_peak, "unit": "TOPS", "frac": tops / tensor_peak,
+            "ops_per_byte": ai, "ceiling_tops": tensor_peak}
+
+
+def time_shape(df, st, wl, steps, peaks, rank=0):
+    """One more conv shape, device-resident, rotating buffers (> 2x L2 when the batch allows), CUDA-graph replay."""
+    p = conv_params(wl)
+    n, h, w, ic, oc, oc1, dst = p["n"], p["h"], p["w"], p["ic"], p["oc"], p["oc1"], p["dst"]
+    ts_out = 4 if dst in ("f32", "s32") else 1
+    src_bytes, dst_bytes = n * h * w * ic, n * h * w * oc1 * ts_out
+    op = df.Conv(n, h, w, ic, oc, oc1, df.DT_OF[dst], p["w0b"], p["w1b"], p["b0"], p["b1"], p["s0"], p["s1"], df.S32, df.S32)
+    n_sets = max(2, min(64, -(-2 * L2_BYTES // (src_bytes + dst_bytes))))
+    base = synth.src_u8(1 + 100 * rank, (n, h, w, ic))
+    sets = [(df.DeviceBuffer.from_numpy(base), df.DeviceBuffer(dst_bytes)) for _ in range(n_sets)]
+    for i in range(3):
+        op.run(*sets[i % n_sets], stream=st.ptr)
+    with df.Graph(st) as g:
+        for i in range(steps):
+            op.run(*sets[i % n_sets], stream=st.ptr)
+    g.launch()
+    st.sync()
+    e0, e1 = df.Event(), df.Event()
+    e0.record(st.ptr)
+    g.launch()
+    e1.record(st.ptr)
+    st.sync()
+    us = e0.elapsed_ms(e1) / steps * 1e3
+    tops = n * ops_per_image(p) / us / 1e6
+    info = op.info()
+    out = {"workload": WORKLOADS[wl][7], "us_per_launch": us, "tops": tops, "images_per_s": n / us * 1e6, "steps": steps,
+           "footprint_mib": n_sets * (src_bytes + dst_bytes) >> 20, "weights_resident": [info.w0_resident, info.w1_resident],
+           "roofline": shape_roofline(p, peaks, tops)}
+    del g, e0, e1
+    op.close()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import dfb200 as df
     from dfb200 import hostapi as H
@@ -309,6 +389,55 @@ def run_ours(args, rank, world, local_rank):
     c_ms = barrier_and_max(dist, ce0.elapsed_ms(ce1) / c_steps)
     concat_gbs = c_bytes / (c_ms * 1e-3) / 1e9
 
+    # ---- concat+ReLU at a footprint far beyond L2 (N = 1024: 205 MB per launch): the bandwidth the kernel
+    #      sustains once a launch is longer than one DRAM round trip
+    big = None
+    if not args.quick:
+        bn = 1024
+        b_bytes = 2 * bn * chh * cww * sum(cics)
+        b_in = [df.DeviceBuffer(bn * chh * cww * c) for c in cics]
+        for b in b_in:
+            b.fill(7)
+        b_out = df.DeviceBuffer(b_bytes // 2)
+        bcall = df.ConcatCall(df.U8, True, [b.ptr for b in b_in], list(cics), b_out.ptr, bn * chh * cww, stream=st.ptr)
+        for _ in range(3):
+            bcall()
+        st.sync()
+        be0, be1 = df.Event(), df.Event()
+        be0.record(st.ptr)
+        for _ in range(10):
+            bcall()
+        be1.record(st.ptr)
+        st.sync()
+        b_ms = be0.elapsed_ms(be1) / 10
+        big = {"workload": "concat+ReLU u8, 28x28, C=64/128/32/32, batch 1024", "bytes_per_launch": b_bytes, "us_per_launch": b_ms * 1e3,
+               "value": b_bytes / (b_ms * 1e-3) / 1e9, "unit": "GB/s", "frac_of_hbm": b_bytes / (b_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        del b_in, b_out
+
+    # ---- the headline shape sustained for >= 1 s (clocks settle under load), against 2 x the SUSTAINED bf16 figure
+    sustained = None
+    if not args.quick and graph is not None:
+        reps = max(1, int(1000.0 / max(ms_total, 1e-3)) + 1)
+        s0, s1 = df.Event(), df.Event()
+        t_s0 = time.time()
+        s0.record(st.ptr)
+        for _ in range(reps):
+            graph.launch()
+        s1.record(st.ptr)
+        st.sync()
+        t_s1 = time.time()
+        s_ms = s0.elapsed_ms(s1) / (reps * args.steps)
+        s_tops = n * ops_per_image(p) / (s_ms * 1e-3) / 1e12
+        peak_s = 2.0 * (peaks["bf16_sustained"] or peaks["bf16_tflops"])
+        sustained = {"seconds": s0.elapsed_ms(s1) / 1e3, "launches": reps * args.steps, "us_per_launch": s_ms * 1e3, "tops": s_tops,
+                     "peak": peak_s, "frac": s_tops / peak_s, "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json",
+                     "clocks": sampler.summary(t_s0, t_s1)}
+
+    # ---- the other BASELINE conv shapes, each against its own roofline
+    others = None
+    if not args.quick and world == 1:
+        others = {wl: time_shape(df, st, wl, 50 if wl != "cfg1" else 200, peaks, rank) for wl in ("cfg1", "cfg1x64", "cfg4", "cfg4s32", "cfg4f32")}
+
     # ---- end-to-end leg: the reference's API with host buffers (H2D + kernel + D2H per step)
     hsrc = H.Memory((n, ic, h, w), "nhwc", "u8")
     hsrc.set(base)
@@ -345,29 +474,45 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu:
         use_all_host_threads()
-        ips, runs, imgs, kind, cores = cpu_port_time(p, budget_s=args.cpu_seconds)
-        cpu = {"value": ips * ops_per_image(p) / 1e12, "unit": "TOPS", "images_per_s": ips, "cores": cores, "kind": "port",
-               "sample": f"{runs} passes over {imgs} images of the same workload ({kind}); the reference binary needs Xbyak and cannot be built offline"}
+        arm = CpuArm(p)
+        arm.warm(2.0, 3)
+        steps_cpu = arm.budget_steps(args.cpu_seconds)
+        dt = arm.timed(steps_cpu)
+        dt_cold = arm.timed(max(3, min(steps_cpu, 20)), cold=True)
+        cpu = {"value": arm.n * ops_per_image(p) / dt / 1e12, "unit": "TOPS", "images_per_s": arm.n / dt, "cores": arm.cores, "kind": "port",
+               "sample": f"{steps_cpu} passes over {arm.n} images of the same workload after a 2 s warm-up, destination pre-allocated ({arm.kind})",
+               "cold_cache_value": arm.n * ops_per_image(p) / dt_cold / 1e12,
+               "cold_cache_protocol": "2 MB per thread scrubbed between iterations (reference test/test_utils.cc:23-49)"}
     tensor_peak = 2.0 * peaks["bf16_tflops"]
+    consts = ncu_constants()
+    probe = (consts.get("i8_mma_probe") or {}).get("tops")
     line = {
         "metric": "fused conv3x3+1x1 int8 TOPS", "value": tops, "unit": "TOPS", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "images_per_s": total_images / (ms_step * 1e-3),
-        "config": {"workload": WORKLOADS[args.workload][7], "images_per_gpu": n, "parallelism": f"batch-sharded x{world}, no collective",
-                   "cache": f"rotating {n_sets} src/dst buffer sets ({n_sets * (src_bytes + dst_bytes) >> 20} MiB > 2x L2) so no step finds its data in L2",
-                   "launch": "plain loop of df_conv_run calls" if args.no_graph else f"{args.steps} steps captured in one CUDA graph, replayed once inside the timed region",
-                   "tiles": info.tiles_per_launch, "grid": info.grid, "smem_bytes": info.smem_bytes,
-                   "weights_resident": [info.w0_resident, info.w1_resident], "mma_row_efficiency": round(info.mma_efficiency, 4)},
+        "config": shared_config(args.workload, n, world),
+        "run": {"cache": f"rotating {n_sets} src/dst buffer sets ({n_sets * (src_bytes + dst_bytes) >> 20} MiB > 2x L2) so no step finds its data in L2",
+                "launch": "plain loop of df_conv_run calls" if args.no_graph else f"{args.steps} steps captured in one CUDA graph, replayed once inside the timed region",
+                "tiles": info.tiles_per_launch, "grid": info.grid, "smem_bytes": info.smem_bytes,
+                "weights_resident": [info.w0_resident, info.w1_resident], "mma_row_efficiency": round(info.mma_efficiency, 4)},
         "roofline": {"bound": "tensor", "achieved": kernel_tops_this_rank, "peak": tensor_peak, "unit": "TOPS",
-                     "frac": kernel_tops_this_rank / tensor_peak, "traffic": NCU_TRAFFIC.get(args.workload),
+                     "frac": kernel_tops_this_rank / tensor_peak,
+                     "traffic": (consts.get("conv_" + args.workload) or {}).get("dram_bytes_per_launch"),
+                     "traffic_source": (consts.get("conv_" + args.workload) or {}).get("source"),
                      "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({peaks['which']}); int8 dense rate = 2 x bf16",
-                     "frac_of_i8_mma_probe": kernel_tops_this_rank / 4335.0,
-                     "i8_mma_probe_tops": 4335.0, "kernel": "conv_pair_kernel" if info.w0_resident == 2 else "conv_fused_kernel", "ops_per_launch": n * ops_per_image(p)},
+                     "frac_of_i8_mma_probe": kernel_tops_this_rank / probe if probe else None,
+                     "i8_mma_probe_tops": probe, "i8_mma_probe_source": (consts.get("i8_mma_probe") or {}).get("source"),
+                     "kernel": "conv_pair_kernel" if info.w0_resident == 2 else "conv_fused_kernel", "ops_per_launch": n * ops_per_image(p),
+                     "sustained": sustained},
         "concat": {"workload": "concat+ReLU u8, 28x28, C=64/128/32/32, batch 32 (BASELINE configs[1])", "value": concat_gbs,
                    "unit": "GB/s", "us_per_launch": c_ms * 1e3, "bytes_per_launch": c_bytes,
                    "roofline": {"bound": "hbm", "achieved": concat_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                "frac": concat_gbs / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC["concat_cfg2"]},
-                   "cache": f"rotating {c_sets} buffer sets ({c_sets * c_bytes >> 20} MiB > 2x L2)"},
+                                "frac": concat_gbs / peaks["hbm_gbs"],
+                                "traffic": (consts.get("concat_cfg2") or {}).get("dram_bytes_per_launch"),
+                                "traffic_source": (consts.get("concat_cfg2") or {}).get("source")},
+                   "cache": f"rotating {c_sets} buffer sets ({c_sets * c_bytes >> 20} MiB > 2x L2)",
+                   "large_footprint": big},
+        "other_shapes": others,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_tops, "unit": "TOPS", "images_per_s": total_images / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": src_bytes, "d2h_bytes_per_step": dst_bytes, "steps": e2e_steps,
@@ -388,6 +533,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time a plain loop of launches instead of a CUDA graph replay")
+    ap.add_argument("--quick", action="store_true", help="headline legs only (skip the other shapes, the sustained run and the large concat)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -144,7 +144,8 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned blocks, cudaStream_t s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = getenv("DF_NO_PDL") ? 0 : 1;
+  static const bool pdl = getenv("DF_NO_PDL") == nullptr;  // read once per process, not per launch
+  cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 

@@ -590,6 +590,12 @@ extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, vo
   if (n == 0) return 0;
   if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
     return df::fail(DF_E_INVALID, "conv run: src/dst must be 16-byte aligned");
+  {  // the handle's weights, constants and tensor maps live on the device it was created on
+    int dev = -1;
+    DF_CUDA(cudaGetDevice(&dev));
+    if (dev != op->device)
+      return df::fail(DF_E_INVALID, "conv run: handle was created on device %d, current device is %d", op->device, dev);
+  }
   Params p = op->pair ? op->pair_prm : op->prm;
   if ((long)n * p.Hp * p.Wp + 4L * p.Wp + kTileM >= (1L << 31))
     return df::fail(DF_E_UNSUPPORTED, "conv run: batch too large for 32-bit position index");

@@ -106,7 +106,10 @@ int df_conv_create(const df_conv_desc *desc, const int8_t *wei_OIhw4i16o4i,
                    const int8_t *wei1x1_OIhw4i16o4i, const void *bia0, const void *bia1,
                    const float *scale0, const float *scale1, df_conv **out);
 /* One forward pass over `n` (<= created n) images; src NHWC u8, dst NHWC dst_dt, both device
- * pointers, 16-byte aligned.  Asynchronous on `stream`. */
+ * pointers, 16-byte aligned.  Asynchronous on `stream`.  The current device must be the one the
+ * handle was created on (DF_E_INVALID otherwise).  A handle caches tensor maps per (pointer, batch)
+ * and is NOT thread-safe: use one handle per host thread (the reference has the same rule for one
+ * op, src/op_conv.cc:159-160). */
 int df_conv_run(df_conv *op, const uint8_t *src_dev, void *dst_dev, int n, void *stream);
 int df_conv_query(const df_conv *op, df_conv_info *info);
 int df_conv_destroy(df_conv *op);

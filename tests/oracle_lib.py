@@ -58,10 +58,12 @@ def out_hw(d):
     return (l.dfo_conv_output_size(d.ih, d.kh, d.sh, d.ph), l.dfo_conv_output_size(d.iw, d.kw, d.sw, d.pw))
 
 
-def _conv(fn, d, src, wei, bia0, scale0, wei1, bia1, scale1):
+def _conv(fn, d, src, wei, bia0, scale0, wei1, bia1, scale1, out=None):
     oh, ow = out_hw(d)
     oc_out = d.oc1 if d.oc1 else d.oc
-    dst = np.zeros((d.n, oh, ow, oc_out), dtype=NP_OF[d.dst_dt])
+    # `out`: a caller-owned destination (timing loops must not pay for a fresh allocation + page faults per call)
+    dst = out if out is not None else np.zeros((d.n, oh, ow, oc_out), dtype=NP_OF[d.dst_dt])
+    assert dst.shape == (d.n, oh, ow, oc_out) and dst.dtype == NP_OF[d.dst_dt] and dst.flags.c_contiguous
     scale0 = np.ascontiguousarray(scale0, dtype=np.float32)
     scale1 = None if scale1 is None else np.ascontiguousarray(scale1, dtype=np.float32)
     rc = fn(C.byref(d), _p(src), _p(wei), _p(bia0), _p(scale0), _p(wei1), _p(bia1), _p(scale1), _p(dst))
@@ -70,12 +72,12 @@ def _conv(fn, d, src, wei, bia0, scale0, wei1, bia1, scale1):
     return dst
 
 
-def conv(d, src, wei, bia0, scale0, wei1=None, bia1=None, scale1=None):
-    return _conv(lib().dfo_conv, d, src, wei, bia0, scale0, wei1, bia1, scale1)
+def conv(d, src, wei, bia0, scale0, wei1=None, bia1=None, scale1=None, out=None):
+    return _conv(lib().dfo_conv, d, src, wei, bia0, scale0, wei1, bia1, scale1, out)
 
 
-def replay_conv(d, src, wei, bia0, scale0, wei1=None, bia1=None, scale1=None):
-    return _conv(lib().dfr_conv, d, src, wei, bia0, scale0, wei1, bia1, scale1)
+def replay_conv(d, src, wei, bia0, scale0, wei1=None, bia1=None, scale1=None, out=None):
+    return _conv(lib().dfr_conv, d, src, wei, bia0, scale0, wei1, bia1, scale1, out)
 
 
 def conv_intermediate(d, src, wei, bia0, scale0):
@@ -88,12 +90,12 @@ def conv_intermediate(d, src, wei, bia0, scale0):
     return mid
 
 
-def _concat(fn, dt, relu, srcs):
+def _concat(fn, dt, relu, srcs, out=None):
     n = len(srcs)
     ptrs = (C.c_void_p * n)(*[s.ctypes.data for s in srcs])
     ic = (C.c_int * n)(*[s.shape[-1] for s in srcs])
     npix = int(np.prod(srcs[0].shape[:-1]))
-    dst = np.zeros(srcs[0].shape[:-1] + (sum(s.shape[-1] for s in srcs),), dtype=srcs[0].dtype)
+    dst = out if out is not None else np.zeros(srcs[0].shape[:-1] + (sum(s.shape[-1] for s in srcs),), dtype=srcs[0].dtype)
     rc = fn(dt, int(relu), n, ptrs, ic, _p(dst), C.c_long(npix))
     if rc:
         raise RuntimeError(f"oracle concat rejected: {rc}")
@@ -104,8 +106,8 @@ def concat(dt, relu, srcs):
     return _concat(lib().dfo_concat, dt, relu, srcs)
 
 
-def replay_concat(dt, relu, srcs):
-    return _concat(lib().dfr_concat, dt, relu, srcs)
+def replay_concat(dt, relu, srcs, out=None):
+    return _concat(lib().dfr_concat, dt, relu, srcs, out)
 
 
 def replay_supported():
