@@ -1016,11 +1016,16 @@ __device__ __forceinline__ void epilogue_static(const Params& p, const DstMaps&,
   };
 
   // ---- conv1 chunk j of the current tile (c = chunk counter of this CTA): this warp's 32 rows x 32 channels
+  // A barrier test costs ~150 cycles even when the phase is complete (B300_MICROARCH.md: test_wait 149), and in
+  // this lock-step stream nothing else runs meanwhile.  So every unit tests the NEXT unit's accumulator barrier
+  // before its own arithmetic (`pre`, consumed a unit later): in steady state the test's latency then sits
+  // under ~50 arithmetic instructions and the unit starts without waiting.
+  uint32_t pre = 0;  // result of the early test of chunk c's barrier (all lanes agree)
   auto unit_c = [&](auto j_c, uint32_t c) {
     constexpr int j = decltype(j_c)::value;  // compile-time chunk index: constant offsets everywhere
     const uint32_t cb = c & 1;
     tr.ev(36);
-    mbar_wait_warp(bar_acc1_full + 8 * cb, (c >> 1) & 1);
+    if (!__all_sync(0xffffffffu, pre != 0)) mbar_wait_warp(bar_acc1_full + 8 * cb, (c >> 1) & 1);
     tc_fence_after_sync();
     tr.ev(32);
     uint32_t acc[2][16];
@@ -1042,8 +1047,10 @@ __device__ __forceinline__ void epilogue_static(const Params& p, const DstMaps&,
     tc_fence_before_sync();
     if (lane == 0) arrive(a_acc1_empty + 8 * cb);  // accumulator is in registers: the tensor pipe may overwrite it
     tr.ev(39);
+    pre = mbar_test_wait(bar_acc1_full + 8 * (cb ^ 1), ((c + 1) >> 1) & 1) ? 1u : 0u;  // chunk c + 1, used by the next unit
     // Padding rows are computed like any other and only their store is predicated off (a branch around a
     // row costs more than the wasted arithmetic: 6..8 % of the rows for the BASELINE shapes).
+    if (!dbg_flag(p, 16))
 #pragma unroll
     for (int ri = 0; ri < 4; ++ri) {
       uint32_t v[8], w[ts == 1 ? 2 : 8];
@@ -1051,20 +1058,32 @@ __device__ __forceinline__ void epilogue_static(const Params& p, const DstMaps&,
       for (int i = 0; i < 8; ++i) v[i] = acc[ri >> 1][4 * (i / 2) + 2 * (ri & 1) + (i & 1)];
       finish_conv1<kDst, false, false, 8, true>(v, c4, s4, nullptr, k_add, true, relu1, w);
       uint8_t* out = rptr[ri] + j * (128 * ts);
-      if constexpr (ts == 1) stg64_if(out, w, (rvalid >> ri) & 1u);
-      else stg256_if(out, w, (rvalid >> ri) & 1u);
+      if constexpr (ts == 1) stg64_if(out, w, ((rvalid >> ri) & 1u) && !dbg_flag(p, 4));
+      else stg256_if(out, w, ((rvalid >> ri) & 1u) && !dbg_flag(p, 4));
     }
     tr.ev(33);
   };
 
-  // ---- the unit stream:  E0(0) | C_0(t) .. C_{n-2}(t)  E0(t+1)  C_{n-1}(t) | ...
+  // ---- the unit stream:  E0(0) | C_0(t) .. E0(t+1) C_{e0_pos}(t) .. C_{n-1}(t) | ...
+#ifndef DF_E0_POS
+#define DF_E0_POS (G::n_chunks / 2)  // measured best of the four positions for cfg3 (profiles/r02_variants_e0_position.log)
+#endif
+  // With ONE intermediate tile E0(t+1) has to wait until GEMM2 has read tile t for the last time, and the last
+  // chunk is only issued once C_{n-3}(t) has released an accumulator: anything earlier than n - 1 deadlocks.
+  const int e0_pos = p.NM >= 2 ? ((DF_E0_POS) < G::n_chunks ? (DF_E0_POS) : G::n_chunks - 1) : G::n_chunks - 1;
+
+  // (Tried and dropped: moving the block in four 16 x 16 pieces through a ring of register sets with the loads
+  // running two pieces ahead ACROSS units -- parity-green but 6 % slower on cfg3 and 19 % on cfg1,
+  // profiles/r02_variants_piece_pipeline.log: the extra loads / waits cost more issue slots than the hidden latency
+  // returned.  Likewise two groups of 8 warps on alternate accumulators with per-warp TMA stores,
+  // profiles/r02_variants_seed_epilogue_design.log.)
   uint32_t c = 0;
   if (n_local > 0) unit_e0(0);
   for (int it = 0; it < n_local; ++it) {
     tile_rows(it);
     static_for<G::n_chunks>([&](auto j_c) {
       constexpr int j = decltype(j_c)::value;
-      if (j == G::n_chunks - 1 && it + 1 < n_local) unit_e0(it + 1);
+      if (j == e0_pos && it + 1 < n_local) unit_e0(it + 1);
       unit_c(j_c, c);
       ++c;
     });
