@@ -28,6 +28,8 @@ ABI_SYMBOLS = [
     "df_stream_sync", "df_stream_destroy", "df_event_create", "df_event_record", "df_stream_wait_event", "df_event_elapsed_ms",
     "df_event_destroy", "df_concat_check", "df_concat_run", "df_conv_create", "df_conv_run", "df_conv_query",
     "df_conv_destroy", "df_conv_debug_trace", "df_graph_begin", "df_graph_end", "df_graph_launch", "df_graph_destroy",
+    "df_wei_blocked_offset", "df_repack_oihw_to_blocked", "df_repack_blocked_to_oihw", "df_repack_goihw_to_blocked",
+    "df_repack_blocked_to_goihw", "df_nchw_to_nhwc", "df_nhwc_to_nchw",
 ]
 
 

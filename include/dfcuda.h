@@ -117,6 +117,18 @@ int df_conv_destroy(df_conv *op);
  * into dev_buf[grid * 4 * cap] (u64 words: tag << 48 | clock); NULL switches it off. */
 int df_conv_debug_trace(df_conv *op, void *dev_buf, int cap);
 
+/* ---- format tooling (host memory, no device work): the reference consumes OIhw4i16o4i /
+ *      gOIhw4i16o4i weights (include/deepfusion.h:53-61, layout = jit_conv_kernel.cc:333-338) and
+ *      nhwc activations but ships no converter (its tests fill blocked weights with random bytes,
+ *      test/test_conv_relu_pooling.cc:251-254).  oc / ic are PER GROUP and multiples of 16. -------- */
+size_t df_wei_blocked_offset(int o, int i, int h, int w, int ic, int kh, int kw);
+int df_repack_oihw_to_blocked(const int8_t *oihw, int8_t *blocked, int oc, int ic, int kh, int kw);
+int df_repack_blocked_to_oihw(const int8_t *blocked, int8_t *oihw, int oc, int ic, int kh, int kw);
+int df_repack_goihw_to_blocked(const int8_t *goihw, int8_t *blocked, int groups, int oc, int ic, int kh, int kw);
+int df_repack_blocked_to_goihw(const int8_t *blocked, int8_t *goihw, int groups, int oc, int ic, int kh, int kw);
+int df_nchw_to_nhwc(const void *nchw, void *nhwc, int n, int c, int h, int w, int elem_bytes);
+int df_nhwc_to_nchw(const void *nhwc, void *nchw, int n, int c, int h, int w, int elem_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,3 +104,40 @@ def test_compute_entry_points_fail_loudly_without_a_device():
     rc = _create()
     assert rc > 0, "df_conv_create must surface the CUDA error when no device exists (no CPU fallback)"
     assert df.lib().df_last_error() != b""
+
+
+def test_format_tooling_matches_the_reference_layout_formula():
+    """df_repack_* / df_nchw_to_nhwc (include/dfcuda.h): OIhw4i16o4i per jit_conv_kernel.cc:333-338,
+    gOIhw4i16o4i = one such block per group; checked against the oracle's offset function, the numpy tools and a
+    round trip."""
+    import ctypes as C
+    import numpy as np
+    import dfb200 as df
+    from dfb200 import layout
+    import oracle_lib as O
+    L = df.lib()
+    L.df_wei_blocked_offset.restype = C.c_size_t
+    rng = np.random.default_rng(7)
+    for (g, oc, ic, kh, kw) in [(1, 32, 48, 3, 3), (1, 64, 16, 1, 1), (3, 16, 32, 3, 3)]:
+        w = rng.integers(-128, 128, size=(g, oc, ic, kh, kw), dtype=np.int8)
+        blocked = np.zeros(w.size, np.int8)
+        assert L.df_repack_goihw_to_blocked(w.ctypes.data_as(C.c_void_p), blocked.ctypes.data_as(C.c_void_p), g, oc, ic, kh, kw) == 0
+        for gi in range(g):
+            want = layout.oihw_to_blocked(w[gi])
+            assert np.array_equal(blocked.reshape(g, -1)[gi], want)
+        for (o, i, h, x) in [(0, 0, 0, 0), (oc - 1, ic - 1, kh - 1, kw - 1), (17 % oc, 5, 0, kw - 1)]:
+            assert L.df_wei_blocked_offset(o, i, h, x, ic, kh, kw) == O.lib().dfo_wei_off(o, i, h, x, ic, kh, kw)
+        back = np.zeros_like(w)
+        assert L.df_repack_blocked_to_goihw(blocked.ctypes.data_as(C.c_void_p), back.ctypes.data_as(C.c_void_p), g, oc, ic, kh, kw) == 0
+        assert np.array_equal(back, w)
+    assert L.df_repack_oihw_to_blocked(None, None, 16, 16, 1, 1) != 0
+    w = np.zeros((20, 16, 1, 1), np.int8)
+    assert L.df_repack_oihw_to_blocked(w.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p), 20, 16, 1, 1) != 0  # oc % 16
+    for dt in (np.uint8, np.float32):
+        x = rng.integers(0, 200, size=(2, 5, 3, 4)).astype(dt)
+        y = np.zeros((2, 3, 4, 5), dt)
+        assert L.df_nchw_to_nhwc(x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), 2, 5, 3, 4, x.itemsize) == 0
+        assert np.array_equal(y, layout.nchw_to_nhwc(x))
+        z = np.zeros_like(x)
+        assert L.df_nhwc_to_nchw(y.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), 2, 5, 3, 4, x.itemsize) == 0
+        assert np.array_equal(z, x)
