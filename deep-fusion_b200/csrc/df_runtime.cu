@@ -31,6 +31,11 @@ int df_set_device(int device) {
   DF_CUDA(cudaSetDevice(device));
   return 0;
 }
+int df_get_device(int* device) {
+  if (!device) return df::fail(DF_E_INVALID, "df_get_device: null");
+  DF_CUDA(cudaGetDevice(device));
+  return 0;
+}
 int df_device_sm_count(int* sms) {
   int dev;
   DF_CUDA(cudaGetDevice(&dev));

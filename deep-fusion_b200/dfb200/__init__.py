@@ -23,7 +23,7 @@ NP_OF = {F32: np.float32, S32: np.int32, S8: np.int8, U8: np.uint8}
 
 # every symbol include/dfcuda.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "df_last_error", "df_version", "df_device_count", "df_set_device", "df_device_sm_count", "df_malloc",
+    "df_last_error", "df_version", "df_device_count", "df_set_device", "df_get_device", "df_device_sm_count", "df_malloc",
     "df_free", "df_memset", "df_host_register", "df_host_unregister", "df_h2d", "df_d2h", "df_stream_create",
     "df_stream_sync", "df_stream_destroy", "df_event_create", "df_event_record", "df_stream_wait_event", "df_event_elapsed_ms",
     "df_event_destroy", "df_concat_check", "df_concat_run", "df_conv_create", "df_conv_run", "df_conv_query",

@@ -49,6 +49,11 @@ def lib():
         l.dfh_conv_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int,
                                       C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int]
+        l.dfh_conv_sharded_create.restype = C.c_void_p
+        l.dfh_conv_sharded_create.argtypes = [C.POINTER(C.c_int), C.c_int] + l.dfh_conv_create.argtypes
+        for f in ("dfh_sharded_upload", "dfh_sharded_sync", "dfh_sharded_download"):
+            getattr(l, f).argtypes = [C.c_void_p]
+            getattr(l, f).restype = None
         l.dfh_op_submit_device.argtypes = [C.c_void_p, C.c_void_p]
         l.dfh_op_submit_device.restype = None
         l.dfh_op_launches.argtypes = [C.c_void_p]
@@ -141,3 +146,31 @@ def conv(src, wei, bia, stride, padding, dst, wei1x1=None, bia1x1=None, conv0_re
                               bia1x1.h if bia1x1 else None, dst.h, int(conv0_relu), s0.ctypes.data_as(fp), s0.size,
                               conv0_round_mode, int(conv1_relu), s1.ctypes.data_as(fp), s1.size, conv1_round_mode)
     return Op(h, (src, wei, bia, wei1x1, bia1x1, dst))
+
+
+class ShardedOp(Op):
+    """ext::conv_sharded: device-resident helpers for timing."""
+
+    def upload(self):
+        lib().dfh_sharded_upload(self.h)
+
+    def sync(self):
+        lib().dfh_sharded_sync(self.h)
+
+    def download(self):
+        lib().dfh_sharded_download(self.h)
+
+
+def conv_sharded(devices, src, wei, bia, stride, padding, dst, wei1x1=None, bia1x1=None, conv0_relu=False, conv0_scales=(1.0,),
+                 conv0_round_mode=NEAREST, conv1_relu=False, conv1_scales=(1.0,), conv1_round_mode=NEAREST) -> ShardedOp:
+    """deepfusion::ext::conv_sharded (include/deepfusion_ext.h): the batch split over `devices` in contiguous slabs."""
+    s0 = np.ascontiguousarray(conv0_scales, dtype=np.float32)
+    s1 = np.ascontiguousarray(conv1_scales, dtype=np.float32)
+    st = (C.c_int * 2)(*stride)
+    pd = (C.c_int * 2)(*padding)
+    dv = (C.c_int * len(devices))(*devices)
+    fp = C.POINTER(C.c_float)
+    h = lib().dfh_conv_sharded_create(dv, len(devices), src.h, wei.h, bia.h if bia else None, st, pd, wei1x1.h if wei1x1 else None,
+                                      bia1x1.h if bia1x1 else None, dst.h, int(conv0_relu), s0.ctypes.data_as(fp), s0.size,
+                                      conv0_round_mode, int(conv1_relu), s1.ctypes.data_as(fp), s1.size, conv1_round_mode)
+    return ShardedOp(h, (src, wei, bia, wei1x1, bia1x1, dst))

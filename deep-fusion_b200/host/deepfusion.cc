@@ -14,6 +14,7 @@
 #include <string.h>
 #include <sys/time.h>
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -278,12 +279,13 @@ public:
           std::array<int, 2> sz_stride, std::array<int, 2> sz_padding, std::unique_ptr<memory> &dst,
           const std::vector<float> &conv0_scales, const std::vector<float> &conv1_scales,
           const std::unique_ptr<memory> &wei1x1, const std::unique_ptr<memory> &bia1x1, bool conv0_relu,
-          bool conv1_relu, round_mode conv0_round_mode, round_mode conv1_round_mode)
+          bool conv1_relu, round_mode conv0_round_mode, round_mode conv1_round_mode, bool create_handle = true)
       : src_(src.get()), dst_(dst.get()) {
     memset(&desc_, 0, sizeof desc_);
     if (!init_conf(src, wei, bia, sz_stride, sz_padding, dst, conv0_scales, conv1_scales, wei1x1, bia1x1, conv0_relu,
                    conv1_relu, conv0_round_mode, conv1_round_mode))
       error_and_exit("Init Conv op failed!");
+    if (!create_handle) return;  // sharded_conv_op creates one handle per device
     // parameters are captured now (the reference keeps raw pointers and a dangling scales
     // pointer, defect D7); the activations stay borrowed
     int rc = df_conv_create(&desc_, static_cast<const int8_t *>(wei->data()),
@@ -461,10 +463,172 @@ private:
       for (void *st : streams) df_stream_destroy(st);
     }
   };
+protected:
   memory *src_, *dst_;
   df_conv_desc desc_;
+
+private:
   df_conv *handle_ = nullptr;
   resources *res_ = nullptr;
+};
+
+// ------------------------------------------------------------------------ conv, batch-sharded
+// The same operator over the GPUs of one box: every image is independent -- the reference itself
+// splits the work over n * oh rows with balance211 (src/op_conv.cc:155-156) -- so device g owns the contiguous
+// slab of ceil(N / G) images starting at g * ceil(N / G); NHWC makes that one byte range of src and dst.
+// Weights / biases / scales are replicated at creation, there is no data-path collective and no NCCL.  ONE host
+// thread drives every device: per device three streams (upload, kernel, download) and sub-slabs, so that the
+// PCIe directions and the kernels of all devices overlap; submit() returns when the last download has landed.
+class sharded_conv_op : public conv_op {
+public:
+  sharded_conv_op(const std::vector<int> &devices, const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei,
+                  const std::unique_ptr<memory> &bia, std::array<int, 2> sz_stride, std::array<int, 2> sz_padding,
+                  std::unique_ptr<memory> &dst, const std::vector<float> &conv0_scales, const std::vector<float> &conv1_scales,
+                  const std::unique_ptr<memory> &wei1x1, const std::unique_ptr<memory> &bia1x1, bool conv0_relu, bool conv1_relu,
+                  round_mode r0, round_mode r1)
+      : conv_op(src, wei, bia, sz_stride, sz_padding, dst, conv0_scales, conv1_scales, wei1x1, bia1x1, conv0_relu, conv1_relu,
+                r0, r1, /*create_handle=*/false) {
+    if (devices.empty()) error_and_exit("conv_sharded: no devices");
+    sh_ = new shards();
+    detail::adopt_resources(this, sh_);
+    int count = 0;
+    cuda_or_exit(df_get_device(&home_), "get device");
+    cuda_or_exit(df_device_count(&count), "device count");
+    for (int d : devices)
+      if (d < 0 || d >= count) error_and_exit("conv_sharded: device %d does not exist (%d devices)", d, count);
+    const int G = (int)devices.size(), n = desc_.n, per = (n + G - 1) / G;
+    detail::memory_state *ss = detail::state_of(*src_), *ds = detail::state_of(*dst_);
+    if (!ss->pinned && df_host_register(src_->data(), src_->buffer_size()) == 0) ss->pinned = true;
+    if (!ds->pinned && df_host_register(dst_->data(), dst_->buffer_size()) == 0) ds->pinned = true;
+    const size_t src_img = src_->buffer_size() / n, dst_img = dst_->buffer_size() / n;
+    for (int g = 0; g < G; ++g) {
+      shard s;
+      s.device = devices[g];
+      s.first = std::min(g * per, n);
+      s.count = std::max(0, std::min(per, n - s.first));
+      if (s.count > 0) {
+        cuda_or_exit(df_set_device(s.device), "set device");
+        df_conv_desc d = desc_;
+        d.n = s.count;
+        int rc = df_conv_create(&d, static_cast<const int8_t *>(wei->data()), wei1x1 ? static_cast<const int8_t *>(wei1x1->data()) : nullptr,
+                                bia ? bia->data() : nullptr, bia1x1 ? bia1x1->data() : nullptr, conv0_scales.data(),
+                                conv1_scales.data(), &s.handle);
+        if (rc == DF_E_UNSUPPORTED) error_and_exit("unsupported on B200 path: %s", df_last_error());
+        if (rc != 0) {
+          info("%s", df_last_error());
+          error_and_exit("Init Conv op failed!");
+        }
+        cuda_or_exit(df_malloc(s.count * src_img, &s.d_src), "device allocation");
+        cuda_or_exit(df_malloc(s.count * dst_img, &s.d_dst), "device allocation");
+        for (void *&st : s.streams) cuda_or_exit(df_stream_create(&st), "stream create");
+        for (void *&e : s.events) cuda_or_exit(df_event_create(&e), "event create");
+      }
+      sh_->v.push_back(s);
+    }
+    cuda_or_exit(df_set_device(home_), "set device");
+  }
+
+  // kernels only, on slabs already resident on the devices (ext::submit_device): asynchronous
+  void launch(void *) override {
+    for (shard &s : sh_->v) {
+      if (!s.count) continue;
+      cuda_or_exit(df_set_device(s.device), "set device");
+      cuda_or_exit(df_conv_run(s.handle, static_cast<const uint8_t *>(s.d_src), s.d_dst, s.count, s.streams[1]), "conv launch");
+    }
+    cuda_or_exit(df_set_device(home_), "set device");
+  }
+  int launches() const override {
+    int k = 0;
+    for (const shard &s : sh_->v) k += s.count > 0 ? (s.count >= 8 ? kSub : 1) : 0;
+    return k;
+  }
+  void sync_all() {
+    for (shard &s : sh_->v) {
+      if (!s.count) continue;
+      cuda_or_exit(df_set_device(s.device), "set device");
+      cuda_or_exit(df_stream_sync(s.streams[1]), "sync");
+      cuda_or_exit(df_stream_sync(s.streams[2]), "sync");
+    }
+    cuda_or_exit(df_set_device(home_), "set device");  // the caller's device, as at creation
+  }
+  void upload() {  // host src -> every device's slab (for device-resident timing)
+    const size_t src_img = src_->buffer_size() / desc_.n;
+    for (shard &s : sh_->v) {
+      if (!s.count) continue;
+      cuda_or_exit(df_set_device(s.device), "set device");
+      cuda_or_exit(df_h2d(s.d_src, static_cast<const uint8_t *>(src_->data()) + s.first * src_img, s.count * src_img, s.streams[1]), "H2D");
+    }
+    sync_all();
+  }
+  void download() {
+    const size_t dst_img = dst_->buffer_size() / desc_.n;
+    for (shard &s : sh_->v) {
+      if (!s.count) continue;
+      cuda_or_exit(df_set_device(s.device), "set device");
+      cuda_or_exit(df_d2h(static_cast<uint8_t *>(dst_->data()) + s.first * dst_img, s.d_dst, s.count * dst_img, s.streams[1]), "D2H");
+    }
+    sync_all();
+  }
+  int device_count_used() const {
+    int k = 0;
+    for (const shard &s : sh_->v) k += s.count > 0;
+    return k;
+  }
+
+protected:
+  void infer() override {
+    const int n = desc_.n;
+    const size_t src_img = src_->buffer_size() / n, dst_img = dst_->buffer_size() / n;
+    const uint8_t *h_src = static_cast<const uint8_t *>(src_->data());
+    uint8_t *h_dst = static_cast<uint8_t *>(dst_->data());
+    // sub-slab k of every device before sub-slab k + 1 of any: all devices start uploading at once
+    for (int k = 0; k < kSub; ++k)
+      for (shard &s : sh_->v) {
+        if (!s.count) continue;
+        const int subs = s.count >= 8 ? kSub : 1;
+        if (k >= subs) continue;
+        const int per = (s.count + subs - 1) / subs, first = k * per;
+        const int cnt = first + per <= s.count ? per : s.count - first;
+        if (cnt <= 0) continue;
+        cuda_or_exit(df_set_device(s.device), "set device");
+        uint8_t *d_src = static_cast<uint8_t *>(s.d_src) + first * src_img, *d_dst = static_cast<uint8_t *>(s.d_dst) + first * dst_img;
+        cuda_or_exit(df_h2d(d_src, h_src + (s.first + first) * src_img, cnt * src_img, s.streams[0]), "conv H2D");
+        cuda_or_exit(df_event_record(s.events[2 * k], s.streams[0]), "event record");
+        cuda_or_exit(df_stream_wait_event(s.streams[1], s.events[2 * k]), "stream wait");
+        cuda_or_exit(df_conv_run(s.handle, d_src, d_dst, cnt, s.streams[1]), "conv launch");
+        cuda_or_exit(df_event_record(s.events[2 * k + 1], s.streams[1]), "event record");
+        cuda_or_exit(df_stream_wait_event(s.streams[2], s.events[2 * k + 1]), "stream wait");
+        cuda_or_exit(df_d2h(h_dst + (s.first + first) * dst_img, d_dst, cnt * dst_img, s.streams[2]), "conv D2H");
+      }
+    sync_all();
+  }
+  const char *name() override { return "conv_sharded"; }
+
+private:
+  static constexpr int kSub = 4;
+  struct shard {
+    int device = 0, first = 0, count = 0;
+    df_conv *handle = nullptr;
+    void *d_src = nullptr, *d_dst = nullptr;
+    void *streams[3] = {nullptr, nullptr, nullptr};
+    void *events[2 * kSub] = {};
+  };
+  struct shards : detail::op_resources {
+    std::vector<shard> v;
+    ~shards() override {
+      for (shard &s : v) {
+        if (!s.count) continue;
+        df_set_device(s.device);
+        df_conv_destroy(s.handle);
+        df_free(s.d_src);
+        df_free(s.d_dst);
+        for (void *e : s.events) df_event_destroy(e);
+        for (void *st : s.streams) df_stream_destroy(st);
+      }
+    }
+  };
+  shards *sh_ = nullptr;
+  int home_ = 0;
 };
 
 }  // namespace
@@ -530,6 +694,31 @@ int launches_per_submit(op &o) {
 void pin(memory &m) {
   detail::memory_state *st = detail::state_of(m);
   if (!st->pinned && df_host_register(m.data(), m.buffer_size()) == 0) st->pinned = true;
+}
+std::unique_ptr<op> conv_sharded(const std::vector<int> &devices, const std::unique_ptr<memory> &src,
+                                 const std::unique_ptr<memory> &wei, const std::unique_ptr<memory> &bia,
+                                 std::array<int, 2> sz_stride, std::array<int, 2> sz_padding,
+                                 const std::unique_ptr<memory> &wei1x1, const std::unique_ptr<memory> &bia1x1,
+                                 std::unique_ptr<memory> &dst, bool conv0_relu, std::vector<float> conv0_scales,
+                                 round_mode conv0_round_mode, bool conv1_relu, std::vector<float> conv1_scales,
+                                 round_mode conv1_round_mode) {
+  return std::unique_ptr<op>(new sharded_conv_op(devices, src, wei, bia, sz_stride, sz_padding, dst, conv0_scales, conv1_scales,
+                                                 wei1x1, bia1x1, conv0_relu, conv1_relu, conv0_round_mode, conv1_round_mode));
+}
+void sharded_upload(op &o) {
+  sharded_conv_op *s = dynamic_cast<sharded_conv_op *>(&o);
+  if (!s) error_and_exit("sharded_upload: not a sharded op");
+  s->upload();
+}
+void sharded_download(op &o) {
+  sharded_conv_op *s = dynamic_cast<sharded_conv_op *>(&o);
+  if (!s) error_and_exit("sharded_download: not a sharded op");
+  s->download();
+}
+void sharded_sync(op &o) {
+  sharded_conv_op *s = dynamic_cast<sharded_conv_op *>(&o);
+  if (!s) error_and_exit("sharded_sync: not a sharded op");
+  s->sync_all();
 }
 void release(std::unique_ptr<op> &o) {
   if (o) detail::release_resources(o.get());

@@ -32,6 +32,15 @@ dfh_op *dfh_conv_create(dfh_memory *src, dfh_memory *wei, dfh_memory *bia, const
                         dfh_memory *wei1x1, dfh_memory *bia1x1, dfh_memory *dst, int conv0_relu,
                         const float *conv0_scales, int n_conv0_scales, int conv0_round_mode, int conv1_relu,
                         const float *conv1_scales, int n_conv1_scales, int conv1_round_mode);
+/* ext::conv_sharded(): the same operator split over `devices` by contiguous batch slabs (no collective) */
+dfh_op *dfh_conv_sharded_create(const int *devices, int n_devices, dfh_memory *src, dfh_memory *wei, dfh_memory *bia,
+                                const int stride[2], const int padding[2], dfh_memory *wei1x1, dfh_memory *bia1x1,
+                                dfh_memory *dst, int conv0_relu, const float *conv0_scales, int n_conv0_scales,
+                                int conv0_round_mode, int conv1_relu, const float *conv1_scales, int n_conv1_scales,
+                                int conv1_round_mode);
+void dfh_sharded_upload(dfh_op *op);   /* slabs -> devices (device-resident timing) */
+void dfh_sharded_sync(dfh_op *op);     /* wait for every device */
+void dfh_sharded_download(dfh_op *op); /* devices -> host destination, synchronous */
 void dfh_op_submit(dfh_op *op);                       /* op::submit(): H2D + kernel + D2H, synchronous */
 void dfh_op_submit_device(dfh_op *op, void *stream);  /* ext::submit_device(): kernel only, async */
 int dfh_op_launches(dfh_op *op);

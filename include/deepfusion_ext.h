@@ -22,6 +22,23 @@ void sync(void *stream = nullptr);
 int launches_per_submit(op &o);
 // Pin the host buffer of a memory (cudaHostRegister) so submit()'s copies run at full PCIe speed.
 void pin(memory &m);
+// The fused conv (or, with wei1x1 == nullptr, the conv-only operator) over the GPUs `devices` of one box:
+// contiguous batch slabs of ceil(N / G) images, parameters replicated, no data-path collective (the reference
+// splits the same way over threads, src/op_conv.cc:155-156).  Same arguments and checks as conv(); submit()
+// uploads, computes and downloads every slab and returns when the last byte has landed.  One host thread.
+std::unique_ptr<op> conv_sharded(const std::vector<int> &devices, const std::unique_ptr<memory> &src,
+                                 const std::unique_ptr<memory> &wei, const std::unique_ptr<memory> &bia,
+                                 std::array<int, 2> sz_stride, std::array<int, 2> sz_padding,
+                                 const std::unique_ptr<memory> &wei1x1, const std::unique_ptr<memory> &bia1x1,
+                                 std::unique_ptr<memory> &dst, bool conv0_relu = false,
+                                 std::vector<float> conv0_scales = {1.f}, round_mode conv0_round_mode = round_mode::nearest,
+                                 bool conv1_relu = false, std::vector<float> conv1_scales = {1.f},
+                                 round_mode conv1_round_mode = round_mode::nearest);
+// device-resident use of a sharded op (timing): upload the slabs once, submit_device() launches the kernels on
+// every device, sharded_sync() waits for all of them, sharded_download() brings the result back
+void sharded_upload(op &o);
+void sharded_sync(op &o);
+void sharded_download(op &o);
 // Destroys an op together with the device resources it owns.  Plain destruction through std::unique_ptr<op>
 // cannot do that: the reference's `op` (include/deepfusion.h:105-114, kept verbatim) has no virtual destructor,
 // so the resources of an op that is simply dropped are reclaimed only when its address is reused or at exit.

@@ -40,6 +40,7 @@ const char *df_version(void);
  *      residency of memory::data(), util/memory.cc:21-40, src/deepfusion.cc:76-80) ---------- */
 int df_device_count(int *count);
 int df_set_device(int device);
+int df_get_device(int *device);
 int df_device_sm_count(int *sms);
 int df_malloc(size_t bytes, void **dev_ptr);
 int df_free(void *dev_ptr);

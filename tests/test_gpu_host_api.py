@@ -123,3 +123,50 @@ def test_concat_feeds_conv_on_device(H):
     d = O.make_desc(n, h, w, 256, 128, 256, O.U8, O.S32, O.S32, nscale0=128, nscale1=256)
     want = O.conv(d, cat_ref, wb, b0, s0, w1b, b1, s1)
     assert np.array_equal(dst.array(), want)
+
+
+def _conv_memories(H, c, n=None):
+    n = n or c.n
+    src_a, w0, w1, b0, b1, s0, s1 = cases.ConvCase(c.name, n, c.h, c.w, c.ic, c.oc, c.oc1, c.dst, c.b0, c.b1, c.r0, c.r1,
+                                                   c.relu0, c.relu1, c.per_channel, c.k0, c.k1, c.data).tensors()
+    wb, w1b = c.blocked(w0, w1)
+    src = H.Memory((n, c.ic, c.h, c.w), "nhwc", "u8")
+    src.set(src_a)
+    wei = H.Memory((c.oc, c.ic, 3, 3), "OIhw4i16o4i", "s8")
+    wei.array().reshape(-1)[...] = wb
+    wei1 = H.Memory((c.oc1, c.oc, 1, 1), "OIhw4i16o4i", "s8")
+    wei1.array().reshape(-1)[...] = w1b
+    bia = H.Memory((c.oc,), "x", c.b0, nchw=False)
+    bia.set(b0)
+    bia1 = H.Memory((c.oc1,), "x", c.b1, nchw=False)
+    bia1.set(b1)
+    dst = H.Memory((n, c.oc1, c.h, c.w), "nhwc", c.dst)
+    return src, wei, bia, wei1, bia1, dst, s0, s1
+
+
+@pytest.mark.parametrize("n", [1, 3, 13, 64])
+@pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
+def test_sharded_equals_unsharded(H, n, n_dev):
+    """ext::conv_sharded (SURVEY §8e): contiguous batch slabs over the GPUs of one box, no collective.  The sharded
+    result must be bit-identical to the single-device op -- also when the batch is smaller than the device count
+    (idle devices) and when the slabs are ragged.  Devices beyond those present are skipped."""
+    import dfb200 as df
+    if df.device_count() < n_dev:
+        pytest.skip(f"needs {n_dev} devices")
+    c = {x.name: x for x in cases.FULL_CONV}["cfg3"]
+    src, wei, bia, wei1, bia1, dst, s0, s1 = _conv_memories(H, c, n)
+    H.conv(src, wei, bia, (1, 1), (1, 1), dst, wei1x1=wei1, bia1x1=bia1, conv0_scales=s0, conv1_scales=s1).submit()
+    want = dst.array().copy()
+    dst.array()[...] = 0
+    op = H.conv_sharded(list(range(n_dev)), src, wei, bia, (1, 1), (1, 1), dst, wei1x1=wei1, bia1x1=bia1, conv0_scales=s0,
+                        conv1_scales=s1)
+    op.submit()
+    assert np.array_equal(dst.array(), want)
+    # device-resident path: upload once, kernels only, download
+    dst.array()[...] = 0
+    op.upload()
+    op.submit_device()
+    op.sync()
+    op.download()
+    assert np.array_equal(dst.array(), want)
+    assert df.lib().df_get_device is not None
