@@ -70,7 +70,7 @@ struct df_conv {
   df_conv() : desc(), prm(), kernel{nullptr, nullptr}, pair(false), pair_kernel{nullptr, nullptr}, pair_prm(), pair_smem(0),
               tmW0h(), tmW1h(), geom_id(0), smem_bytes(0), device(0), sms(0), d_w0(nullptr),
               d_w1(nullptr), d_bias0(nullptr), d_scale0(nullptr), d_bias1(nullptr), d_scale1(nullptr), d_k1(nullptr),
-              tmW0(), tmW1(), a_maps(), d_maps(), a_next(0), d_next(0), trace(nullptr), trace_cap(0) {}
+              tmW0(), tmW1(), a_maps(), d_maps(), a_next(0), d_next(0), trace(nullptr), trace_cap(0), n_src(1), src_ic() {}
   df_conv_desc desc;
   Params prm;        // everything except n-dependent fields and dst
   KernelFn kernel;
@@ -90,9 +90,9 @@ struct df_conv {
   // activation / destination tensor maps depend on (pointer, batch): a small round-robin cache keeps
   // callers that cycle through a few buffers from re-encoding on every call
   struct SrcSlot {
-    const void* ptr;
+    const void* ptr[kMaxSrc];  // ptr[0] == nullptr: empty slot
     int n;
-    CUtensorMap map;
+    SrcMaps maps;
   };
   struct DstSlot {
     const void* ptr;
@@ -105,6 +105,8 @@ struct df_conv {
   int a_next, d_next;
   unsigned long long* trace;
   int trace_cap;
+  int n_src;            // inputs whose channel concatenation is the conv's source (1: plain conv)
+  int src_ic[kMaxSrc];  // their channel counts
 };
 
 namespace {
@@ -194,12 +196,31 @@ int encode_2d(CUtensorMap* tm, void* base, int row_bytes, long rows, int box_row
 
 }  // namespace
 
-extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const int8_t* wei1, const void* bia0,
-                              const void* bia1, const float* scale0, const float* scale1, df_conv** out) {
+// n_src == 0: plain conv.  n_src >= 1: the source is the channel concatenation of n_src tensors (fused concat)
+static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic, int concat_relu, const int8_t* wei,
+                            const int8_t* wei1, const void* bia0, const void* bia1, const float* scale0,
+                            const float* scale1, df_conv** out) {
   if (!out) return df::fail(DF_E_INVALID, "conv: null out");
   *out = nullptr;
   int rc = validate(d);
   if (rc) return rc;
+  const bool fused_cat = n_src > 0;
+  int swb_cat = 128;
+  if (fused_cat) {
+    // acceptance of the concat half = jit_concat_kernel::init_conf for 1-byte types (every input's channel
+    // count a multiple of 16, src/jit_concat_kernel.cc:157-176); the fused A-operand load additionally needs
+    // whole 32-byte K-steps per input
+    if (n_src > kMaxSrc || !src_ic) return df::fail(DF_E_UNSUPPORTED, "concat+conv: at most %d inputs", kMaxSrc);
+    long sum = 0;
+    for (int i = 0; i < n_src; ++i) {
+      if (src_ic[i] <= 0 || src_ic[i] % 16) return df::fail(DF_E_INVALID, "concat+conv: input %d has %d channels (not a positive multiple of 16)", i, src_ic[i]);
+      if (src_ic[i] % 32) return df::fail(DF_E_UNSUPPORTED, "concat+conv: fused A-operand load needs channel counts that are multiples of 32 (input %d: %d)", i, src_ic[i]);
+      while (src_ic[i] % swb_cat) swb_cat /= 2;
+      sum += src_ic[i];
+    }
+    if (sum != d->ic) return df::fail(DF_E_INVALID, "concat+conv: inputs have %ld channels, the conv expects %d", sum, d->ic);
+    if (d->ic / swb_cat > kMaxKBlocks) return df::fail(DF_E_UNSUPPORTED, "concat+conv: more than %d K-blocks", kMaxKBlocks);
+  }
   if (!wei || !scale0) return df::fail(DF_E_INVALID, "conv: null weights / scales");
   if ((d->bia0_dt != DF_UNDEF && !bia0) || (d->oc1 != 0 && d->bia1_dt != DF_UNDEF && !bia1))
     return df::fail(DF_E_INVALID, "conv: bias dtype given but pointer is null");
@@ -225,8 +246,20 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
 #else
   p.dbg_no_mma = 0;
 #endif
-  p.swb = pick_swb(d->ic);
+  p.swb = fused_cat ? swb_cat : pick_swb(d->ic);
   p.nkb = (d->ic + p.swb - 1) / p.swb;
+  p.n_src = fused_cat ? n_src : 1;
+  p.concat_relu = fused_cat && concat_relu;
+  op->n_src = p.n_src;
+  op->src_ic[0] = d->ic;
+  if (fused_cat)
+    for (int i = 0, kb = 0; i < n_src; ++i) {
+      op->src_ic[i] = src_ic[i];
+      for (int c0 = 0; c0 < src_ic[i]; c0 += p.swb, ++kb) {
+        p.kb_src[kb] = (unsigned char)i;
+        p.kb_c0[kb] = (unsigned short)c0;
+      }
+    }
   p.ks_last = (d->ic - (p.nkb - 1) * p.swb + 31) / 32;
   p.swb1 = pick_swb(d->oc);
   p.nkb1 = (d->oc + p.swb1 - 1) / p.swb1;
@@ -410,7 +443,7 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   // to wait for GEMM2 of tile t (profiles/r02_knockout.log: with one tile the two strictly alternate and
   // their hand-offs alone cost ~3000 cycles per tile).  Anything else runs the run-time-geometry kernel.
   const bool static_ok = !conv0_only && p.fast1 && p.k1_uniform != 0 && d->round0 == DF_ROUND_NEAREST && d->round1 == DF_ROUND_NEAREST &&
-                         !p.nan_safe && !getenv("DF_FORCE_DYNAMIC_GEOMETRY");  // (env: test hook for the generic path)
+                         !p.nan_safe && !fused_cat && !getenv("DF_FORCE_DYNAMIC_GEOMETRY");  // (env: test hook for the generic path)
   auto match_static = [&]() {
     if (geom_matches<GeoCfg1>(p)) { p.SB = GeoCfg1::SB; return 1; }
     if (geom_matches<GeoCfg3>(p)) { p.SB = GeoCfg3::SB; return 3; }
@@ -520,35 +553,56 @@ extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const in
   return 0;
 }
 
+extern "C" int df_conv_create(const df_conv_desc* d, const int8_t* wei, const int8_t* wei1, const void* bia0,
+                              const void* bia1, const float* scale0, const float* scale1, df_conv** out) {
+  return conv_create_impl(d, 0, nullptr, 0, wei, wei1, bia0, bia1, scale0, scale1, out);
+}
+
+extern "C" int df_conv_create_concat(const df_conv_desc* d, int n_src, const int* src_ic, int concat_relu,
+                                     const int8_t* wei, const int8_t* wei1, const void* bia0, const void* bia1,
+                                     const float* scale0, const float* scale1, df_conv** out) {
+  if (n_src <= 0) return df::fail(DF_E_INVALID, "concat+conv: no inputs");
+  return conv_create_impl(d, n_src, src_ic, concat_relu, wei, wei1, bia0, bia1, scale0, scale1, out);
+}
+
 static int tiles_for(const Params& p, int n) {
   const long q_first = 2L * p.Wp, q_end = ((long)n * p.Hp + 1) * p.Wp;
   return (int)((q_end - q_first + kTileM - 1) / kTileM);
 }
 
-// Activation map: 4-D u8 {IC, W, H, n} over the NHWC source, box {swb, Wp, 1, 1} (one halo row of one
-// K-block).  Looked up in / added to a round-robin cache keyed by (pointer, batch).
-static int src_map(df_conv* op, const Params& p, const void* ptr, int n, const CUtensorMap** out) {
-  for (int i = 0; i < df_conv::kMapSlots; ++i)
-    if (op->a_maps[i].ptr == ptr && op->a_maps[i].n == n) {
-      *out = &op->a_maps[i].map;
+// Activation maps: 4-D u8 {C_i, W, H, n} over each NHWC source (one for a plain conv, n_src for a fused
+// concat), box {swb, Wp, 1, 1} (one halo row of one K-block).  Looked up in / added to a round-robin cache keyed
+// by (pointers, batch).
+static int src_maps(df_conv* op, const Params& p, const void* const* ptrs, int n, const SrcMaps** out) {
+  for (int i = 0; i < df_conv::kMapSlots; ++i) {
+    const df_conv::SrcSlot& c = op->a_maps[i];
+    if (!c.ptr[0] || c.n != n) continue;
+    bool same = true;
+    for (int k = 0; k < op->n_src; ++k) same = same && c.ptr[k] == ptrs[k];
+    if (same) {
+      *out = &c.maps;
       return 0;
     }
+  }
   EncodeTiledFn enc = get_encode();
   if (!enc) return df::fail(DF_E_NODRIVER, "cuTensorMapEncodeTiled unavailable");
   df_conv::SrcSlot& s = op->a_maps[op->a_next];
   op->a_next = (op->a_next + 1) % df_conv::kMapSlots;
-  cuuint64_t gd[4] = {(cuuint64_t)p.IC, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)n};
-  cuuint64_t gs[3] = {(cuuint64_t)p.IC, (cuuint64_t)p.W * p.IC, (cuuint64_t)p.H * p.W * p.IC};
-  cuuint32_t box[4] = {(cuuint32_t)p.swb, (cuuint32_t)p.Wp, 1, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  s.ptr = nullptr;
-  CUresult r = enc(&s.map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(ptr), gd, gs, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(p.swb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return df::fail(DF_E_INTERNAL, "cuTensorMapEncodeTiled(src) failed: %d", (int)r);
-  s.ptr = ptr;
+  s.ptr[0] = nullptr;
+  for (int k = 0; k < op->n_src; ++k) {
+    const cuuint64_t c = (cuuint64_t)op->src_ic[k];
+    cuuint64_t gd[4] = {c, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)n};
+    cuuint64_t gs[3] = {c, (cuuint64_t)p.W * c, (cuuint64_t)p.H * p.W * c};
+    cuuint32_t box[4] = {(cuuint32_t)p.swb, (cuuint32_t)p.Wp, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&s.maps.m[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(ptrs[k]), gd, gs, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(p.swb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return df::fail(DF_E_INTERNAL, "cuTensorMapEncodeTiled(src %d) failed: %d", k, (int)r);
+  }
+  for (int k = op->n_src - 1; k >= 0; --k) s.ptr[k] = ptrs[k];
   s.n = n;
-  *out = &s.map;
+  *out = &s.maps;
   return 0;
 }
 
@@ -584,12 +638,13 @@ static int dst_maps(df_conv* op, const Params& p, const void* ptr, int n, const 
   return 0;
 }
 
-extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, void* stream) {
-  if (!op || !src || !dst) return df::fail(DF_E_INVALID, "conv run: null argument");
+static int conv_run_impl(df_conv* op, const void* const* srcs, void* dst, int n, void* stream) {
+  if (!op || !srcs || !dst) return df::fail(DF_E_INVALID, "conv run: null argument");
+  for (int k = 0; k < op->n_src; ++k)
+    if (!srcs[k] || (reinterpret_cast<uintptr_t>(srcs[k]) & 15)) return df::fail(DF_E_INVALID, "conv run: source %d is null or not 16-byte aligned", k);
   if (n < 0 || n > op->desc.n) return df::fail(DF_E_INVALID, "conv run: batch %d outside [0, %d]", n, op->desc.n);
   if (n == 0) return 0;
-  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
-    return df::fail(DF_E_INVALID, "conv run: src/dst must be 16-byte aligned");
+  if (reinterpret_cast<uintptr_t>(dst) & 15) return df::fail(DF_E_INVALID, "conv run: src/dst must be 16-byte aligned");
   {  // the handle's weights, constants and tensor maps live on the device it was created on
     int dev = -1;
     DF_CUDA(cudaGetDevice(&dev));
@@ -599,10 +654,10 @@ extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, vo
   Params p = op->pair ? op->pair_prm : op->prm;
   if ((long)n * p.Hp * p.Wp + 4L * p.Wp + kTileM >= (1L << 31))
     return df::fail(DF_E_UNSUPPORTED, "conv run: batch too large for 32-bit position index");
-  const CUtensorMap* tmA = nullptr;
+  const SrcMaps* tmA = nullptr;
   const DstMaps* tmD = &op->d_maps[0].maps;  // not read by the kernel unless stage_out
   {
-    int rc = src_map(op, p, src, n, &tmA);
+    int rc = src_maps(op, p, srcs, n, &tmA);
     if (rc) return rc;
     if (p.stage_out) rc = dst_maps(op, p, dst, n, &tmD);
     if (rc) return rc;
@@ -630,6 +685,16 @@ extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, vo
   set_tile_step(grid);
   DF_CUDA(op->kernel.launch(grid, op->smem_bytes, (cudaStream_t)stream, *tmA, op->tmW0, op->tmW1, *tmD, p));
   return 0;
+}
+
+extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, void* stream) {
+  if (op && op->n_src != 1) return df::fail(DF_E_INVALID, "conv run: handle was created for %d concatenated inputs (df_conv_run_concat)", op->n_src);
+  const void* srcs[1] = {src};
+  return conv_run_impl(op, srcs, dst, n, stream);
+}
+
+extern "C" int df_conv_run_concat(df_conv* op, const void* const* srcs, void* dst, int n, void* stream) {
+  return conv_run_impl(op, srcs, dst, n, stream);
 }
 
 // Diagnostic: record a per-role clock64 timeline into `dev_buf` (grid * 4 * cap u64 words) on the

@@ -59,6 +59,8 @@ constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);  // 640: a 21st warp woul
 constexpr int kTileM = 128;
 constexpr int kMaxAStages = 4;
 constexpr int kMaxBStages = 8;
+constexpr int kMaxSrc = 8;       // inputs of a fused concat -> conv
+constexpr int kMaxKBlocks = 16;  // K-blocks of the conv0 reduction when the input is a fused concat
 constexpr int kAcc1Col = 256;   // TMEM column of the first conv1 accumulator
 constexpr int kAcc1Stride = 128;
 constexpr uint32_t kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
@@ -95,6 +97,14 @@ struct Params {
   void* dst;
   unsigned long long* trace;  // optional timeline buffer (df_conv_debug_trace), normally null
   int trace_cap;
+  // concat fused into the A-operand load (df_conv_create_concat; run-time geometry only): the conv's input is the
+  // channel concatenation of n_src NHWC tensors that are never materialised -- K-block kb of the halo is loaded
+  // from tensor map kb_src[kb] at channel kb_c0[kb] (every source's channel count is a multiple of swb, so a
+  // K-block never straddles two sources).  concat_relu: the reference's literal u8 ReLU (vpmaxsb: bytes >= 128
+  // become 0, jit_concat_kernel.cc:43-51) is applied to the halo in shared memory before the tensor pipe reads it.
+  int n_src, concat_relu;
+  unsigned char kb_src[kMaxKBlocks];
+  unsigned short kb_c0[kMaxKBlocks];
 };
 
 // Diagnostic switches that produce garbage results (skip the MMAs / the TMA stores / the staging writes to
@@ -182,6 +192,7 @@ constexpr bool static_epilogue() { return G::is_static && DF_STATIC_EPI != 0; }
 
 struct Barriers {
   uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
+  uint64_t a_ready[kMaxAStages];  // fused concat + ReLU: halo stage clamped and visible to the tensor pipe
   uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
   uint64_t res_full;
   uint64_t acc0_full[2], acc0_empty[2];
@@ -213,6 +224,10 @@ constexpr uint32_t kStageBytes = kTileM * 128;  // one staged conv1 chunk: 128 p
 //     rejected by the hardware for stores -- probe/tma_store_probe.cu.)
 struct DstMaps {
   CUtensorMap m[8];  // m[i]: box = {128, 128 >> i}
+};
+// Activation maps: m[0] is the conv's source; m[1 ..] only exist for a fused concat -> conv (Params::n_src)
+struct SrcMaps {
+  CUtensorMap m[kMaxSrc];
 };
 
 // number of valid (= real pixel) positions with linear index < q; for a valid q this is its flat NHW
@@ -1145,7 +1160,7 @@ __device__ __forceinline__ void load_epilogue_constants(const Params& p, uint8_t
 // ------------------------------------------------------------------------------- the kernel
 template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
+conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ CUtensorMap tmW0,
                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ DstMaps tmD,
                   const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1186,8 +1201,9 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(smem_u32(&bar->stage_empty[i]), 1);
     }
     for (int i = 0; i < kG1Ahead; ++i) mbar_init(smem_u32(&bar->g1_prog[i]), 1);
+    for (int i = 0; i < kMaxAStages; ++i) mbar_init(smem_u32(&bar->a_ready[i]), 1);
     fence_mbar_init();
-    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmS.m[0]);
     tma_prefetch_desc(&tmW0);
     tma_prefetch_desc(&tmW1);
   }
@@ -1204,37 +1220,99 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // alternatives measured slow (probe/mma_contention.cu, profiles/r01_mma_issue_probe.log): a
   // per-tap elect/__syncwarp costs ~370 cycles per iteration, and rebuilding descriptors from
   // vector registers (R2UR) ~140 cycles per tap -- more than the 96..256 cycles of MMA work in a tap.
+  // fused concat -> conv (run-time geometry only): K-blocks come from several tensor maps, and with the concat's
+  // ReLU the whole producer warp clamps every halo stage before the tensor pipe may read it
+  const bool multi_src = !G::is_static && p.n_src > 1;
+  const bool clamp_a = !G::is_static && p.concat_relu != 0;
   if (warp == 0) {
     // =============================== TMA producer: halo rows ===============================
-    if (elect_one()) {
-      Tracer tr(p, 0);
-      griddep_wait();  // the source may have been written by the previous kernel in the stream
-      for (int it = 0; it < n_local; ++it) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        const int s = it % p.SA;
-        mbar_wait(smem_u32(&bar->a_empty[s]), ((it / p.SA) & 1) ^ 1);
-        tr.ev(1);
-        const int q0 = q_first + tile * kTileM;
-        const int g_lo = (q0 - p.Wp - 1) / p.Wp;
-        const int g_hi = (q0 + kTileM + p.Wp) / p.Wp;
-        const int nrows = g_hi - g_lo + 1;
-        const uint32_t full = smem_u32(&bar->a_full[s]);
-        const uint32_t stage = sbase + p.off_a + s * p.a_stage_bytes;
-        mbar_expect_tx(full, (uint32_t)(nrows * g.nkb() * p.Wp * g.swb()));
-        int n = (g_lo > 0) ? (g_lo - 1) / p.Hp : 0;
-        int h = (g_lo > 0) ? (g_lo - 1) - n * p.Hp - 1 : -2;  // -2: the all-zero row above everything
-        uint32_t dst = stage;
-        const uint32_t row_bytes = p.Wp * g.swb();
-        for (int r = 0; r < nrows; ++r, dst += row_bytes) {
+    // one thread issues the per-row, per-K-block loads of local tile `it` into stage it % SA
+    auto issue_halo = [&](int it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int s = it % p.SA;
+      const int q0 = q_first + tile * kTileM;
+      const int g_lo = (q0 - p.Wp - 1) / p.Wp;
+      const int g_hi = (q0 + kTileM + p.Wp) / p.Wp;
+      const int nrows = g_hi - g_lo + 1;
+      const uint32_t full = smem_u32(&bar->a_full[s]);
+      const uint32_t stage = sbase + p.off_a + s * p.a_stage_bytes;
+      mbar_expect_tx(full, (uint32_t)(nrows * g.nkb() * p.Wp * g.swb()));
+      int n = (g_lo > 0) ? (g_lo - 1) / p.Hp : 0;
+      int h = (g_lo > 0) ? (g_lo - 1) - n * p.Hp - 1 : -2;  // -2: the all-zero row above everything
+      uint32_t dst = stage;
+      const uint32_t row_bytes = p.Wp * g.swb();
+      for (int r = 0; r < nrows; ++r, dst += row_bytes) {
+        if (multi_src) {
+          for (int kb = 0; kb < g.nkb(); ++kb)
+            tma_load_4d(dst + kb * p.a_kb_stride, &tmS.m[p.kb_src[kb]], full, (int)p.kb_c0[kb], 0, h, n);
+        } else {
 #pragma unroll
-          for (int kb = 0; kb < g.nkb(); ++kb) tma_load_4d(dst + kb * p.a_kb_stride, &tmA, full, kb * g.swb(), 0, h, n);
-          if (h == -2) {
-            h = -1;  // g = 1: the zero row above image 0
-          } else if (++h == p.H) {
-            h = -1;  // shared zero row between images
-            ++n;
+          for (int kb = 0; kb < g.nkb(); ++kb) tma_load_4d(dst + kb * p.a_kb_stride, &tmS.m[0], full, kb * g.swb(), 0, h, n);
+        }
+        if (h == -2) {
+          h = -1;  // g = 1: the zero row above image 0
+        } else if (++h == p.H) {
+          h = -1;  // shared zero row between images
+          ++n;
+        }
+      }
+    };
+    if (!clamp_a) {
+      if (elect_one()) {
+        Tracer tr(p, 0);
+        griddep_wait();  // the source may have been written by the previous kernel in the stream
+        for (int it = 0; it < n_local; ++it) {
+          mbar_wait(smem_u32(&bar->a_empty[it % p.SA]), ((it / p.SA) & 1) ^ 1);
+          tr.ev(1);
+          issue_halo(it);
+        }
+      }
+    } else {
+      // Lane 0 issues the loads, the whole warp clamps: stage s of tile `it` is waited for (a_full), every byte
+      // goes through a per-byte signed max with 0 (= vpmaxsb with zero, the reference's u8 / s8 concat ReLU),
+      // the writes are made visible to the async proxy and a_ready[s] tells the MMA thread.  The next tile's
+      // loads are issued BEFORE the clamp when their stage is already free, after it otherwise (the stage is
+      // released by GEMM1 of tile it + 1 - SA, which itself may be waiting for this clamp).
+      griddep_wait();
+      if (lane == 0 && n_local > 0) issue_halo(0);  // stage 0 is free at kernel start
+      for (int it = 0; it < n_local; ++it) {
+        int issued = 1;
+        if (it + 1 < n_local) {
+          if (lane == 0) {
+            issued = mbar_test_wait(smem_u32(&bar->a_empty[(it + 1) % p.SA]), (((it + 1) / p.SA) & 1) ^ 1) ? 1 : 0;
+            if (issued) issue_halo(it + 1);
+          }
+          issued = __shfl_sync(0xffffffffu, issued, 0);
+        }
+        const int s = it % p.SA;
+        mbar_wait_warp(smem_u32(&bar->a_full[s]), (it / p.SA) & 1);
+        const uint32_t stage = sbase + p.off_a + s * p.a_stage_bytes;
+        for (uint32_t off = (uint32_t)lane * 16u; off < p.a_stage_bytes; off += 4 * 512u) {
+          uint32_t v[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (off + u * 512u < p.a_stage_bytes)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3])
+                           : "r"(stage + off + u * 512u));
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (off + u * 512u < p.a_stage_bytes) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v[u][i] = __vmaxs4(v[u][i], 0u);
+              sts128(stage + off + u * 512u, v[u]);
+            }
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to tcgen05.mma (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&bar->a_ready[s]));
+          if (!issued) {
+            mbar_wait(smem_u32(&bar->a_empty[(it + 1) % p.SA]), (((it + 1) / p.SA) & 1) ^ 1);
+            issue_halo(it + 1);
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 2) {
@@ -1324,6 +1402,8 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // position of the tile inside its halo window, advanced without divisions
       int a_off_px = (q_first - p.Wp - 1 + (int)blockIdx.x * kTileM) % p.Wp;
       uint32_t sa = 0, a_par = 0;
+      // halo hand-off: the TMA's own barrier, or (fused concat + ReLU) the clamp's
+      const uint32_t a_go = clamp_a ? smem_u32(&bar->a_ready[0]) : smem_u32(&bar->a_full[0]);
       Tracer tr(p, 1);
       tr.ev(9);
 
@@ -1399,7 +1479,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int it = 0; it < n_local; ++it) {
           const int ab = it % g.n_acc0();
           mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / g.n_acc0()) & 1) ^ 1);
-          mbar_wait(smem_u32(&bar->a_full[sa]), a_par);
+          mbar_wait(a_go + 8 * sa, a_par);
           tc_fence_after_sync();
           tr.ev(10);
           const uint32_t d_tmem = tmem + ab * g.OC();
@@ -1460,7 +1540,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (g1_kh == 0) {
               const int ab = g1_it % g.n_acc0();
               ok = mbar_test_wait(smem_u32(&bar->acc0_empty[ab]), ((g1_it / g.n_acc0()) & 1) ^ 1) &&
-                   mbar_test_wait(smem_u32(&bar->a_full[sa]), a_par);
+                   mbar_test_wait(a_go + 8 * sa, a_par);
               if (ok) {
                 tc_fence_after_sync();
                 tr.ev(10);
@@ -1491,7 +1571,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (it < n_local) {
             const int ab = it % g.n_acc0();
             mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / g.n_acc0()) & 1) ^ 1);
-            mbar_wait(smem_u32(&bar->a_full[sa]), a_par);
+            mbar_wait(a_go + 8 * sa, a_par);
             tc_fence_after_sync();
             tr.ev(10);
             const uint32_t d_tmem = tmem + ab * g.OC();
@@ -1794,7 +1874,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // The kernel instantiations are spread over several translation units (conv_inst_*.cu) so that they compile
 // in parallel; conv_fused.cu (create / run) reaches them through these type-erased function pointers.
 // type-erased launcher: the epilogue-constant parameter type depends on the geometry
-typedef cudaError_t (*LaunchFn)(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
+typedef cudaError_t (*LaunchFn)(int grid, uint32_t smem, cudaStream_t st, const SrcMaps& a, const CUtensorMap& w0,
                                 const CUtensorMap& w1, const DstMaps& d, const Params& p);
 typedef cudaError_t (*AttrFn)(uint32_t smem);
 
@@ -1803,8 +1883,8 @@ typedef cudaError_t (*AttrFn)(uint32_t smem);
 // DF_NO_PDL=1 (read once per process) launches without the programmatic-stream-serialization attribute
 bool pdl_enabled();
 
-template <class Kernel>
-cudaError_t launch_pdl(Kernel kernel, int grid, int threads, uint32_t smem, cudaStream_t st, const CUtensorMap& a,
+template <class Kernel, class AMaps>
+cudaError_t launch_pdl(Kernel kernel, int grid, int threads, uint32_t smem, cudaStream_t st, const AMaps& a,
                        const CUtensorMap& w0, const CUtensorMap& w1, const DstMaps& d, const Params& p) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
@@ -1820,7 +1900,7 @@ cudaError_t launch_pdl(Kernel kernel, int grid, int threads, uint32_t smem, cuda
 }
 
 template <class G, int kDst, bool kDown0, bool kDown1, bool kNanSafe>
-cudaError_t launch_conv(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
+cudaError_t launch_conv(int grid, uint32_t smem, cudaStream_t st, const SrcMaps& a, const CUtensorMap& w0,
                         const CUtensorMap& w1, const DstMaps& d, const Params& p) {
   return launch_pdl(conv_fused_kernel<G, kDst, kDown0, kDown1, kNanSafe>, grid, kThreads, smem, st, a, w0, w1, d, p);
 }
@@ -1835,9 +1915,9 @@ struct KernelFn {
 };
 
 template <class G, int kDst>
-cudaError_t launch_pair(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& a, const CUtensorMap& w0,
+cudaError_t launch_pair(int grid, uint32_t smem, cudaStream_t st, const SrcMaps& a, const CUtensorMap& w0,
                         const CUtensorMap& w1, const DstMaps& d, const Params& p) {
-  return launch_pdl(conv_pair_kernel<G, kDst>, grid, kThreads, smem, st, a, w0, w1, d, p);
+  return launch_pdl(conv_pair_kernel<G, kDst>, grid, kThreads, smem, st, a.m[0], w0, w1, d, p);
 }
 template <class G, int kDst>
 cudaError_t attr_pair(uint32_t smem) {

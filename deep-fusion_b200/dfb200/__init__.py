@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "df_last_error", "df_version", "df_device_count", "df_set_device", "df_get_device", "df_device_sm_count", "df_malloc",
     "df_free", "df_memset", "df_host_register", "df_host_unregister", "df_h2d", "df_d2h", "df_stream_create",
     "df_stream_sync", "df_stream_destroy", "df_event_create", "df_event_record", "df_stream_wait_event", "df_event_elapsed_ms",
-    "df_event_destroy", "df_concat_check", "df_concat_run", "df_conv_create", "df_conv_run", "df_conv_query",
+    "df_event_destroy", "df_concat_check", "df_concat_run", "df_conv_create", "df_conv_run", "df_conv_query", "df_conv_create_concat", "df_conv_run_concat",
     "df_conv_destroy", "df_conv_debug_trace", "df_graph_begin", "df_graph_end", "df_graph_launch", "df_graph_destroy",
     "df_wei_blocked_offset", "df_repack_oihw_to_blocked", "df_repack_blocked_to_oihw", "df_repack_goihw_to_blocked",
     "df_repack_blocked_to_goihw", "df_nchw_to_nhwc", "df_nhwc_to_nchw",
@@ -90,6 +90,10 @@ def lib():
         l.df_conv_create.argtypes = [C.POINTER(ConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.POINTER(C.c_void_p)]
         l.df_conv_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        l.df_conv_create_concat.argtypes = [C.POINTER(ConvDesc), C.c_int, C.POINTER(C.c_int), C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_void_p)]
+        l.df_conv_run_concat.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p]
         l.df_conv_query.argtypes = [C.c_void_p, C.POINTER(ConvInfo)]
         l.df_conv_destroy.argtypes = [C.c_void_p]
         l.df_conv_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -289,6 +293,46 @@ class Conv:
             self.close()
         except Exception:
             pass
+
+
+class ConcatConv(Conv):
+    """concat(+ReLU) fused into the conv's A-operand load (df_conv_create_concat / df_conv_run_concat): the conv's
+    source is the channel concatenation of several NHWC u8 tensors that is never written to memory."""
+
+    def __init__(self, n, ih, iw, src_ics, concat_relu, oc, oc1, dst_dt, wei_blocked, wei1_blocked, bias0=None, bias1=None,
+                 scale0=(1.0,), scale1=(1.0,), bia0_dt=UNDEF, bia1_dt=UNDEF, relu0=False, relu1=False,
+                 round0=NEAREST, round1=NEAREST):
+        scale0 = np.ascontiguousarray(scale0, dtype=np.float32)
+        scale1 = np.ascontiguousarray(scale1, dtype=np.float32)
+        self.src_ics = list(src_ics)
+        ic = sum(self.src_ics)
+        self.desc = ConvDesc(n, ih, iw, ic, oc, oc1, 3, 3, 1, 1, 1, 1, dst_dt, bia0_dt, bia1_dt,
+                             int(relu0), int(relu1), round0, round1, scale0.size, scale1.size)
+        h = C.c_void_p()
+        keep = [np.ascontiguousarray(x) if x is not None else None for x in (wei_blocked, wei1_blocked, bias0, bias1)]
+        ics = (C.c_int * len(self.src_ics))(*self.src_ics)
+        check(lib().df_conv_create_concat(C.byref(self.desc), len(self.src_ics), ics, int(concat_relu), _ptr(keep[0]),
+                                          _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]), scale0.ctypes.data,
+                                          scale1.ctypes.data, C.byref(h)))
+        self.handle = h.value
+        self.oh, self.ow = ih, iw
+        self.out_c = oc1 if oc1 else oc
+        self.dst_dt = dst_dt
+
+    def run(self, src_devs, dst_dev, n=None, stream=None):
+        ptrs = (C.c_void_p * len(src_devs))(*[b.ptr if isinstance(b, DeviceBuffer) else b for b in src_devs])
+        d = dst_dev.ptr if isinstance(dst_dev, DeviceBuffer) else dst_dev
+        check(lib().df_conv_run_concat(self.handle, ptrs, d, self.desc.n if n is None else n, stream))
+
+    def __call__(self, srcs) -> np.ndarray:
+        n = srcs[0].shape[0]
+        bufs = [DeviceBuffer.from_numpy(s) for s in srcs]
+        shape = (n, self.oh, self.ow, self.out_c)
+        dbuf = DeviceBuffer(int(np.prod(shape)) * np.dtype(NP_OF[self.dst_dt]).itemsize)
+        dbuf.fill(0xCD)
+        self.run(bufs, dbuf, n)
+        sync()
+        return dbuf.download(shape, NP_OF[self.dst_dt])
 
 
 class ConcatCall:

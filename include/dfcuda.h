@@ -112,6 +112,17 @@ int df_conv_create(const df_conv_desc *desc, const int8_t *wei_OIhw4i16o4i,
  * and is NOT thread-safe: use one handle per host thread (the reference has the same rule for one
  * op, src/op_conv.cc:159-160). */
 int df_conv_run(df_conv *op, const uint8_t *src_dev, void *dst_dev, int n, void *stream);
+/* ---- concat(+ReLU) fused into the conv's A-operand load: the producer -> consumer chain
+ *      op_concat<T>::infer (src/op_concat.cc:22-72) -> op_conv<T>::infer (src/op_conv.cc:140-260) as ONE
+ *      kernel.  The conv's source is the channel concatenation of `n_src` NHWC u8 tensors (src_ic[i] channels
+ *      each, sum == desc->ic) which is never materialised: each K-block of the halo is loaded by TMA from the
+ *      input that owns those channels.  concat_relu = the reference's literal u8 ReLU (vpmaxsb, bytes >= 128
+ *      become 0), applied in shared memory.  Result == df_concat_run followed by df_conv_run, bit for bit.
+ *      DF_E_UNSUPPORTED when an input's channel count is not a multiple of 32 (run the two ops instead). ---- */
+int df_conv_create_concat(const df_conv_desc *desc, int n_src, const int *src_ic, int concat_relu,
+                          const int8_t *wei_OIhw4i16o4i, const int8_t *wei1x1_OIhw4i16o4i, const void *bia0,
+                          const void *bia1, const float *scale0, const float *scale1, df_conv **out);
+int df_conv_run_concat(df_conv *op, const void *const *src_dev, void *dst_dev, int n, void *stream);
 int df_conv_query(const df_conv *op, df_conv_info *info);
 int df_conv_destroy(df_conv *op);
 /* Diagnostic only (no reference counterpart): per-role clock64 timeline of the next launches

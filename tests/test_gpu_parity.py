@@ -297,3 +297,57 @@ def test_conv_generic_geometry_and_i2f_paths(df):
     assert "OK" in _run_cfg3_in_subprocess({"DF_FORCE_DYNAMIC_GEOMETRY": "1"})
     assert "OK" in _run_cfg3_in_subprocess({"DF_NO_FAST_CONV1": "1"})
     assert "OK" in _run_cfg3_in_subprocess({"DF_FORCE_DYNAMIC_GEOMETRY": "1", "DF_NO_FAST_CONV1": "1"})
+
+
+# ---------------------------------------------------------------- concat fused into the conv's A-operand load
+# op_concat (src/op_concat.cc:22-72) feeding op_conv (src/op_conv.cc:140-260) as ONE kernel.  The
+# checker is the oracle's concat followed by the oracle's conv on the concatenated tensor; full-range u8 inputs,
+# so the literal ReLU (bytes >= 128 -> 0) is exercised.
+CONCAT_CONV = [
+    # name, n, h, w, input channels, oc, oc1, dst
+    ("two_32", 2, 7, 9, (32, 32), 48, 80, "u8"),
+    ("three_mixed", 2, 9, 7, (64, 32, 96), 64, 144, "s8"),
+    ("one_input", 2, 6, 6, (64,), 32, 64, "u8"),
+    ("four_128", 1, 8, 8, (128, 128, 128, 128), 64, 128, "s32"),
+    ("cfg2_crop", 2, 28, 28, (64, 128, 32, 32), 64, 256, "u8"),
+    ("cfg2_conv0_only", 2, 14, 28, (64, 128, 32, 32), 128, 0, "u8"),
+    ("cfg2_f32", 1, 12, 28, (64, 128, 32, 32), 128, 256, "f32"),
+]
+
+
+@pytest.mark.parametrize("relu", [False, True], ids=["copy", "relu"])
+@pytest.mark.parametrize("case", CONCAT_CONV, ids=lambda c: c[0])
+def test_concat_fused_into_conv(df, case, relu):
+    name, n, h, w, ics, oc, oc1, dst = case
+    ic = sum(ics)
+    srcs = [cases.synth.uniform_int(20 + i, (n, h, w, c), 0, 255, np.uint8) for i, c in enumerate(ics)]
+    w0 = cases.synth.wei_s8(2, (oc, ic, 3, 3))
+    wb = cases.layout.oihw_to_blocked(w0)
+    b0 = cases.synth.bias(4, oc, "s32")
+    k0 = {64: 12, 96: 12, 128: 13, 192: 13, 256: 14, 512: 15}.get(ic, 12) + (1 if not relu else 0)
+    s0 = cases.synth.channel_scales(oc, k0)
+    if oc1:
+        w1 = cases.synth.wei_s8(3, (oc1, oc))
+        w1b = cases.layout.oihw_to_blocked(w1.reshape(oc1, oc, 1, 1))
+        b1 = cases.synth.bias(5, oc1, "s32")
+        s1 = cases.synth.channel_scales(oc1, 12)
+    else:
+        w1b, b1, s1 = None, None, np.array([1.0], np.float32)
+    cat = O.concat(O.U8, relu, srcs)
+    d = O.make_desc(n, h, w, ic, oc, oc1, cases.DT[dst], O.S32, O.S32 if oc1 else O.UNDEF, nscale0=oc, nscale1=s1.size)
+    fn = O.replay_conv if (O.replay_supported() and oc1) else O.conv
+    want = fn(d, cat, wb, b0, s0, w1b, b1, s1)
+    op = df.ConcatConv(n, h, w, ics, relu, oc, oc1, cases.DT[dst], wb, w1b, b0, b1, s0, s1, df.S32, df.S32 if oc1 else df.UNDEF)
+    got = op(srcs)
+    op.close()
+    _assert_same(got, want, dst)
+    assert want.any(), "degenerate case: the expected output is all zero"
+
+
+def test_concat_fused_rejects_what_it_cannot_load(df):
+    """Channel counts that are multiples of 16 but not of 32 are valid for concat (jit_concat_kernel.cc:157-176) but
+    not for the fused load: DF_E_UNSUPPORTED, so that the caller runs the two ops instead -- never a wrong result."""
+    wb = cases.layout.oihw_to_blocked(cases.synth.wei_s8(2, (32, 48, 3, 3)))
+    with pytest.raises(df.DfError) as e:
+        df.ConcatConv(1, 4, 4, (16, 32), True, 32, 0, df.U8, wb, None, None, None, np.ones(32, np.float32))
+    assert e.value.code == -2
