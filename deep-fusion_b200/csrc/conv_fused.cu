@@ -227,10 +227,17 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   // ---- the B200 path: fused 3x3 s1 p1 + 1x1
   const bool conv0_only = d->oc1 == 0;  // conv() without the 1x1 stage (include/deepfusion.h:121-129)
   if (!conv0_only && (!wei1 || !scale1)) return df::fail(DF_E_INVALID, "conv: null 1x1 weights / scales");
-  if (d->kh != 3 || d->kw != 3 || d->sh != 1 || d->sw != 1 || d->ph != 1 || d->pw != 1)
-    return df::fail(DF_E_UNSUPPORTED, "B200 path supports k3 s1 p1 only");
+  // any window with stride 1 whose output is not larger than its input (2 p <= k - 1: every "same" or "valid"
+  // convolution); taps are constant offsets in the linearised padded pixel space (conv_kernels.cuh)
+  if (d->sh != 1 || d->sw != 1) return df::fail(DF_E_UNSUPPORTED, "B200 path supports stride 1 only (got %d x %d)", d->sh, d->sw);
+  if (2 * d->ph > d->kh - 1 || 2 * d->pw > d->kw - 1)
+    return df::fail(DF_E_UNSUPPORTED, "B200 path supports padding <= (kernel - 1) / 2 (got k %dx%d p %dx%d)", d->kh, d->kw, d->ph, d->pw);
+  if (d->kh * d->kw > 121) return df::fail(DF_E_UNSUPPORTED, "B200 path supports windows of at most 121 taps");
+  if (fused_cat && (d->kh != 3 || d->kw != 3 || d->ph != 1 || d->pw != 1))
+    return df::fail(DF_E_UNSUPPORTED, "concat+conv: k3 s1 p1 only");
   if (d->oc > 256) return df::fail(DF_E_UNSUPPORTED, "B200 path supports conv0 oc <= 256 (got %d)", d->oc);
-  if (d->iw > 254) return df::fail(DF_E_UNSUPPORTED, "B200 path supports width <= 254 (TMA box limit)");
+  const int zr_w = d->pw > d->kw - 1 - d->pw ? d->pw : d->kw - 1 - d->pw;  // zero columns between rows
+  if (d->iw + zr_w > 256) return df::fail(DF_E_UNSUPPORTED, "B200 path supports padded width <= 256 (TMA box limit)");
 
   df_conv* op = new df_conv();
   op->desc = *d;
@@ -264,10 +271,19 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   p.swb1 = pick_swb(d->oc);
   p.nkb1 = (d->oc + p.swb1 - 1) / p.swb1;
   p.ks1_last = (d->oc - (p.nkb1 - 1) * p.swb1 + 31) / 32;
-  p.Hp = d->ih + 1;
+  p.KH = d->kh;
+  p.KW = d->kw;
+  p.PH = d->ph;
+  p.PW = d->pw;
+  p.OH = d->ih + 2 * d->ph - d->kh + 1;
+  p.OW = d->iw + 2 * d->pw - d->kw + 1;
+  p.ZR = d->ph > d->kh - 1 - d->ph ? d->ph : d->kh - 1 - d->ph;
+  p.Hp = d->ih + p.ZR;
   const int wp_align = 128 / p.swb;  // every halo row must start 128 B aligned for TMA
-  p.Wp = (d->iw + 1 + wp_align - 1) / wp_align * wp_align;
-  p.NR = (kTileM + 2 * p.Wp) / p.Wp + 2;  // rows touched by 128 + 2*Wp + 2 consecutive positions
+  p.Wp = (d->iw + zr_w + wp_align - 1) / wp_align * wp_align;
+  p.q_first = (p.ZR + 1) * p.Wp;
+  // rows touched by the 128 + (KH - 1) * Wp + KW - 1 consecutive positions a tile's taps read
+  p.NR = (kTileM + (p.KH - 1) * p.Wp + p.KW - 3) / p.Wp + 2;
   p.r8_dw = 8 % p.Wp;
   p.r8_dn = (8 / p.Wp) / p.Hp;
   p.r8_dh = (8 / p.Wp) % p.Hp;
@@ -281,14 +297,15 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   // ---- parameters: weights re-laid out K-major per (tap, K-block); bias -> f32; scales expanded
   // Row r of a weight block (= MMA N index = accumulator column r) holds output channel
   // col_to_channel(r): the order the epilogue's row-pair fragments want (see tmem_ld_16x256b_x8).
-  std::vector<int8_t> w0((size_t)9 * p.nkb * p.OC * p.swb, 0);
-  for (int tap = 0; tap < 9; ++tap)
+  const int taps = p.KH * p.KW;
+  std::vector<int8_t> w0((size_t)taps * p.nkb * p.OC * p.swb, 0);
+  for (int tap = 0; tap < taps; ++tap)
     for (int r = 0; r < p.OC; ++r) {
       const int o = col_to_channel(r, p.OC);
       for (int i = 0; i < p.IC; ++i) {
         const int kb = i / p.swb;
         w0[(((size_t)tap * p.nkb + kb) * p.OC + r) * p.swb + (i - kb * p.swb)] =
-            wei[blocked_off(o, i, tap / 3, tap % 3, p.IC, 3, 3)];
+            wei[blocked_off(o, i, tap / p.KW, tap % p.KW, p.IC, p.KH, p.KW)];
       }
     }
   std::vector<int8_t> w1((size_t)p.n_chunks * p.nkb1 * p.nc1 * p.swb1, 0);  // stays zero (and unused) for conv0-only
@@ -388,7 +405,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
     p.a_stage_bytes = align_up(p.nkb * p.a_kb_stride, 1024);
     p.w0_block_bytes = (uint32_t)p.OC * p.swb;
     p.w1_block_bytes = (uint32_t)p.nc1 * p.swb1;
-    const uint32_t w0_bytes = align_up(9 * p.nkb * p.w0_block_bytes, 1024);
+    const uint32_t w0_bytes = align_up(taps * p.nkb * p.w0_block_bytes, 1024);
     const uint32_t w1_bytes = conv0_only ? 0 : align_up(p.n_chunks * p.nkb1 * p.w1_block_bytes, 1024);
     const uint32_t fixed = off;
     if (fixed + 2 * p.a_stage_bytes + w0_bytes + w1_bytes <= avail) {
@@ -442,7 +459,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   // and -- when it fits -- keep TWO intermediate tiles, so that the conv0 epilogue of tile t+1 does not have
   // to wait for GEMM2 of tile t (profiles/r02_knockout.log: with one tile the two strictly alternate and
   // their hand-offs alone cost ~3000 cycles per tile).  Anything else runs the run-time-geometry kernel.
-  const bool static_ok = !conv0_only && p.fast1 && p.k1_uniform != 0 && d->round0 == DF_ROUND_NEAREST && d->round1 == DF_ROUND_NEAREST &&
+  const bool static_ok = !conv0_only && taps == 9 && p.KH == 3 && p.PH == 1 && p.PW == 1 && p.fast1 && p.k1_uniform != 0 && d->round0 == DF_ROUND_NEAREST && d->round1 == DF_ROUND_NEAREST &&
                          !p.nan_safe && !fused_cat && !getenv("DF_FORCE_DYNAMIC_GEOMETRY");  // (env: test hook for the generic path)
   auto match_static = [&]() {
     if (geom_matches<GeoCfg1>(p)) { p.SB = GeoCfg1::SB; return 1; }
@@ -507,7 +524,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   p.bias1 = op->d_bias1;
   p.scale1 = op->d_scale1;
   p.k1 = op->d_k1;
-  DF_TRY(encode_2d(&op->tmW0, op->d_w0, p.swb, (long)9 * p.nkb * p.OC, p.OC));
+  DF_TRY(encode_2d(&op->tmW0, op->d_w0, p.swb, (long)taps * p.nkb * p.OC, p.OC));
   DF_TRY(encode_2d(&op->tmW1, op->d_w1, p.swb1, (long)p.n_chunks * p.nkb1 * p.nc1, p.nc1));
 
   op->kernel = pick_kernel(op->geom_id, d->dst_dt, p.round0 == DF_ROUND_DOWN, p.round1 == DF_ROUND_DOWN, p.nan_safe != 0);
@@ -566,7 +583,7 @@ extern "C" int df_conv_create_concat(const df_conv_desc* d, int n_src, const int
 }
 
 static int tiles_for(const Params& p, int n) {
-  const long q_first = 2L * p.Wp, q_end = ((long)n * p.Hp + 1) * p.Wp;
+  const long q_first = p.q_first, q_end = ((long)n * p.Hp + 1) * p.Wp;
   return (int)((q_end - q_first + kTileM - 1) / kTileM);
 }
 
@@ -621,7 +638,7 @@ static int dst_maps(df_conv* op, const Params& p, const void* ptr, int n, const 
   df_conv::DstSlot& s = op->d_maps[op->d_next];
   op->d_next = (op->d_next + 1) % df_conv::kMapSlots;
   s.ptr = nullptr;
-  const cuuint64_t pixels = (cuuint64_t)n * p.H * p.W;
+  const cuuint64_t pixels = (cuuint64_t)n * p.OH * p.OW;
   for (int i = 0; i < (per_warp ? 6 : 8); ++i) {
     cuuint64_t gd[2] = {(cuuint64_t)p.OC1, pixels};
     cuuint64_t gs[1] = {(cuuint64_t)p.OC1};
@@ -719,8 +736,8 @@ extern "C" int df_conv_query(const df_conv* op, df_conv_info* info) {
   info->b_stages = op->pair ? 0 : p.SB;
   info->padded_w = p.Wp;
   info->padded_h = p.Hp;
-  info->macs_per_image = (double)p.H * p.W * (9.0 * p.IC * p.OC + (p.conv0_only ? 0.0 : (double)p.OC * p.OC1));
-  info->mma_efficiency = (double)op->desc.n * p.H * p.W / ((double)info->tiles_per_launch * kTileM);
+  info->macs_per_image = (double)p.OH * p.OW * ((double)p.KH * p.KW * p.IC * p.OC + (p.conv0_only ? 0.0 : (double)p.OC * p.OC1));
+  info->mma_efficiency = (double)op->desc.n * p.OH * p.OW / ((double)info->tiles_per_launch * kTileM);
   return 0;
 }
 

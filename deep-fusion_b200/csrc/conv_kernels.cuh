@@ -67,6 +67,11 @@ constexpr uint32_t kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_
 
 struct Params {
   int N, H, W, IC, OC, OC1;
+  // conv0 window: KH x KW taps, padding PH / PW, stride 1 (2 PH <= KH - 1, 2 PW <= KW - 1, so the output is not
+  // larger than the input: OH = H + 2 PH - KH + 1 <= H, likewise OW).  ZR = max(PH, KH - 1 - PH) zero rows separate
+  // the images of the linearised padded pixel space (Hp = H + ZR); q_first = (ZR + 1) * Wp is the position of image
+  // 0, row 0, column 0.  The BASELINE geometry is 3, 3, 1, 1 -> OH = H, OW = W, ZR = 1, q_first = 2 Wp.
+  int KH, KW, PH, PW, OH, OW, ZR, q_first;
   int Hp, Wp, NR;
   int n_tiles;
   int swb, nkb, ks_last;     // conv0: K-block bytes (= swizzle span), blocks, 32 B steps in last
@@ -236,9 +241,10 @@ __device__ __forceinline__ int valid_before(const Params& p, int q) {
   const int gq = q / p.Wp, wq = q - gq * p.Wp;
   const int t = gq - 1;
   const int n = t / p.Hp, hp = t - n * p.Hp;
-  if (n >= p.N) return p.N * p.H * p.W;
-  if (hp < 1) return n * p.H * p.W;
-  return (n * p.H + hp - 1) * p.W + min(wq, p.W);
+  if (n >= p.N) return p.N * p.OH * p.OW;
+  if (hp < p.ZR) return n * p.OH * p.OW;
+  if (hp >= p.ZR + p.OH) return (n + 1) * p.OH * p.OW;
+  return (n * p.OH + hp - p.ZR) * p.OW + min(wq, p.OW);
 }
 
 // Position q = ((n * Hp + hp) + 1) * Wp + wq of the linearised padded pixel space, kept as (wq, n, hp) and
@@ -272,14 +278,15 @@ __device__ __forceinline__ void pos_step(const Params& p, PosState& s, int dw, i
 }
 // NHW pixel index of a position, -1 for padding positions
 __device__ __forceinline__ int pos_pixel(const Params& p, const PosState& s) {
-  const bool ok = (s.wq < p.W) && (s.hp >= 1) && (s.n < p.N);
-  return ok ? (s.n * p.H + s.hp - 1) * p.W + s.wq : -1;
+  const bool ok = (s.wq < p.OW) && (s.hp >= p.ZR) && (s.hp < p.ZR + p.OH) && (s.n < p.N);
+  return ok ? (s.n * p.OH + s.hp - p.ZR) * p.OW + s.wq : -1;
 }
 // = valid_before(q) for the position's q
 __device__ __forceinline__ int pos_valid_before(const Params& p, const PosState& s) {
-  if (s.n >= p.N) return p.N * p.H * p.W;
-  if (s.hp < 1) return s.n * p.H * p.W;
-  return (s.n * p.H + s.hp - 1) * p.W + min(s.wq, p.W);
+  if (s.n >= p.N) return p.N * p.OH * p.OW;
+  if (s.hp < p.ZR) return s.n * p.OH * p.OW;
+  if (s.hp >= p.ZR + p.OH) return (s.n + 1) * p.OH * p.OW;
+  return (s.n * p.OH + s.hp - p.ZR) * p.OW + min(s.wq, p.OW);
 }
 
 __device__ __forceinline__ void store_staged_chunk(const DstMaps& dm, uint32_t stage, int f0, int V, int ch0) {
@@ -310,6 +317,7 @@ struct StaticGeom {
   static constexpr int nc1 = kOC1 < 128 ? kOC1 : 128;
   static constexpr int n_chunks = (kOC1 + nc1 - 1) / nc1;
   static constexpr int n_acc0 = kOC <= 128 ? 2 : 1;
+  static constexpr int KH = 3, KW = 3, PH = 1, PW = 1;
 };
 struct DynGeom {
   static constexpr bool is_static = false;
@@ -325,7 +333,7 @@ struct Geo {
   const Params& p;
   DF_GEO(IC) DF_GEO(OC) DF_GEO(OC1) DF_GEO(w0_res) DF_GEO(w1_res) DF_GEO(SB)
   DF_GEO(swb) DF_GEO(nkb) DF_GEO(ks_last) DF_GEO(swb1) DF_GEO(nkb1) DF_GEO(ks1_last)
-  DF_GEO(nc1) DF_GEO(n_chunks) DF_GEO(n_acc0)
+  DF_GEO(nc1) DF_GEO(n_chunks) DF_GEO(n_acc0) DF_GEO(KH) DF_GEO(KW) DF_GEO(PH) DF_GEO(PW)
   __device__ __forceinline__ uint32_t w0_block_bytes() const { return (uint32_t)(OC() * swb()); }
   __device__ __forceinline__ uint32_t w1_block_bytes() const { return (uint32_t)(nc1() * swb1()); }
   __device__ __forceinline__ uint32_t mid_kb_stride() const { return (uint32_t)(kTileM * swb1()); }
@@ -595,7 +603,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
   const bool fast1 = G::is_static ? true : (p.fast1 != 0);
   const int k_uni = p.k1_uniform;  // static geometries: never 0 (df_conv_create)
   const bool c0_only = !G::is_static && p.conv0_only != 0;
-  const int q_first = 2 * p.Wp;
+  const int q_first = p.q_first;
   // staged output (1-byte destinations, see store_staged_chunk): always for the static geometries
   constexpr bool kCanStage = (kDst == DF_U8 || kDst == DF_S8);
   const bool staged = kCanStage && !G::is_static && p.stage_out != 0;  // static geometries store straight from registers
@@ -907,7 +915,7 @@ __device__ __forceinline__ void epilogue_static(const Params& p, const DstMaps&,
   const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
   constexpr int ts = (kDst == DF_F32 || kDst == DF_S32) ? 4 : 1;
   const bool relu1 = p.relu1 != 0;
-  const int q_first = 2 * p.Wp;
+  const int q_first = p.q_first;
   // this thread's 8 channels inside a chunk / a conv0 block row, and where their constants live
   const int chl = cbi * 32 + 8 * m4;
   const uint32_t sb1 = sbase + p.off_bias1 + 4 * chl, ss1 = sbase + p.off_scale1 + 4 * chl;
@@ -1111,7 +1119,7 @@ template <class G, class Bar>
 __device__ __forceinline__ void store_role(const Params& p, const DstMaps& tmD, Bar* bar, uint32_t sbase, int n_local,
                                            int tile0, int tile_stride) {
   const Geo<G> g{p};
-  const int q_first = 2 * p.Wp;
+  const int q_first = p.q_first;
   Tracer tr(p, 2);
   uint32_t c = 0;
   griddep_wait();  // earlier kernels in the stream may still be reading / writing the destination
@@ -1213,7 +1221,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
   tc_fence_after_sync();
   const uint32_t tmem = bar->tmem_base;
 
-  const int q_first = 2 * p.Wp;  // linear index of image 0, row 0, column 0
+  const int q_first = p.q_first;  // linear index of image 0, row 0, column 0
 
   // The three single-thread roles each run their whole loop inside ONE elect.sync region and advance
   // shared-memory descriptors by ADDITION: that keeps descriptor math in the uniform datapath.  Both
@@ -1231,14 +1239,16 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
       const int tile = blockIdx.x + it * gridDim.x;
       const int s = it % p.SA;
       const int q0 = q_first + tile * kTileM;
-      const int g_lo = (q0 - p.Wp - 1) / p.Wp;
-      const int g_hi = (q0 + kTileM + p.Wp) / p.Wp;
+      const int g_lo = (q0 - g.PH() * p.Wp - g.PW()) / p.Wp;
+      const int g_hi = (q0 + kTileM - 1 + (g.KH() - 1 - g.PH()) * p.Wp + (g.KW() - 1 - g.PW())) / p.Wp;
       const int nrows = g_hi - g_lo + 1;
       const uint32_t full = smem_u32(&bar->a_full[s]);
       const uint32_t stage = sbase + p.off_a + s * p.a_stage_bytes;
       mbar_expect_tx(full, (uint32_t)(nrows * g.nkb() * p.Wp * g.swb()));
+      // row g >= 1 of the padded space is row hp = (g - 1) % Hp of image (g - 1) / Hp, i.e. source row h = hp - ZR
+      // (negative: one of the zero rows above the image, filled by the TMA unit); g = 0 is all zero
       int n = (g_lo > 0) ? (g_lo - 1) / p.Hp : 0;
-      int h = (g_lo > 0) ? (g_lo - 1) - n * p.Hp - 1 : -2;  // -2: the all-zero row above everything
+      int h = (g_lo > 0) ? (g_lo - 1) - n * p.Hp - p.ZR : -p.ZR - 1;  // -ZR - 1: the all-zero row above everything
       uint32_t dst = stage;
       const uint32_t row_bytes = p.Wp * g.swb();
       for (int r = 0; r < nrows; ++r, dst += row_bytes) {
@@ -1249,10 +1259,10 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
 #pragma unroll
           for (int kb = 0; kb < g.nkb(); ++kb) tma_load_4d(dst + kb * p.a_kb_stride, &tmS.m[0], full, kb * g.swb(), 0, h, n);
         }
-        if (h == -2) {
-          h = -1;  // g = 1: the zero row above image 0
+        if (h == -p.ZR - 1) {
+          h = -p.ZR;  // g = 1: first row (zero row, if any) of image 0
         } else if (++h == p.H) {
-          h = -1;  // shared zero row between images
+          h = -p.ZR;  // zero rows shared by neighbouring images
           ++n;
         }
       }
@@ -1319,7 +1329,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
     // =============================== TMA producer: weights =================================
     if (elect_one()) {
       const bool c0_only = !G::is_static && p.conv0_only != 0;
-      const int n_w0 = 9 * g.nkb(), n_w1 = c0_only ? 0 : g.n_chunks() * g.nkb1();
+      const int n_w0 = g.KH() * g.KW() * g.nkb(), n_w1 = c0_only ? 0 : g.n_chunks() * g.nkb1();
       if (g.w0_res() || g.w1_res()) {
         const uint32_t full = smem_u32(&bar->res_full);
         mbar_expect_tx(full, (g.w0_res() ? n_w0 * g.w0_block_bytes() : 0) + (g.w1_res() ? n_w1 * g.w1_block_bytes() : 0));
@@ -1400,7 +1410,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
       uint32_t bs = 0, bph = 0;
       uint32_t c1count = 0;
       // position of the tile inside its halo window, advanced without divisions
-      int a_off_px = (q_first - p.Wp - 1 + (int)blockIdx.x * kTileM) % p.Wp;
+      int a_off_px = (q_first - g.PH() * p.Wp - g.PW() + (int)blockIdx.x * kTileM) % p.Wp;
       uint32_t sa = 0, a_par = 0;
       // halo hand-off: the TMA's own barrier, or (fused concat + ReLU) the clamp's
       const uint32_t a_go = clamp_a ? smem_u32(&bar->a_ready[0]) : smem_u32(&bar->a_full[0]);
@@ -1417,7 +1427,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
             mbar_wait(smem_u32(&bar->g1_prog[tap_i % kG1Ahead]), ((tap_i / kG1Ahead) - 1) & 1);
 #pragma unroll
           for (int kb = 0; kb < g.nkb(); ++kb) {
-            const int blk = (kh * 3 + kw) * g.nkb() + kb;  // block index inside the tile
+            const int blk = (kh * g.KW() + kw) * g.nkb() + kb;  // block index inside the tile
             uint64_t b_desc;
             uint32_t st = 0;
             if (g.w0_res()) {
@@ -1485,7 +1495,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
           const uint32_t d_tmem = tmem + ab * g.OC();
           const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swb()) >> 4);
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) gemm1_taps(kh, 0, 3, d_tmem, a_tile);
+          for (int kh = 0; kh < g.KH(); ++kh) gemm1_taps(kh, 0, g.KW(), d_tmem, a_tile);
           umma_commit(smem_u32(&bar->a_empty[sa]));
           umma_commit(smem_u32(&bar->acc0_full[ab]));
           tr.ev(11);
@@ -1549,10 +1559,10 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
               }
             }
             if (ok) {
-              gemm1_taps(g1_kh, 0, 3, d0, a_tile);
+              gemm1_taps(g1_kh, 0, g.KW(), d0, a_tile);
               did = true;
               idle = 0;
-              if (++g1_kh == 3) {
+              if (++g1_kh == g.KH()) {
                 umma_commit(smem_u32(&bar->a_empty[sa]));
                 umma_commit(smem_u32(&bar->acc0_full[g1_it % g.n_acc0()]));
                 tr.ev(11);
@@ -1577,7 +1587,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
             const uint32_t d_tmem = tmem + ab * g.OC();
             const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swb()) >> 4);
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) gemm1_taps(kh, 0, 3, d_tmem, a_tile);
+            for (int kh = 0; kh < g.KH(); ++kh) gemm1_taps(kh, 0, g.KW(), d_tmem, a_tile);
             umma_commit(smem_u32(&bar->a_empty[sa]));
             umma_commit(smem_u32(&bar->acc0_full[ab]));
             tr.ev(11);
@@ -1702,7 +1712,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();  // both CTAs' barriers exist before anyone arrives remotely
   tc_fence_after_sync();
   const uint32_t tmem = bar->tmem_base;
-  const int q_first = 2 * p.Wp;
+  const int q_first = p.q_first;
   const uint32_t a_origin = (uint32_t)p.Wp * G::swb;  // tile origin inside a halo stage (same in both CTAs)
 
   if (warp == 0) {

@@ -248,15 +248,18 @@ class Conv:
                  round0=NEAREST, round1=NEAREST, k=3, stride=1, pad=1):
         scale0 = np.ascontiguousarray(scale0, dtype=np.float32)
         scale1 = np.ascontiguousarray(scale1, dtype=np.float32)
-        self.desc = ConvDesc(n, ih, iw, ic, oc, oc1, k, k, stride, stride, pad, pad, dst_dt, bia0_dt, bia1_dt,
+        kh, kw = (k, k) if isinstance(k, int) else k
+        sh, sw = (stride, stride) if isinstance(stride, int) else stride
+        ph, pw = (pad, pad) if isinstance(pad, int) else pad
+        self.desc = ConvDesc(n, ih, iw, ic, oc, oc1, kh, kw, sh, sw, ph, pw, dst_dt, bia0_dt, bia1_dt,
                              int(relu0), int(relu1), round0, round1, scale0.size, scale1.size)
         h = C.c_void_p()
         keep = [np.ascontiguousarray(x) if x is not None else None for x in (wei_blocked, wei1_blocked, bias0, bias1)]
         check(lib().df_conv_create(C.byref(self.desc), _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]),
                                    scale0.ctypes.data, scale1.ctypes.data, C.byref(h)))
         self.handle = h.value
-        self.oh = (ih + 2 * pad - k) // stride + 1
-        self.ow = (iw + 2 * pad - k) // stride + 1
+        self.oh = (ih + 2 * ph - kh) // sh + 1
+        self.ow = (iw + 2 * pw - kw) // sw + 1
         self.out_c = oc1 if oc1 else oc
         self.dst_dt = dst_dt
 

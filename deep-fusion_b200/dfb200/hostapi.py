@@ -51,6 +51,9 @@ def lib():
                                       C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int]
         l.dfh_conv_sharded_create.restype = C.c_void_p
         l.dfh_conv_sharded_create.argtypes = [C.POINTER(C.c_int), C.c_int] + l.dfh_conv_create.argtypes
+        l.dfh_concat_conv_create.restype = C.c_void_p
+        l.dfh_concat_conv_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int] + l.dfh_conv_create.argtypes[1:]
+        l.dfh_concat_conv_is_fused.argtypes = [C.c_void_p]
         for f in ("dfh_sharded_upload", "dfh_sharded_sync", "dfh_sharded_download"):
             getattr(l, f).argtypes = [C.c_void_p]
             getattr(l, f).restype = None
@@ -146,6 +149,27 @@ def conv(src, wei, bia, stride, padding, dst, wei1x1=None, bia1x1=None, conv0_re
                               bia1x1.h if bia1x1 else None, dst.h, int(conv0_relu), s0.ctypes.data_as(fp), s0.size,
                               conv0_round_mode, int(conv1_relu), s1.ctypes.data_as(fp), s1.size, conv1_round_mode)
     return Op(h, (src, wei, bia, wei1x1, bia1x1, dst))
+
+
+def concat_conv(srcs, concat_relu, wei, bia, stride, padding, dst, wei1x1=None, bia1x1=None, conv0_relu=False,
+                conv0_scales=(1.0,), conv0_round_mode=NEAREST, conv1_relu=False, conv1_scales=(1.0,),
+                conv1_round_mode=NEAREST) -> Op:
+    """deepfusion::ext::concat_conv (include/deepfusion_ext.h): concat(+ReLU) fused into the conv's input load."""
+    s0 = np.ascontiguousarray(conv0_scales, dtype=np.float32)
+    s1 = np.ascontiguousarray(conv1_scales, dtype=np.float32)
+    st = (C.c_int * 2)(*stride)
+    pd = (C.c_int * 2)(*padding)
+    fp = C.POINTER(C.c_float)
+    arr = (C.c_void_p * len(srcs))(*[m.h for m in srcs])
+    h = lib().dfh_concat_conv_create(arr, len(srcs), int(concat_relu), wei.h, bia.h if bia else None, st, pd,
+                                     wei1x1.h if wei1x1 else None, bia1x1.h if bia1x1 else None, dst.h, int(conv0_relu),
+                                     s0.ctypes.data_as(fp), s0.size, conv0_round_mode, int(conv1_relu),
+                                     s1.ctypes.data_as(fp), s1.size, conv1_round_mode)
+    return Op(h, (list(srcs), wei, bia, wei1x1, bia1x1, dst))
+
+
+def concat_conv_is_fused(op: Op) -> bool:
+    return bool(lib().dfh_concat_conv_is_fused(op.h))
 
 
 class ShardedOp(Op):

@@ -631,6 +631,86 @@ private:
   int home_ = 0;
 };
 
+// ------------------------------------------------------------------ concat fused into the conv
+// ext::concat_conv(): the producer -> consumer pair op_concat<u8> (src/op_concat.cc:22-72) -> op_conv<T>
+// (src/op_conv.cc:140-260) as ONE operator.  The concatenated tensor is never materialised: the conv kernel's
+// halo loads read each K-block from the input that owns those channels (df_conv_create_concat).  Checks = the
+// concat's (same dtype / format / N,H,W, jit_concat_kernel.cc:178-190) + the conv's, made against a shape-only
+// stand-in for the concatenated source.  When the fused load cannot take the channel split (an input that is a
+// multiple of 16 but not of 32) the op runs the two kernels back to back on the device instead.
+class concat_conv_op : public conv_op {
+public:
+  concat_conv_op(std::unique_ptr<memory> &cat_shape, const std::vector<std::unique_ptr<memory>> &srcs, bool concat_relu,
+                 const std::unique_ptr<memory> &wei, const std::unique_ptr<memory> &bia, std::array<int, 2> sz_stride,
+                 std::array<int, 2> sz_padding, std::unique_ptr<memory> &dst, const std::vector<float> &conv0_scales,
+                 const std::vector<float> &conv1_scales, const std::unique_ptr<memory> &wei1x1,
+                 const std::unique_ptr<memory> &bia1x1, bool conv0_relu, bool conv1_relu, round_mode r0, round_mode r1)
+      : conv_op(cat_shape, wei, bia, sz_stride, sz_padding, dst, conv0_scales, conv1_scales, wei1x1, bia1x1, conv0_relu,
+                conv1_relu, r0, r1, /*create_handle=*/false),
+        relu_(concat_relu) {
+    cc_ = new cc_resources();
+    detail::adopt_resources(this, cc_);
+    cc_->shape = std::move(cat_shape);
+    for (auto &m : srcs) {
+      cc_->srcs.push_back(m.get());
+      cc_->ic.push_back(m->actual_dims()[3]);
+    }
+    const int8_t *w0 = static_cast<const int8_t *>(wei->data());
+    const int8_t *w1 = wei1x1 ? static_cast<const int8_t *>(wei1x1->data()) : nullptr;
+    const void *b0 = bia ? bia->data() : nullptr, *b1 = bia1x1 ? bia1x1->data() : nullptr;
+    int rc = df_conv_create_concat(&desc_, (int)cc_->ic.size(), cc_->ic.data(), concat_relu, w0, w1, b0, b1,
+                                   conv0_scales.data(), conv1_scales.data(), &cc_->handle);
+    if (rc == DF_E_UNSUPPORTED) {  // two kernels, concatenated tensor in a device buffer
+      fused_ = false;
+      rc = df_conv_create(&desc_, w0, w1, b0, b1, conv0_scales.data(), conv1_scales.data(), &cc_->handle);
+      if (rc == DF_E_UNSUPPORTED) error_and_exit("unsupported on B200 path: %s", df_last_error());
+      if (rc == 0) cuda_or_exit(df_malloc(cc_->shape->buffer_size(), &cc_->d_cat), "device allocation");
+    }
+    if (rc != 0) {
+      info("%s", df_last_error());
+      error_and_exit("Init Conv op failed!");
+    }
+  }
+
+  void launch(void *stream) override {
+    std::vector<const void *> ptrs(cc_->srcs.size());
+    for (size_t i = 0; i < ptrs.size(); ++i) ptrs[i] = mirror(*cc_->srcs[i]);
+    if (fused_) {
+      cuda_or_exit(df_conv_run_concat(cc_->handle, ptrs.data(), mirror(*dst_), desc_.n, stream), "concat+conv launch");
+    } else {
+      cuda_or_exit(df_concat_run(DF_U8, relu_, (int)ptrs.size(), ptrs.data(), cc_->ic.data(), cc_->d_cat,
+                                 (long)desc_.n * desc_.ih * desc_.iw, stream), "concat launch");
+      cuda_or_exit(df_conv_run(cc_->handle, static_cast<const uint8_t *>(cc_->d_cat), mirror(*dst_), desc_.n, stream), "conv launch");
+    }
+  }
+  int launches() const override { return fused_ ? 1 : 2; }
+  bool fused() const { return fused_; }
+
+protected:
+  void infer() override {
+    for (memory *m : cc_->srcs) cuda_or_exit(df_h2d(mirror(*m), m->data(), m->buffer_size(), nullptr), "concat+conv H2D");
+    launch(nullptr);
+    cuda_or_exit(df_d2h(dst_->data(), mirror(*dst_), dst_->buffer_size(), nullptr), "concat+conv D2H");
+    cuda_or_exit(df_stream_sync(nullptr), "concat+conv sync");
+  }
+  const char *name() override { return "concat+conv"; }
+
+private:
+  struct cc_resources : detail::op_resources {
+    std::unique_ptr<memory> shape;  // shape-only stand-in for the concatenated source (its buffer is never touched)
+    std::vector<memory *> srcs;
+    std::vector<int> ic;
+    df_conv *handle = nullptr;
+    void *d_cat = nullptr;
+    ~cc_resources() override {
+      df_conv_destroy(handle);
+      if (d_cat) df_free(d_cat);
+    }
+  };
+  cc_resources *cc_ = nullptr;
+  bool relu_, fused_ = true;
+};
+
 }  // namespace
 
 // ---------------------------------------------------------------------------- factories
@@ -704,6 +784,35 @@ std::unique_ptr<op> conv_sharded(const std::vector<int> &devices, const std::uni
                                  round_mode conv1_round_mode) {
   return std::unique_ptr<op>(new sharded_conv_op(devices, src, wei, bia, sz_stride, sz_padding, dst, conv0_scales, conv1_scales,
                                                  wei1x1, bia1x1, conv0_relu, conv1_relu, conv0_round_mode, conv1_round_mode));
+}
+std::unique_ptr<op> concat_conv(const std::vector<std::unique_ptr<memory>> &srcs, bool concat_relu,
+                                const std::unique_ptr<memory> &wei, const std::unique_ptr<memory> &bia,
+                                std::array<int, 2> sz_stride, std::array<int, 2> sz_padding,
+                                const std::unique_ptr<memory> &wei1x1, const std::unique_ptr<memory> &bia1x1,
+                                std::unique_ptr<memory> &dst, bool conv0_relu, std::vector<float> conv0_scales,
+                                round_mode conv0_round_mode, bool conv1_relu, std::vector<float> conv1_scales,
+                                round_mode conv1_round_mode) {
+  // the concat half of the checks (jit_concat_kernel::init_conf, src/jit_concat_kernel.cc:130-197, u8 only here)
+  if (srcs.empty() || !dst) error_and_exit("Init Concat op failed!");
+  const memory::dims d0 = srcs[0]->actual_dims();
+  int channels = 0;
+  for (auto &m : srcs) {
+    const memory::dims d = m->actual_dims();
+    if (m->dim_format() != memory::format::nhwc || m->data_type() != memory::dtype::u8 || d.size() != 4 || d[0] != d0[0] ||
+        d[1] != d0[1] || d[2] != d0[2] || d[3] % 16) {
+      info("concat_conv inputs must be nhwc u8 with equal N, H, W and channels in multiples of 16");
+      error_and_exit("Init Concat op failed!");
+    }
+    channels += d[3];
+  }
+  std::unique_ptr<memory> shape(new memory(memory::nchw_dims{d0[0], channels, d0[1], d0[2]}, memory::format::nhwc, memory::dtype::u8));
+  return std::unique_ptr<op>(new concat_conv_op(shape, srcs, concat_relu, wei, bia, sz_stride, sz_padding, dst, conv0_scales,
+                                                conv1_scales, wei1x1, bia1x1, conv0_relu, conv1_relu, conv0_round_mode,
+                                                conv1_round_mode));
+}
+bool concat_conv_is_fused(op &o) {
+  concat_conv_op *c = dynamic_cast<concat_conv_op *>(&o);
+  return c && c->fused();
 }
 void sharded_upload(op &o) {
   sharded_conv_op *s = dynamic_cast<sharded_conv_op *>(&o);

@@ -81,6 +81,26 @@ dfh_op *dfh_conv_sharded_create(const int *devices, int n_devices, dfh_memory *s
                            conv1_relu != 0, sc1, (round_mode)r1);
   return h;
 }
+dfh_op *dfh_concat_conv_create(dfh_memory *const *srcs, int n, int concat_relu, dfh_memory *wei, dfh_memory *bia,
+                               const int stride[2], const int padding[2], dfh_memory *wei1x1, dfh_memory *bia1x1,
+                               dfh_memory *dst, int conv0_relu, const float *s0, int n0, int r0, int conv1_relu,
+                               const float *s1, int n1, int r1) {
+  static const std::unique_ptr<memory> none;
+  std::vector<float> sc0(s0, s0 + (n0 > 0 ? n0 : 0)), sc1;
+  if (sc0.empty()) sc0.push_back(1.f);
+  if (s1 && n1 > 0) sc1.assign(s1, s1 + n1);
+  if (sc1.empty()) sc1.push_back(1.f);
+  std::vector<std::unique_ptr<memory>> v;  // lend the pointers for the duration of the call (see dfh_concat_create)
+  for (int i = 0; i < n; ++i) v.emplace_back(srcs[i]->m.release());
+  dfh_op *h = new dfh_op();
+  const std::array<int, 2> st = {stride[0], stride[1]}, pd = {padding[0], padding[1]};
+  h->o = ext::concat_conv(v, concat_relu != 0, wei->m, bia ? bia->m : none, st, pd, wei1x1 ? wei1x1->m : none,
+                          bia1x1 ? bia1x1->m : none, dst->m, conv0_relu != 0, sc0, (round_mode)r0, conv1_relu != 0, sc1,
+                          (round_mode)r1);
+  for (int i = 0; i < n; ++i) srcs[i]->m.reset(v[i].release());
+  return h;
+}
+int dfh_concat_conv_is_fused(dfh_op *op) { return ext::concat_conv_is_fused(*op->o) ? 1 : 0; }
 void dfh_sharded_upload(dfh_op *op) { ext::sharded_upload(*op->o); }
 void dfh_sharded_sync(dfh_op *op) { ext::sharded_sync(*op->o); }
 void dfh_sharded_download(dfh_op *op) { ext::sharded_download(*op->o); }

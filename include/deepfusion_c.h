@@ -38,6 +38,13 @@ dfh_op *dfh_conv_sharded_create(const int *devices, int n_devices, dfh_memory *s
                                 dfh_memory *dst, int conv0_relu, const float *conv0_scales, int n_conv0_scales,
                                 int conv0_round_mode, int conv1_relu, const float *conv1_scales, int n_conv1_scales,
                                 int conv1_round_mode);
+/* ext::concat_conv(): concat(+ReLU) of `srcs` fused into the conv's input load */
+dfh_op *dfh_concat_conv_create(dfh_memory *const *srcs, int n_srcs, int concat_relu, dfh_memory *wei, dfh_memory *bia,
+                               const int stride[2], const int padding[2], dfh_memory *wei1x1, dfh_memory *bia1x1,
+                               dfh_memory *dst, int conv0_relu, const float *conv0_scales, int n_conv0_scales,
+                               int conv0_round_mode, int conv1_relu, const float *conv1_scales, int n_conv1_scales,
+                               int conv1_round_mode);
+int dfh_concat_conv_is_fused(dfh_op *op);
 void dfh_sharded_upload(dfh_op *op);   /* slabs -> devices (device-resident timing) */
 void dfh_sharded_sync(dfh_op *op);     /* wait for every device */
 void dfh_sharded_download(dfh_op *op); /* devices -> host destination, synchronous */

@@ -34,6 +34,20 @@ std::unique_ptr<op> conv_sharded(const std::vector<int> &devices, const std::uni
                                  std::vector<float> conv0_scales = {1.f}, round_mode conv0_round_mode = round_mode::nearest,
                                  bool conv1_relu = false, std::vector<float> conv1_scales = {1.f},
                                  round_mode conv1_round_mode = round_mode::nearest);
+// concat(+ReLU) fused into the conv that consumes it: the reference's concat() followed by conv() /
+// fused conv(), as one operator whose kernel loads its input halo straight from `srcs` -- the concatenated tensor
+// is never written.  `srcs` are nhwc u8 memories with equal N, H, W; the remaining arguments are conv()'s.  The
+// result is bit-identical to concat(srcs, tmp, concat_relu) followed by conv(tmp, ...).  Inputs whose channel
+// count is a multiple of 16 but not of 32 make the op run the two kernels back to back (concat_conv_is_fused()).
+std::unique_ptr<op> concat_conv(const std::vector<std::unique_ptr<memory>> &srcs, bool concat_relu,
+                                const std::unique_ptr<memory> &wei, const std::unique_ptr<memory> &bia,
+                                std::array<int, 2> sz_stride, std::array<int, 2> sz_padding,
+                                const std::unique_ptr<memory> &wei1x1, const std::unique_ptr<memory> &bia1x1,
+                                std::unique_ptr<memory> &dst, bool conv0_relu = false,
+                                std::vector<float> conv0_scales = {1.f}, round_mode conv0_round_mode = round_mode::nearest,
+                                bool conv1_relu = false, std::vector<float> conv1_scales = {1.f},
+                                round_mode conv1_round_mode = round_mode::nearest);
+bool concat_conv_is_fused(op &o);
 // device-resident use of a sharded op (timing): upload the slabs once, submit_device() launches the kernels on
 // every device, sharded_sync() waits for all of them, sharded_download() brings the result back
 void sharded_upload(op &o);

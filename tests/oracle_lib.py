@@ -49,7 +49,10 @@ def _p(a):
 
 def make_desc(n, ih, iw, ic, oc, oc1, dst_dt, bia0_dt=UNDEF, bia1_dt=UNDEF, k=3, stride=1, pad=1,
               relu0=0, relu1=0, round0=0, round1=0, nscale0=1, nscale1=1, literal=0):
-    return ConvDesc(n, ih, iw, ic, oc, oc1, k, k, stride, stride, pad, pad, dst_dt, bia0_dt, bia1_dt,
+    kh, kw = (k, k) if isinstance(k, int) else k
+    sh, sw = (stride, stride) if isinstance(stride, int) else stride
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    return ConvDesc(n, ih, iw, ic, oc, oc1, kh, kw, sh, sw, ph, pw, dst_dt, bia0_dt, bia1_dt,
                     relu0, relu1, round0, round1, nscale0, nscale1, literal)
 
 

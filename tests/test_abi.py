@@ -90,11 +90,13 @@ def test_conv_create_rejects_like_reference_without_touching_the_gpu():
     assert _create(round1=3) == INVALID
     assert _create(ph=6, pw=6, ih=8, iw=8) == INVALID      # l_pad > ur_w (:657-661)
     # accepted by the reference, outside the B200 path: documented as unsupported, never a CPU fallback
-    assert _create(kh=1, kw=1, ph=0, pw=0) == UNSUPPORTED
+    assert _create(kh=3, kw=3, ph=2, pw=2, ih=8, iw=8) == UNSUPPORTED   # output larger than the input
     assert _create(sh=2, sw=2) == UNSUPPORTED
     assert _create(oc=512) == UNSUPPORTED
-    # the conv0-only operator (oc1 = 0) is on the B200 path: it gets as far as the device
+    # the conv0-only operator (oc1 = 0) and other stride-1 windows are on the B200 path: they get as far as the device
     assert _create(oc1=0) not in (INVALID, UNSUPPORTED)
+    assert _create(kh=1, kw=1, ph=0, pw=0) not in (INVALID, UNSUPPORTED)
+    assert _create(kh=5, kw=5, ph=2, pw=2) not in (INVALID, UNSUPPORTED)
 
 
 def test_compute_entry_points_fail_loudly_without_a_device():

@@ -125,6 +125,34 @@ def test_concat_feeds_conv_on_device(H):
     assert np.array_equal(dst.array(), want)
 
 
+@pytest.mark.parametrize("ics,fused", [((64, 128, 32, 32), True), ((16, 48, 64), False)], ids=["fused", "two_kernels"])
+def test_concat_conv_submit(H, ics, fused):
+    """ext::concat_conv through the C++ API: submit() == oracle concat followed by oracle conv; channel splits the
+    fused load cannot take (multiples of 16 that are not multiples of 32) run as two kernels with the same result."""
+    from dfb200 import synth
+    n, h, w, ic = 2, 14, 14, sum(ics)
+    ins = [synth.uniform_int(20 + i, (n, h, w, c), 0, 255, np.uint8) for i, c in enumerate(ics)]
+    srcs = [H.Memory((n, c, h, w), "nhwc", "u8") for c in ics]
+    for m, a in zip(srcs, ins):
+        m.set(a)
+    c = cases.ConvCase("cc", n, h, w, ic, 64, 128, "u8", "s32", "s32", k0=13)
+    _, w0, w1, b0, b1, s0, s1 = c.tensors()
+    wb, w1b = c.blocked(w0, w1)
+    wei = H.Memory((64, ic, 3, 3), "OIhw4i16o4i", "s8"); wei.array().reshape(-1)[...] = wb
+    wei1 = H.Memory((128, 64, 1, 1), "OIhw4i16o4i", "s8"); wei1.array().reshape(-1)[...] = w1b
+    bia = H.Memory((64,), "x", "s32", nchw=False); bia.set(b0)
+    bia1 = H.Memory((128,), "x", "s32", nchw=False); bia1.set(b1)
+    dst = H.Memory((n, 128, h, w), "nhwc", "u8")
+    op = H.concat_conv(srcs, True, wei, bia, (1, 1), (1, 1), dst, wei1x1=wei1, bia1x1=bia1, conv0_scales=s0, conv1_scales=s1)
+    assert H.concat_conv_is_fused(op) == fused
+    assert op.launches() == (1 if fused else 2)
+    op.submit()
+    d = O.make_desc(n, h, w, ic, 64, 128, O.U8, O.S32, O.S32, nscale0=64, nscale1=128)
+    want = O.conv(d, O.concat(O.U8, True, ins), wb, b0, s0, w1b, b1, s1)
+    assert want.any()
+    assert np.array_equal(dst.array(), want)
+
+
 def _conv_memories(H, c, n=None):
     n = n or c.n
     src_a, w0, w1, b0, b1, s0, s1 = cases.ConvCase(c.name, n, c.h, c.w, c.ic, c.oc, c.oc1, c.dst, c.b0, c.b1, c.r0, c.r1,

@@ -351,3 +351,73 @@ def test_concat_fused_rejects_what_it_cannot_load(df):
     with pytest.raises(df.DfError) as e:
         df.ConcatConv(1, 4, 4, (16, 32), True, 32, 0, df.U8, wb, None, None, None, np.ones(32, np.float32))
     assert e.value.code == -2
+
+
+# ------------------------------------------------------------------------------ general conv0 windows
+# jit_conv_kernel::init_conf (src/jit_conv_kernel.cc:586-661) accepts any kh x kw window; the
+# B200 kernel runs every stride-1 window whose output is not larger than its input (2 p <= k - 1), for the
+# conv-only operator and for the fused pair alike.  Checker: the scalar oracle (general in k / s / p).
+WINDOWS = [
+    # kh, kw, ph, pw
+    (1, 1, 0, 0), (3, 3, 0, 0), (3, 3, 1, 0), (5, 5, 2, 2), (5, 5, 1, 2), (7, 7, 3, 3), (1, 3, 0, 1), (3, 1, 1, 0),
+    (2, 2, 0, 0), (1, 7, 0, 3),
+]
+
+
+def _window_case(kh, kw, ic, oc, seed=2):
+    w0 = cases.synth.wei_s8(seed, (oc, ic, kh, kw))
+    return cases.layout.oihw_to_blocked(w0)
+
+
+@pytest.mark.parametrize("dst", ["u8", "s32"])
+@pytest.mark.parametrize("win", WINDOWS, ids=lambda w: "k%dx%d_p%dx%d" % w)
+def test_conv0_only_general_window(df, win, dst):
+    kh, kw, ph, pw = win
+    n, h, w, ic, oc = 2, 11, 13, 32, 48
+    src = cases.synth.src_u8(1, (n, h, w, ic))
+    wb = _window_case(kh, kw, ic, oc)
+    b0 = cases.synth.bias(4, oc, "s32")
+    s0 = cases.synth.channel_scales(oc, 10 + (kh * kw > 8))
+    d = O.make_desc(n, h, w, ic, oc, 0, cases.DT[dst], O.S32, O.UNDEF, k=(kh, kw), pad=(ph, pw), relu0=1, nscale0=oc)
+    want = O.conv(d, src, wb, b0, s0)
+    op = df.Conv(n, h, w, ic, oc, 0, cases.DT[dst], wb, None, b0, None, s0, (1.0,), df.S32, df.UNDEF, relu0=True,
+                 k=(kh, kw), pad=(ph, pw))
+    got = op(src)
+    op.close()
+    assert got.shape == want.shape
+    _assert_same(got, want, dst)
+    assert want.any()
+
+
+@pytest.mark.parametrize("win", [(1, 1, 0, 0), (5, 5, 2, 2), (3, 3, 0, 0), (1, 3, 0, 1), (7, 7, 3, 3)], ids=lambda w: "k%dx%d_p%dx%d" % w)
+def test_fused_conv_general_window(df, win):
+    """kh x kw conv + ReLU + 1x1 conv + ReLU: the reference's fused operator with another first-stage window."""
+    kh, kw, ph, pw = win
+    n, h, w, ic, oc, oc1 = 2, 12, 10, 64, 64, 144
+    src = cases.synth.src_u8(1, (n, h, w, ic))
+    wb = _window_case(kh, kw, ic, oc)
+    w1b = cases.layout.oihw_to_blocked(cases.synth.wei_s8(3, (oc1, oc)).reshape(oc1, oc, 1, 1))
+    b0, b1 = cases.synth.bias(4, oc, "s32"), cases.synth.bias(5, oc1, "s32")
+    s0, s1 = cases.synth.channel_scales(oc, 10 + (kh * kw > 8) + (kh * kw > 24)), cases.synth.channel_scales(oc1, 12)
+    d = O.make_desc(n, h, w, ic, oc, oc1, O.U8, O.S32, O.S32, k=(kh, kw), pad=(ph, pw), nscale0=oc, nscale1=oc1)
+    want = O.conv(d, src, wb, b0, s0, w1b, b1, s1)
+    op = df.Conv(n, h, w, ic, oc, oc1, df.U8, wb, w1b, b0, b1, s0, s1, df.S32, df.S32, k=(kh, kw), pad=(ph, pw))
+    got = op(src)
+    op.close()
+    _assert_same(got, want, "u8")
+    assert want.any()
+
+
+def test_one_by_one_conv_full_width(df):
+    """1x1 p0: no zero columns at all (Wp == W when W is aligned) -- every tile row is a real pixel."""
+    n, h, w, ic, oc = 3, 8, 16, 128, 256
+    src = cases.synth.src_u8(1, (n, h, w, ic))
+    wb = _window_case(1, 1, ic, oc)
+    s0 = cases.synth.channel_scales(oc, 9)
+    d = O.make_desc(n, h, w, ic, oc, 0, O.U8, O.UNDEF, O.UNDEF, k=1, pad=0, nscale0=oc)
+    want = O.conv(d, src, wb, None, s0)
+    op = df.Conv(n, h, w, ic, oc, 0, df.U8, wb, None, None, None, s0, (1.0,), k=1, pad=0)
+    assert abs(op.info().mma_efficiency - 1.0) < 0.2
+    got = op(src)
+    op.close()
+    _assert_same(got, want, "u8")

@@ -92,3 +92,38 @@ def test_concat_oracle_equals_reference(dt, src_dims, data, relu):
     want = O.ref_concat(O.DT_OF[dt], relu, ins)
     got = O.concat(O.DT_OF[dt], relu, ins)
     assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
+GENERAL = [  # (kh, kw), stride, pad -- windows jit_conv_kernel::init_conf accepts besides 3x3 s1 p1
+    ((1, 1), 1, 0), ((3, 3), 1, 0), ((3, 3), 1, (1, 0)), ((5, 5), 1, 2), ((5, 5), 1, (1, 2)), ((7, 7), 1, 3), ((1, 3), 1, (0, 1)),
+    ((3, 1), 1, (1, 0)), ((2, 2), 1, 0), ((3, 3), 2, 1), ((1, 1), 2, 0), ((5, 5), 2, 2), ((3, 3), (2, 1), 1), ((7, 7), 2, 3),
+    ((3, 3), 1, 2), ((2, 2), 2, 0),
+]
+
+
+@pytest.mark.parametrize("k,stride,pad", GENERAL, ids=lambda v: str(v).replace(" ", ""))
+def test_general_window_oracle_equals_reference(k, stride, pad):
+    """conv-only operator with other windows, strides and paddings: the reference's generator vs the oracle."""
+    n, h, w, ic, oc = 2, 11, 13, 32, 48
+    src = cases.synth.src_u8(1, (n, h, w, ic))
+    wb = cases.layout.oihw_to_blocked(cases.synth.wei_s8(2, (oc, ic) + tuple(k)))
+    b0 = cases.synth.bias(4, oc, "s32")
+    s0 = cases.synth.channel_scales(oc, 10 + (k[0] * k[1] > 8))
+    for dst in ("u8", "s32"):
+        d = O.make_desc(n, h, w, ic, oc, 0, O.DT_OF[dst], O.S32, O.UNDEF, k=k, stride=stride, pad=pad, relu0=1, nscale0=oc)
+        want = O.ref_conv(d, src, wb, b0, s0)
+        got = O.conv(d, src, wb, b0, s0)
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
+@pytest.mark.parametrize("k,pad", [(1, 0), (5, 2), ((1, 3), (0, 1)), (7, 3)], ids=str)
+def test_fused_general_window_oracle_equals_reference(k, pad):
+    n, h, w, ic, oc, oc1 = 2, 12, 10, 64, 64, 144
+    kk = (k, k) if isinstance(k, int) else k
+    src = cases.synth.src_u8(1, (n, h, w, ic))
+    wb = cases.layout.oihw_to_blocked(cases.synth.wei_s8(2, (oc, ic) + tuple(kk)))
+    w1b = cases.layout.oihw_to_blocked(cases.synth.wei_s8(3, (oc1, oc)).reshape(oc1, oc, 1, 1))
+    b0, b1 = cases.synth.bias(4, oc, "s32"), cases.synth.bias(5, oc1, "s32")
+    s0, s1 = cases.synth.channel_scales(oc, 12), cases.synth.channel_scales(oc1, 12)
+    d = O.make_desc(n, h, w, ic, oc, oc1, O.U8, O.S32, O.S32, k=k, pad=pad, nscale0=oc, nscale1=oc1)
+    assert np.array_equal(O.conv(d, src, wb, b0, s0, w1b, b1, s1), O.ref_conv(d, src, wb, b0, s0, w1b, b1, s1))
