@@ -70,7 +70,7 @@ struct df_conv {
   df_conv() : desc(), prm(), kernel{nullptr, nullptr}, pair(false), pair_kernel{nullptr, nullptr}, pair_prm(), pair_smem(0),
               tmW0h(), tmW1h(), geom_id(0), smem_bytes(0), device(0), sms(0), d_w0(nullptr),
               d_w1(nullptr), d_bias0(nullptr), d_scale0(nullptr), d_bias1(nullptr), d_scale1(nullptr), d_k1(nullptr),
-              tmW0(), tmW1(), a_maps(), d_maps(), a_next(0), d_next(0), trace(nullptr), trace_cap(0), n_src(1), src_ic() {}
+              tmW0(), tmW1(), a_maps(), d_maps(), a_next(0), d_next(0), trace(nullptr), trace_cap(0), n_src(1), src_ic(), parts() {}
   df_conv_desc desc;
   Params prm;        // everything except n-dependent fields and dst
   KernelFn kernel;
@@ -107,6 +107,16 @@ struct df_conv {
   int trace_cap;
   int n_src;            // inputs whose channel concatenation is the conv's source (1: plain conv)
   int src_ic[kMaxSrc];  // their channel counts
+  // Composite operators (this handle then owns no kernel of its own):
+  //   groups  : the conv-only operator with more than 256 output channels = one launch per group of <= 256
+  //             channels, each writing its channel range of the same destination pixels;
+  //   chained : the fused operator whose first stage has more than 256 output channels (or does not fit one
+  //             CTA's shared memory) = conv-only stage -> u8 intermediate in device memory `d_mid` (L2-resident
+  //             for the batches this is used with) -> 1x1 conv-only stage.  Same arithmetic, bit for bit: the
+  //             fused kernel's intermediate IS the conv-only operator's u8 output.
+  std::vector<df_conv*> parts;
+  bool chained = false;
+  void* d_mid = nullptr;
 };
 
 namespace {
@@ -196,6 +206,79 @@ int encode_2d(CUtensorMap* tm, void* base, int row_bytes, long rows, int box_row
 
 }  // namespace
 
+static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic, int concat_relu, const int8_t* wei,
+                            const int8_t* wei1, const void* bia0, const void* bia1, const float* scale0,
+                            const float* scale1, df_conv** out);
+
+static size_t dt_bytes(int dt) { return (dt == DF_F32 || dt == DF_S32) ? 4 : 1; }
+
+// Composite operators (see df_conv::parts).  Everything the reference accepts for these shapes
+// (src/jit_conv_kernel.cc:586-661 has no upper bound on oc) runs on the device; nothing falls back to the CPU.
+static int conv_create_composite(const df_conv_desc* d, const int8_t* wei, const int8_t* wei1, const void* bia0,
+                                 const void* bia1, const float* scale0, const float* scale1, df_conv** out) {
+  df_conv* op = new df_conv();
+  op->desc = *d;
+  int rc = 0;
+  if (d->oc1 == 0) {
+    // ---- conv-only, oc > 256: groups of <= 256 output channels.  OIhw4i16o4i is output-block major, so the
+    //      weights of channels [o0, o0 + n) are one contiguous slice (jit_conv_kernel.cc:333-338).
+    for (int o0 = 0; o0 < d->oc && rc == 0; o0 += 256) {
+      df_conv_desc g = *d;
+      g.oc = d->oc - o0 < 256 ? d->oc - o0 : 256;
+      g.nscale0 = d->nscale0 > 1 ? g.oc : 1;
+      const int8_t* w = wei + (size_t)(o0 / 16) * (d->ic / 16) * d->kh * d->kw * 256;
+      const void* b = bia0 ? static_cast<const char*>(bia0) + (size_t)o0 * dt_bytes(d->bia0_dt) : nullptr;
+      df_conv* part = nullptr;
+      rc = conv_create_impl(&g, 0, nullptr, 0, w, nullptr, b, nullptr, scale0 + (d->nscale0 > 1 ? o0 : 0), nullptr, &part);
+      if (rc) break;
+      part->prm.dst_pitch = d->oc;
+      part->prm.dst_ch0 = o0;
+      op->parts.push_back(part);
+    }
+  } else {
+    // ---- fused, first stage too wide for one accumulator / one CTA's shared memory: conv-only stage with u8
+    //      destination (ReLU + round0 + unsigned saturation = the fused kernel's intermediate, jit_conv_kernel.cc
+    //      :264-277), then the 1x1 stage as a conv-only operator over that intermediate
+    op->chained = true;
+    df_conv_desc a = *d;
+    a.oc1 = 0;
+    a.dst_dt = DF_U8;
+    a.bia1_dt = DF_UNDEF;
+    a.relu0 = 1;
+    df_conv_desc b = *d;
+    b.ih = (d->ih + 2 * d->ph - d->kh) / d->sh + 1;
+    b.iw = (d->iw + 2 * d->pw - d->kw) / d->sw + 1;
+    b.ic = d->oc;
+    b.oc = d->oc1;
+    b.oc1 = 0;
+    b.kh = b.kw = b.sh = b.sw = 1;
+    b.ph = b.pw = 0;
+    b.bia0_dt = d->bia1_dt;
+    b.bia1_dt = DF_UNDEF;
+    b.relu0 = d->relu1;
+    b.round0 = d->round1;
+    b.nscale0 = d->nscale1;
+    df_conv *pa = nullptr, *pb = nullptr;
+    if (!wei1 || !scale1) rc = df::fail(DF_E_INVALID, "conv: null 1x1 weights / scales");
+    if (!rc) rc = conv_create_impl(&a, 0, nullptr, 0, wei, nullptr, bia0, nullptr, scale0, nullptr, &pa);
+    if (pa) op->parts.push_back(pa);
+    if (!rc) rc = conv_create_impl(&b, 0, nullptr, 0, wei1, nullptr, bia1, nullptr, scale1, nullptr, &pb);
+    if (pb) op->parts.push_back(pb);
+    if (!rc) {
+      cudaError_t e = cudaMalloc(&op->d_mid, (size_t)d->n * b.ih * b.iw * d->oc);
+      if (e != cudaSuccess) rc = df::fail((int)e, "cudaMalloc(intermediate) failed: %s", cudaGetErrorString(e));
+    }
+  }
+  if (rc) {
+    df_conv_destroy(op);
+    return rc;
+  }
+  cudaGetDevice(&op->device);
+  op->n_src = 1;
+  *out = op;
+  return 0;
+}
+
 // n_src == 0: plain conv.  n_src >= 1: the source is the channel concatenation of n_src tensors (fused concat)
 static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic, int concat_relu, const int8_t* wei,
                             const int8_t* wei1, const void* bia0, const void* bia1, const float* scale0,
@@ -229,15 +312,18 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   if (!conv0_only && (!wei1 || !scale1)) return df::fail(DF_E_INVALID, "conv: null 1x1 weights / scales");
   // any window with stride 1 whose output is not larger than its input (2 p <= k - 1: every "same" or "valid"
   // convolution); taps are constant offsets in the linearised padded pixel space (conv_kernels.cuh)
-  if (d->sh != 1 || d->sw != 1) return df::fail(DF_E_UNSUPPORTED, "B200 path supports stride 1 only (got %d x %d)", d->sh, d->sw);
+  if (fused_cat && (d->sh != 1 || d->sw != 1)) return df::fail(DF_E_UNSUPPORTED, "concat+conv: k3 s1 p1 only");
   if (2 * d->ph > d->kh - 1 || 2 * d->pw > d->kw - 1)
     return df::fail(DF_E_UNSUPPORTED, "B200 path supports padding <= (kernel - 1) / 2 (got k %dx%d p %dx%d)", d->kh, d->kw, d->ph, d->pw);
   if (d->kh * d->kw > 121) return df::fail(DF_E_UNSUPPORTED, "B200 path supports windows of at most 121 taps");
   if (fused_cat && (d->kh != 3 || d->kw != 3 || d->ph != 1 || d->pw != 1))
     return df::fail(DF_E_UNSUPPORTED, "concat+conv: k3 s1 p1 only");
-  if (d->oc > 256) return df::fail(DF_E_UNSUPPORTED, "B200 path supports conv0 oc <= 256 (got %d)", d->oc);
+  if (d->oc > 256) {  // more channels than one TMEM accumulator: composite operator
+    if (fused_cat) return df::fail(DF_E_UNSUPPORTED, "concat+conv: conv0 oc <= 256 (got %d)", d->oc);
+    return conv_create_composite(d, wei, wei1, bia0, bia1, scale0, scale1, out);
+  }
   const int zr_w = d->pw > d->kw - 1 - d->pw ? d->pw : d->kw - 1 - d->pw;  // zero columns between rows
-  if (d->iw + zr_w > 256) return df::fail(DF_E_UNSUPPORTED, "B200 path supports padded width <= 256 (TMA box limit)");
+  if (fused_cat && d->iw + zr_w > 256) return df::fail(DF_E_UNSUPPORTED, "concat+conv: padded width <= 256");
 
   df_conv* op = new df_conv();
   op->desc = *d;
@@ -277,16 +363,25 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   p.PW = d->pw;
   p.OH = d->ih + 2 * d->ph - d->kh + 1;
   p.OW = d->iw + 2 * d->pw - d->kw + 1;
+  p.SH = d->sh;
+  p.SW = d->sw;
+  p.OHS = (d->ih + 2 * d->ph - d->kh) / d->sh + 1;
+  p.OWS = (d->iw + 2 * d->pw - d->kw) / d->sw + 1;
   p.ZR = d->ph > d->kh - 1 - d->ph ? d->ph : d->kh - 1 - d->ph;
   p.Hp = d->ih + p.ZR;
   const int wp_align = 128 / p.swb;  // every halo row must start 128 B aligned for TMA
   p.Wp = (d->iw + zr_w + wp_align - 1) / wp_align * wp_align;
+  p.n_box = (p.Wp + 255) / 256;  // TMA boxes are at most 256 positions wide
+  p.box_w = ((p.Wp + p.n_box - 1) / p.n_box + wp_align - 1) / wp_align * wp_align;
+  p.Wp = p.n_box * p.box_w;
   p.q_first = (p.ZR + 1) * p.Wp;
   // rows touched by the 128 + (KH - 1) * Wp + KW - 1 consecutive positions a tile's taps read
   p.NR = (kTileM + (p.KH - 1) * p.Wp + p.KW - 3) / p.Wp + 2;
   p.r8_dw = 8 % p.Wp;
   p.r8_dn = (8 / p.Wp) / p.Hp;
   p.r8_dh = (8 / p.Wp) % p.Hp;
+  p.dst_pitch = p.OC1;
+  p.dst_ch0 = 0;
   p.nc1 = p.OC1 < 128 ? p.OC1 : 128;
   p.n_chunks = (p.OC1 + p.nc1 - 1) / p.nc1;
   p.n_acc0 = d->oc <= 128 ? 2 : 1;
@@ -383,7 +478,9 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   // ---- shared memory plan.  plan(nm, stage): nm intermediate tiles; stage = staged 1-byte output wanted
   const int oc1_pad = p.n_chunks * p.nc1;
   const uint32_t avail = kSmemLimit - 1024;  // base alignment slack
-  auto plan = [&](int nm, bool stage) -> bool {
+  // sa_min: halo stages when the weights stream (2; 1 as a last resort for shapes whose halo alone is > 100 KB --
+  // loads and MMAs of successive tiles then alternate instead of overlapping)
+  auto plan = [&](int nm, bool stage, int sa_min = 2) -> bool {
     uint32_t off = 1024;  // barriers
     p.off_bias0 = off;
     off += align_up(p.OC * 4, 128);
@@ -421,8 +518,8 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
     } else {
       const uint32_t stage_w0 = align_up(p.w0_block_bytes, 1024);
       const uint32_t stage_both = align_up(p.w0_block_bytes > p.w1_block_bytes ? p.w0_block_bytes : p.w1_block_bytes, 1024);
-      p.SA = 2;
-      if (fixed + 2 * p.a_stage_bytes + w1_bytes + 3 * stage_w0 <= avail) {
+      p.SA = sa_min;
+      if (fixed + p.SA * p.a_stage_bytes + w1_bytes + 3 * stage_w0 <= avail) {
         p.w0_res = 0;
         p.w1_res = 1;
         p.off_w1 = fixed;
@@ -459,7 +556,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   // and -- when it fits -- keep TWO intermediate tiles, so that the conv0 epilogue of tile t+1 does not have
   // to wait for GEMM2 of tile t (profiles/r02_knockout.log: with one tile the two strictly alternate and
   // their hand-offs alone cost ~3000 cycles per tile).  Anything else runs the run-time-geometry kernel.
-  const bool static_ok = !conv0_only && taps == 9 && p.KH == 3 && p.PH == 1 && p.PW == 1 && p.fast1 && p.k1_uniform != 0 && d->round0 == DF_ROUND_NEAREST && d->round1 == DF_ROUND_NEAREST &&
+  const bool static_ok = !conv0_only && taps == 9 && p.KH == 3 && p.PH == 1 && p.PW == 1 && p.SH * p.SW == 1 && p.n_box == 1 && p.fast1 && p.k1_uniform != 0 && d->round0 == DF_ROUND_NEAREST && d->round1 == DF_ROUND_NEAREST &&
                          !p.nan_safe && !fused_cat && !getenv("DF_FORCE_DYNAMIC_GEOMETRY");  // (env: test hook for the generic path)
   auto match_static = [&]() {
     if (geom_matches<GeoCfg1>(p)) { p.SB = GeoCfg1::SB; return 1; }
@@ -479,8 +576,10 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   if (!op->geom_id) {
     const bool can_stage = (d->dst_dt == DF_U8 || d->dst_dt == DF_S8) && p.nc1 == 128 &&
                            !(getenv("DF_NO_STAGED_STORE") && atoi(getenv("DF_NO_STAGED_STORE")) != 0);
-    if (!plan(1, can_stage)) {
+    if (!plan(1, can_stage) && !plan(1, can_stage, 1) && !plan(1, false, 1)) {
       delete op;
+      if (!conv0_only && !fused_cat)  // the two stages as two launches need less shared memory each
+        return conv_create_composite(d, wei, wei1, bia0, bia1, scale0, scale1, out);
       return df::fail(DF_E_UNSUPPORTED, "conv: shape does not fit the shared-memory plan");
     }
   }
@@ -532,7 +631,9 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
     df_conv_destroy(op);
     return df::fail(DF_E_UNSUPPORTED, "conv: no kernel for this configuration in this build");
   }
-  DF_TRY_CUDA(op->kernel.attr(op->smem_bytes));
+  // the opt-in limit is a property of the kernel FUNCTION, shared by every handle that uses it: always raise it to
+  // the maximum (a later handle with a smaller plan must not lower it under an earlier handle's launches)
+  DF_TRY_CUDA(op->kernel.attr(kSmemLimit));
 
   // ---- CTA-pair variant: BASELINE cfg3 with everything resident once the weights are split in two.
   // Default for that shape (DF_PAIR=0 selects the single-CTA kernel, which has to stream 144 KB of
@@ -560,7 +661,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
       op->pair_prm = q;
       op->pair_smem = q.off_b + 1024;
       op->pair_kernel = pick_pair_cfg3(d->dst_dt);
-      DF_TRY_CUDA(op->pair_kernel.attr(op->pair_smem));
+      DF_TRY_CUDA(op->pair_kernel.attr(kSmemLimit));
       DF_TRY(encode_2d(&op->tmW0h, op->d_w0, q.swb, (long)9 * q.nkb * q.OC, q.OC / 2));
       DF_TRY(encode_2d(&op->tmW1h, op->d_w1, q.swb1, (long)q.n_chunks * q.nkb1 * q.nc1, q.nc1 / 2));
       op->pair = true;
@@ -610,7 +711,7 @@ static int src_maps(df_conv* op, const Params& p, const void* const* ptrs, int n
     const cuuint64_t c = (cuuint64_t)op->src_ic[k];
     cuuint64_t gd[4] = {c, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)n};
     cuuint64_t gs[3] = {c, (cuuint64_t)p.W * c, (cuuint64_t)p.H * p.W * c};
-    cuuint32_t box[4] = {(cuuint32_t)p.swb, (cuuint32_t)p.Wp, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)p.swb, (cuuint32_t)p.box_w, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&s.maps.m[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(ptrs[k]), gd, gs, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(p.swb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -638,10 +739,10 @@ static int dst_maps(df_conv* op, const Params& p, const void* ptr, int n, const 
   df_conv::DstSlot& s = op->d_maps[op->d_next];
   op->d_next = (op->d_next + 1) % df_conv::kMapSlots;
   s.ptr = nullptr;
-  const cuuint64_t pixels = (cuuint64_t)n * p.OH * p.OW;
+  const cuuint64_t pixels = (cuuint64_t)n * p.OHS * p.OWS;
   for (int i = 0; i < (per_warp ? 6 : 8); ++i) {
-    cuuint64_t gd[2] = {(cuuint64_t)p.OC1, pixels};
-    cuuint64_t gs[1] = {(cuuint64_t)p.OC1};
+    cuuint64_t gd[2] = {(cuuint64_t)p.dst_pitch, pixels};
+    cuuint64_t gs[1] = {(cuuint64_t)p.dst_pitch};
     cuuint32_t box[2] = {per_warp ? 64u : 128u, (cuuint32_t)((per_warp ? 32 : 128) >> i)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&s.maps.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gd, gs, box, es,
@@ -657,6 +758,19 @@ static int dst_maps(df_conv* op, const Params& p, const void* ptr, int n, const 
 
 static int conv_run_impl(df_conv* op, const void* const* srcs, void* dst, int n, void* stream) {
   if (!op || !srcs || !dst) return df::fail(DF_E_INVALID, "conv run: null argument");
+  if (!op->parts.empty()) {  // composite operator: see df_conv::parts
+    if (n < 0 || n > op->desc.n) return df::fail(DF_E_INVALID, "conv run: batch %d outside [0, %d]", n, op->desc.n);
+    if (op->chained) {
+      const void* mid[1] = {op->d_mid};
+      int rc = conv_run_impl(op->parts[0], srcs, op->d_mid, n, stream);
+      return rc ? rc : conv_run_impl(op->parts[1], mid, dst, n, stream);
+    }
+    for (df_conv* part : op->parts) {
+      int rc = conv_run_impl(part, srcs, dst, n, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   for (int k = 0; k < op->n_src; ++k)
     if (!srcs[k] || (reinterpret_cast<uintptr_t>(srcs[k]) & 15)) return df::fail(DF_E_INVALID, "conv run: source %d is null or not 16-byte aligned", k);
   if (n < 0 || n > op->desc.n) return df::fail(DF_E_INVALID, "conv run: batch %d outside [0, %d]", n, op->desc.n);
@@ -725,6 +839,17 @@ extern "C" int df_conv_debug_trace(df_conv* op, void* dev_buf, int cap) {
 
 extern "C" int df_conv_query(const df_conv* op, df_conv_info* info) {
   if (!op || !info) return df::fail(DF_E_INVALID, "conv query: null argument");
+  if (!op->parts.empty()) {  // composite: the first launch's plan, the whole operator's work
+    int rc = df_conv_query(op->parts[0], info);
+    double macs = 0;
+    for (const df_conv* part : op->parts) {
+      df_conv_info pi = {};
+      if (!rc) rc = df_conv_query(part, &pi);
+      macs += pi.macs_per_image;
+    }
+    info->macs_per_image = macs;
+    return rc;
+  }
   const Params& p = op->prm;
   info->tiles_per_launch = tiles_for(p, op->desc.n);
   info->grid = info->tiles_per_launch < op->sms ? info->tiles_per_launch : op->sms;
@@ -736,13 +861,15 @@ extern "C" int df_conv_query(const df_conv* op, df_conv_info* info) {
   info->b_stages = op->pair ? 0 : p.SB;
   info->padded_w = p.Wp;
   info->padded_h = p.Hp;
-  info->macs_per_image = (double)p.OH * p.OW * ((double)p.KH * p.KW * p.IC * p.OC + (p.conv0_only ? 0.0 : (double)p.OC * p.OC1));
-  info->mma_efficiency = (double)op->desc.n * p.OH * p.OW / ((double)info->tiles_per_launch * kTileM);
+  info->macs_per_image = (double)p.OHS * p.OWS * ((double)p.KH * p.KW * p.IC * p.OC + (p.conv0_only ? 0.0 : (double)p.OC * p.OC1));
+  info->mma_efficiency = (double)op->desc.n * p.OHS * p.OWS / ((double)info->tiles_per_launch * kTileM);
   return 0;
 }
 
 extern "C" int df_conv_destroy(df_conv* op) {
   if (!op) return 0;
+  for (df_conv* part : op->parts) df_conv_destroy(part);
+  cudaFree(op->d_mid);
   cudaFree(op->d_w0);
   cudaFree(op->d_w1);
   cudaFree(op->d_bias0);

@@ -72,6 +72,15 @@ struct Params {
   // the images of the linearised padded pixel space (Hp = H + ZR); q_first = (ZR + 1) * Wp is the position of image
   // 0, row 0, column 0.  The BASELINE geometry is 3, 3, 1, 1 -> OH = H, OW = W, ZR = 1, q_first = 2 Wp.
   int KH, KW, PH, PW, OH, OW, ZR, q_first;
+  // Strided windows (SH, SW > 1; run-time geometry only) are computed as the stride-1 convolution and only every
+  // SH-th row / SW-th column of it is stored: OHS x OWS = the operator's real output size.  (Correct and simple,
+  // at SH * SW times the arithmetic; the strided convs of the networks this serves are few and small.)
+  int SH, SW, OHS, OWS;
+  // destination row pitch in channels and first channel: an operator with more output channels than one TMEM
+  // accumulator holds (256) runs as several launches, each writing its own channel range of the same pixels
+  int dst_pitch, dst_ch0;
+  // halo rows wider than the TMA box limit (256 positions) are loaded as n_box boxes of box_w positions each
+  int n_box, box_w;
   int Hp, Wp, NR;
   int n_tiles;
   int swb, nkb, ks_last;     // conv0: K-block bytes (= swizzle span), blocks, 32 B steps in last
@@ -235,25 +244,27 @@ struct SrcMaps {
   CUtensorMap m[kMaxSrc];
 };
 
+struct PosState {
+  int wq, n, hp;
+};
+__device__ __forceinline__ int pos_valid_before(const Params& p, const PosState& s);
 // number of valid (= real pixel) positions with linear index < q; for a valid q this is its flat NHW
 // pixel index
 __device__ __forceinline__ int valid_before(const Params& p, int q) {
   const int gq = q / p.Wp, wq = q - gq * p.Wp;
   const int t = gq - 1;
   const int n = t / p.Hp, hp = t - n * p.Hp;
-  if (n >= p.N) return p.N * p.OH * p.OW;
-  if (hp < p.ZR) return n * p.OH * p.OW;
-  if (hp >= p.ZR + p.OH) return (n + 1) * p.OH * p.OW;
-  return (n * p.OH + hp - p.ZR) * p.OW + min(wq, p.OW);
+  PosState s;
+  s.wq = wq;
+  s.n = n;
+  s.hp = hp;
+  return pos_valid_before(p, s);
 }
 
 // Position q = ((n * Hp + hp) + 1) * Wp + wq of the linearised padded pixel space, kept as (wq, n, hp) and
 // advanced by precomputed steps: the epilogue needs the coordinates of four positions per thread and
 // tile, and computing them with integer divisions cost more than a conv1 chunk's arithmetic
 // (~1500 cycles per tile with 16 warps, profiles/r01_trace_cfg3_v10.log).
-struct PosState {
-  int wq, n, hp;
-};
 __device__ __forceinline__ PosState pos_of(const Params& p, int q) {
   const int gq = q / p.Wp;
   PosState s;
@@ -279,10 +290,23 @@ __device__ __forceinline__ void pos_step(const Params& p, PosState& s, int dw, i
 // NHW pixel index of a position, -1 for padding positions
 __device__ __forceinline__ int pos_pixel(const Params& p, const PosState& s) {
   const bool ok = (s.wq < p.OW) && (s.hp >= p.ZR) && (s.hp < p.ZR + p.OH) && (s.n < p.N);
+  if (p.SH * p.SW > 1) {  // strided window: only every SH-th row / SW-th column is an output pixel
+    const int r = s.hp - p.ZR, y = r / p.SH, x = s.wq / p.SW;
+    return (ok && y * p.SH == r && x * p.SW == s.wq) ? (s.n * p.OHS + y) * p.OWS + x : -1;
+  }
   return ok ? (s.n * p.OH + s.hp - p.ZR) * p.OW + s.wq : -1;
 }
 // = valid_before(q) for the position's q
 __device__ __forceinline__ int pos_valid_before(const Params& p, const PosState& s) {
+  if (p.SH * p.SW > 1) {
+    if (s.n >= p.N) return p.N * p.OHS * p.OWS;
+    const int r = s.hp - p.ZR;
+    if (r < 0) return s.n * p.OHS * p.OWS;
+    const int rows = min((r + p.SH - 1) / p.SH, p.OHS);  // output rows entirely before this position
+    const int y = r / p.SH;
+    const bool row_valid = y * p.SH == r && y < p.OHS;
+    return (s.n * p.OHS + rows) * p.OWS + (row_valid ? min((s.wq + p.SW - 1) / p.SW, p.OWS) : 0);
+  }
   if (s.n >= p.N) return p.N * p.OH * p.OW;
   if (s.hp < p.ZR) return s.n * p.OH * p.OW;
   if (s.hp >= p.ZR + p.OH) return (s.n + 1) * p.OH * p.OW;
@@ -819,12 +843,12 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
           if (staged) {  // 16-byte unit XOR row-inside-the-1024-B-atom, as SWIZZLE_128B wants
             if (rr >= 0 && !dbg_flag(p, 4)) sts_bytes<CH>(saddr[ri], w);
           } else if (rr >= 0 && !dbg_flag(p, 4)) {
-            uint8_t* out = static_cast<uint8_t*>(p.dst) + (size_t)rr * g.OC1() + ch0;
+            uint8_t* out = static_cast<uint8_t*>(p.dst) + (size_t)rr * p.dst_pitch + p.dst_ch0 + ch0;
             if constexpr (CH == 8) *reinterpret_cast<uint2*>(out) = make_uint2(w[0], w[1]);
             else *reinterpret_cast<uint32_t*>(out) = w[0];
           }
         } else if (rr >= 0) {
-          uint4* out = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.dst) + ((size_t)rr * g.OC1() + ch0) * 4);
+          uint4* out = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.dst) + ((size_t)rr * p.dst_pitch + p.dst_ch0 + ch0) * 4);
 #pragma unroll
           for (int i = 0; i < CH / 4; ++i) out[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
         }
@@ -1130,7 +1154,7 @@ __device__ __forceinline__ void store_role(const Params& p, const DstMaps& tmD, 
       const uint32_t cb = c & 1;
       mbar_wait(smem_u32(&bar->stage_full[cb]), (c >> 1) & 1);
       tr.ev(40);
-      if (!dbg_flag(p, 2)) store_staged_chunk(tmD, sbase + p.off_stage + cb * kStageBytes, f0, V, j * g.nc1());
+      if (!dbg_flag(p, 2)) store_staged_chunk(tmD, sbase + p.off_stage + cb * kStageBytes, f0, V, p.dst_ch0 + j * g.nc1());
       tr.ev(41);
       bulk_wait_read_all();
       tr.ev(42);
@@ -1255,6 +1279,10 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
         if (multi_src) {
           for (int kb = 0; kb < g.nkb(); ++kb)
             tma_load_4d(dst + kb * p.a_kb_stride, &tmS.m[p.kb_src[kb]], full, (int)p.kb_c0[kb], 0, h, n);
+        } else if (!G::is_static && p.n_box > 1) {
+          for (int kb = 0; kb < g.nkb(); ++kb)
+            for (int bx = 0; bx < p.n_box; ++bx)
+              tma_load_4d(dst + kb * p.a_kb_stride + bx * p.box_w * g.swb(), &tmS.m[0], full, kb * g.swb(), bx * p.box_w, h, n);
         } else {
 #pragma unroll
           for (int kb = 0; kb < g.nkb(); ++kb) tma_load_4d(dst + kb * p.a_kb_stride, &tmS.m[0], full, kb * g.swb(), 0, h, n);

@@ -68,7 +68,7 @@ def _create(**kw):
                 bia0_dt=0, bia1_dt=0, relu0=0, relu1=0, round0=0, round1=0, nscale0=1, nscale1=1)
     base.update(kw)
     d = df.ConvDesc(**base)
-    w = np.zeros(base["oc"] * base["ic"] * 9 + 64, np.int8)
+    w = np.zeros(base["oc"] * base["ic"] * base["kh"] * base["kw"] + 64, np.int8)
     w1 = np.zeros(max(1, base["oc1"]) * base["oc"] + 64, np.int8)
     s = np.ones(2048, np.float32)
     h = C.c_void_p()
@@ -91,12 +91,13 @@ def test_conv_create_rejects_like_reference_without_touching_the_gpu():
     assert _create(ph=6, pw=6, ih=8, iw=8) == INVALID      # l_pad > ur_w (:657-661)
     # accepted by the reference, outside the B200 path: documented as unsupported, never a CPU fallback
     assert _create(kh=3, kw=3, ph=2, pw=2, ih=8, iw=8) == UNSUPPORTED   # output larger than the input
-    assert _create(sh=2, sw=2) == UNSUPPORTED
-    assert _create(oc=512) == UNSUPPORTED
     # the conv0-only operator (oc1 = 0) and other stride-1 windows are on the B200 path: they get as far as the device
     assert _create(oc1=0) not in (INVALID, UNSUPPORTED)
     assert _create(kh=1, kw=1, ph=0, pw=0) not in (INVALID, UNSUPPORTED)
     assert _create(kh=5, kw=5, ph=2, pw=2) not in (INVALID, UNSUPPORTED)
+    assert _create(sh=2, sw=2) not in (INVALID, UNSUPPORTED)       # strided windows
+    assert _create(oc=512) not in (INVALID, UNSUPPORTED)           # more channels than one accumulator: composite operator
+    assert _create(iw=300) not in (INVALID, UNSUPPORTED)           # rows wider than one TMA box
 
 
 def test_compute_entry_points_fail_loudly_without_a_device():

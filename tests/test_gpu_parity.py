@@ -421,3 +421,76 @@ def test_one_by_one_conv_full_width(df):
     got = op(src)
     op.close()
     _assert_same(got, want, "u8")
+
+
+# ------------------------------------------------- strides, wide rows, more channels than one accumulator holds
+def _conv0_only_case(df, n, h, w, ic, oc, k, stride, pad, dst="u8", k0=None, relu0=1):
+    kk = (k, k) if isinstance(k, int) else k
+    src = cases.synth.src_u8(1, (n, h, w, ic))
+    wb = cases.layout.oihw_to_blocked(cases.synth.wei_s8(2, (oc, ic) + tuple(kk)))
+    b0 = cases.synth.bias(4, oc, "s32")
+    if k0 is None:
+        k0 = int(np.ceil(np.log2(ic * kk[0] * kk[1] * 64.0))) - 4
+    s0 = cases.synth.channel_scales(oc, k0)
+    d = O.make_desc(n, h, w, ic, oc, 0, cases.DT[dst], O.S32, O.UNDEF, k=k, stride=stride, pad=pad, relu0=relu0, nscale0=oc)
+    want = O.conv(d, src, wb, b0, s0)
+    op = df.Conv(n, h, w, ic, oc, 0, cases.DT[dst], wb, None, b0, None, s0, (1.0,), df.S32, df.UNDEF, relu0=bool(relu0),
+                 k=k, stride=stride, pad=pad)
+    got = op(src)
+    op.close()
+    assert got.shape == want.shape
+    _assert_same(got, want, dst)
+    assert want.any()
+
+
+@pytest.mark.parametrize("dst", ["u8", "f32"])
+@pytest.mark.parametrize("k,stride,pad", [(3, 2, 1), (1, 2, 0), (7, 2, 3), (3, (2, 1), 1), (2, 2, 0), (5, (1, 3), 2), (3, 2, 0)],
+                         ids=lambda v: str(v).replace(" ", ""))
+def test_conv0_only_strided(df, k, stride, pad, dst):
+    """Strided windows (accepted by jit_conv_kernel::init_conf, pinned to the reference generators in
+    tests/test_ref_pin.py): stride-1 arithmetic, strided store."""
+    _conv0_only_case(df, 2, 13, 15, 32, 48, k, stride, pad, dst)
+
+
+@pytest.mark.parametrize("w", [255, 256, 300, 520])
+def test_conv0_only_wide_rows(df, w):
+    """Rows wider than one TMA box (256 positions): several boxes per halo row."""
+    _conv0_only_case(df, 1, 3, w, 16, 32, 3, 1, 1, "u8")
+
+
+@pytest.mark.parametrize("dst", ["u8", "s8", "s32"])
+@pytest.mark.parametrize("oc,k,pad", [(320, 3, 1), (512, 1, 0), (272, 3, 1), (784, 1, 0)])
+def test_conv0_only_many_output_channels(df, oc, k, pad, dst):
+    """oc > 256: groups of <= 256 channels, one launch each, into channel ranges of the same pixels."""
+    _conv0_only_case(df, 2, 7, 9, 32, oc, k, 1, pad, dst, relu0=0 if dst != "u8" else 1)
+
+
+def test_conv0_only_deep_input_single_halo_stage(df):
+    """28x28 with 512 input channels: one halo stage is 119 KB, so the kernel runs with a single stage."""
+    _conv0_only_case(df, 1, 28, 28, 512, 32, 3, 1, 1, "u8")
+
+
+@pytest.mark.parametrize("case", [
+    # n, h, w, ic, oc, oc1, k, stride, pad, dst
+    (2, 7, 9, 32, 288, 272, 3, 1, 1, "u8"),       # first stage wider than one accumulator -> two chained launches
+    (2, 7, 7, 64, 512, 1040, 3, 1, 1, "s32"),     # ... and a second stage in channel groups
+    (2, 13, 15, 32, 64, 144, 3, 2, 1, "u8"),      # strided first stage inside the fused kernel
+    (1, 9, 300, 16, 32, 48, 3, 1, 1, "u8"),       # wide rows inside the fused kernel
+    (2, 14, 14, 48, 320, 96, 1, 1, 0, "f32"),
+], ids=lambda c: "x".join(str(v) for v in c))
+def test_fused_conv_beyond_one_accumulator(df, case):
+    n, h, w, ic, oc, oc1, k, stride, pad, dst = case
+    src = cases.synth.src_u8(1, (n, h, w, ic))
+    wb = cases.layout.oihw_to_blocked(cases.synth.wei_s8(2, (oc, ic, k, k)))
+    w1b = cases.layout.oihw_to_blocked(cases.synth.wei_s8(3, (oc1, oc)).reshape(oc1, oc, 1, 1))
+    b0, b1 = cases.synth.bias(4, oc, "s32"), cases.synth.bias(5, oc1, "s32")
+    s0 = cases.synth.channel_scales(oc, int(np.ceil(np.log2(ic * k * k * 64.0))) - 4)
+    s1 = cases.synth.channel_scales(oc1, int(np.ceil(np.log2(oc * 64.0 * 64))) - 6)
+    d = O.make_desc(n, h, w, ic, oc, oc1, cases.DT[dst], O.S32, O.S32, k=k, stride=stride, pad=pad, nscale0=oc, nscale1=oc1)
+    want = O.conv(d, src, wb, b0, s0, w1b, b1, s1)
+    op = df.Conv(n, h, w, ic, oc, oc1, cases.DT[dst], wb, w1b, b0, b1, s0, s1, df.S32, df.S32, k=k, stride=stride, pad=pad)
+    got = op(src)
+    op.close()
+    assert got.shape == want.shape
+    _assert_same(got, want, dst)
+    assert want.any()

@@ -86,5 +86,7 @@ def test_conv_creation_rules_exit_like_reference():
 
 
 def test_conv_outside_b200_path_says_so():
-    r = _run(_conv_script(stride=2, oh=4, ow=4))
+    """What the reference accepts but the B200 path does not run (padding that makes the output larger than the input)
+    exits with its own message -- never a CPU fallback."""
+    r = _run(_conv_script(pad=2, oh=10, ow=10))
     assert r.returncode != 0 and "unsupported on B200 path" in r.stderr
