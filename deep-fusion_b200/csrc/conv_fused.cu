@@ -117,6 +117,7 @@ struct df_conv {
   std::vector<df_conv*> parts;
   bool chained = false;
   void* d_mid = nullptr;
+  bool with_sum = false;  // created by df_conv_create_sum: run-time-geometry kernel, direct stores
 };
 
 namespace {
@@ -208,16 +209,17 @@ int encode_2d(CUtensorMap* tm, void* base, int row_bytes, long rows, int box_row
 
 static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic, int concat_relu, const int8_t* wei,
                             const int8_t* wei1, const void* bia0, const void* bia1, const float* scale0,
-                            const float* scale1, df_conv** out);
+                            const float* scale1, df_conv** out, bool with_sum = false);
 
 static size_t dt_bytes(int dt) { return (dt == DF_F32 || dt == DF_S32) ? 4 : 1; }
 
 // Composite operators (see df_conv::parts).  Everything the reference accepts for these shapes
 // (src/jit_conv_kernel.cc:586-661 has no upper bound on oc) runs on the device; nothing falls back to the CPU.
 static int conv_create_composite(const df_conv_desc* d, const int8_t* wei, const int8_t* wei1, const void* bia0,
-                                 const void* bia1, const float* scale0, const float* scale1, df_conv** out) {
+                                 const void* bia1, const float* scale0, const float* scale1, df_conv** out, bool with_sum) {
   df_conv* op = new df_conv();
   op->desc = *d;
+  op->with_sum = with_sum;
   int rc = 0;
   if (d->oc1 == 0) {
     // ---- conv-only, oc > 256: groups of <= 256 output channels.  OIhw4i16o4i is output-block major, so the
@@ -229,7 +231,7 @@ static int conv_create_composite(const df_conv_desc* d, const int8_t* wei, const
       const int8_t* w = wei + (size_t)(o0 / 16) * (d->ic / 16) * d->kh * d->kw * 256;
       const void* b = bia0 ? static_cast<const char*>(bia0) + (size_t)o0 * dt_bytes(d->bia0_dt) : nullptr;
       df_conv* part = nullptr;
-      rc = conv_create_impl(&g, 0, nullptr, 0, w, nullptr, b, nullptr, scale0 + (d->nscale0 > 1 ? o0 : 0), nullptr, &part);
+      rc = conv_create_impl(&g, 0, nullptr, 0, w, nullptr, b, nullptr, scale0 + (d->nscale0 > 1 ? o0 : 0), nullptr, &part, with_sum);
       if (rc) break;
       part->prm.dst_pitch = d->oc;
       part->prm.dst_ch0 = o0;
@@ -262,7 +264,7 @@ static int conv_create_composite(const df_conv_desc* d, const int8_t* wei, const
     if (!wei1 || !scale1) rc = df::fail(DF_E_INVALID, "conv: null 1x1 weights / scales");
     if (!rc) rc = conv_create_impl(&a, 0, nullptr, 0, wei, nullptr, bia0, nullptr, scale0, nullptr, &pa);
     if (pa) op->parts.push_back(pa);
-    if (!rc) rc = conv_create_impl(&b, 0, nullptr, 0, wei1, nullptr, bia1, nullptr, scale1, nullptr, &pb);
+    if (!rc) rc = conv_create_impl(&b, 0, nullptr, 0, wei1, nullptr, bia1, nullptr, scale1, nullptr, &pb, with_sum);
     if (pb) op->parts.push_back(pb);
     if (!rc) {
       cudaError_t e = cudaMalloc(&op->d_mid, (size_t)d->n * b.ih * b.iw * d->oc);
@@ -282,7 +284,7 @@ static int conv_create_composite(const df_conv_desc* d, const int8_t* wei, const
 // n_src == 0: plain conv.  n_src >= 1: the source is the channel concatenation of n_src tensors (fused concat)
 static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic, int concat_relu, const int8_t* wei,
                             const int8_t* wei1, const void* bia0, const void* bia1, const float* scale0,
-                            const float* scale1, df_conv** out) {
+                            const float* scale1, df_conv** out, bool with_sum) {
   if (!out) return df::fail(DF_E_INVALID, "conv: null out");
   *out = nullptr;
   int rc = validate(d);
@@ -320,7 +322,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
     return df::fail(DF_E_UNSUPPORTED, "concat+conv: k3 s1 p1 only");
   if (d->oc > 256) {  // more channels than one TMEM accumulator: composite operator
     if (fused_cat) return df::fail(DF_E_UNSUPPORTED, "concat+conv: conv0 oc <= 256 (got %d)", d->oc);
-    return conv_create_composite(d, wei, wei1, bia0, bia1, scale0, scale1, out);
+    return conv_create_composite(d, wei, wei1, bia0, bia1, scale0, scale1, out, with_sum);
   }
   const int zr_w = d->pw > d->kw - 1 - d->pw ? d->pw : d->kw - 1 - d->pw;  // zero columns between rows
   if (fused_cat && d->iw + zr_w > 256) return df::fail(DF_E_UNSUPPORTED, "concat+conv: padded width <= 256");
@@ -344,6 +346,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   p.n_src = fused_cat ? n_src : 1;
   p.concat_relu = fused_cat && concat_relu;
   op->n_src = p.n_src;
+  op->with_sum = with_sum;
   op->src_ic[0] = d->ic;
   if (fused_cat)
     for (int i = 0, kb = 0; i < n_src; ++i) {
@@ -557,7 +560,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   // to wait for GEMM2 of tile t (profiles/r02_knockout.log: with one tile the two strictly alternate and
   // their hand-offs alone cost ~3000 cycles per tile).  Anything else runs the run-time-geometry kernel.
   const bool static_ok = !conv0_only && taps == 9 && p.KH == 3 && p.PH == 1 && p.PW == 1 && p.SH * p.SW == 1 && p.n_box == 1 && p.fast1 && p.k1_uniform != 0 && d->round0 == DF_ROUND_NEAREST && d->round1 == DF_ROUND_NEAREST &&
-                         !p.nan_safe && !fused_cat && !getenv("DF_FORCE_DYNAMIC_GEOMETRY");  // (env: test hook for the generic path)
+                         !p.nan_safe && !fused_cat && !with_sum && !getenv("DF_FORCE_DYNAMIC_GEOMETRY");  // (env: test hook for the generic path)
   auto match_static = [&]() {
     if (geom_matches<GeoCfg1>(p)) { p.SB = GeoCfg1::SB; return 1; }
     if (geom_matches<GeoCfg3>(p)) { p.SB = GeoCfg3::SB; return 3; }
@@ -574,12 +577,12 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   }
   const int shape_id = op->geom_id;  // which BASELINE shape this is (0: none)
   if (!op->geom_id) {
-    const bool can_stage = (d->dst_dt == DF_U8 || d->dst_dt == DF_S8) && p.nc1 == 128 &&
+    const bool can_stage = (d->dst_dt == DF_U8 || d->dst_dt == DF_S8) && p.nc1 == 128 && !with_sum &&
                            !(getenv("DF_NO_STAGED_STORE") && atoi(getenv("DF_NO_STAGED_STORE")) != 0);
     if (!plan(1, can_stage) && !plan(1, can_stage, 1) && !plan(1, false, 1)) {
       delete op;
       if (!conv0_only && !fused_cat)  // the two stages as two launches need less shared memory each
-        return conv_create_composite(d, wei, wei1, bia0, bia1, scale0, scale1, out);
+        return conv_create_composite(d, wei, wei1, bia0, bia1, scale0, scale1, out, with_sum);
       return df::fail(DF_E_UNSUPPORTED, "conv: shape does not fit the shared-memory plan");
     }
   }
@@ -756,17 +759,19 @@ static int dst_maps(df_conv* op, const Params& p, const void* ptr, int n, const 
   return 0;
 }
 
-static int conv_run_impl(df_conv* op, const void* const* srcs, void* dst, int n, void* stream) {
+static int conv_run_impl(df_conv* op, const void* const* srcs, void* dst, int n, void* stream, const void* res = nullptr) {
+  if (op && res && !op->with_sum) return df::fail(DF_E_INVALID, "conv run: handle was not created for an eltwise sum (df_conv_create_sum)");
+  if (res && (reinterpret_cast<uintptr_t>(res) & 15)) return df::fail(DF_E_INVALID, "conv run: residual must be 16-byte aligned");
   if (!op || !srcs || !dst) return df::fail(DF_E_INVALID, "conv run: null argument");
   if (!op->parts.empty()) {  // composite operator: see df_conv::parts
     if (n < 0 || n > op->desc.n) return df::fail(DF_E_INVALID, "conv run: batch %d outside [0, %d]", n, op->desc.n);
     if (op->chained) {
       const void* mid[1] = {op->d_mid};
       int rc = conv_run_impl(op->parts[0], srcs, op->d_mid, n, stream);
-      return rc ? rc : conv_run_impl(op->parts[1], mid, dst, n, stream);
+      return rc ? rc : conv_run_impl(op->parts[1], mid, dst, n, stream, res);
     }
     for (df_conv* part : op->parts) {
-      int rc = conv_run_impl(part, srcs, dst, n, stream);
+      int rc = conv_run_impl(part, srcs, dst, n, stream, res);
       if (rc) return rc;
     }
     return 0;
@@ -796,6 +801,7 @@ static int conv_run_impl(df_conv* op, const void* const* srcs, void* dst, int n,
   p.N = n;
   p.n_tiles = tiles_for(p, n);
   p.dst = dst;
+  p.res = res;
   p.trace = op->trace;
   p.trace_cap = op->trace_cap;
   auto set_tile_step = [&p](long tiles) {  // positions between successive tiles of one CTA
@@ -822,6 +828,18 @@ extern "C" int df_conv_run(df_conv* op, const uint8_t* src, void* dst, int n, vo
   if (op && op->n_src != 1) return df::fail(DF_E_INVALID, "conv run: handle was created for %d concatenated inputs (df_conv_run_concat)", op->n_src);
   const void* srcs[1] = {src};
   return conv_run_impl(op, srcs, dst, n, stream);
+}
+
+extern "C" int df_conv_create_sum(const df_conv_desc* d, const int8_t* wei, const int8_t* wei1, const void* bia0,
+                                  const void* bia1, const float* scale0, const float* scale1, df_conv** out) {
+  return conv_create_impl(d, 0, nullptr, 0, wei, wei1, bia0, bia1, scale0, scale1, out, true);
+}
+
+extern "C" int df_conv_run_sum(df_conv* op, const uint8_t* src, const void* residual, void* dst, int n, void* stream) {
+  if (!residual) return df::fail(DF_E_INVALID, "conv run: null residual");
+  if (op && op->n_src != 1) return df::fail(DF_E_INVALID, "conv run: concat handle");
+  const void* srcs[1] = {src};
+  return conv_run_impl(op, srcs, dst, n, stream, residual);
 }
 
 extern "C" int df_conv_run_concat(df_conv* op, const void* const* srcs, void* dst, int n, void* stream) {

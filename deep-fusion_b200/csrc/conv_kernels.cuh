@@ -109,6 +109,10 @@ struct Params {
   const float *bias0, *scale0, *bias1, *scale1;
   const int* k1;
   void* dst;
+  // eltwise-sum (+ReLU) fused into the final stage (README.md:65 "eltwise-sum + relu fused op"; run-time geometry
+  // only): `res` has the destination's type and layout; t = (float(acc) + bias) * scale, then t = t + float(res)
+  // as one more separately rounded f32 add, then ReLU / round / saturate as always.  Null: no sum.
+  const void* res;
   unsigned long long* trace;  // optional timeline buffer (df_conv_debug_trace), normally null
   int trace_cap;
   // concat fused into the A-operand load (df_conv_create_concat; run-time geometry only): the conv's input is the
@@ -567,12 +571,16 @@ __device__ __forceinline__ void finish_conv0(const uint32_t* v, const float4* b4
 // C[q]; K comes per channel from k4 or, kUniK, as the one uniform `k_uni`).
 template <int kDst, bool kDown, bool kNanSafe, int CH, bool kUniK>
 __device__ __forceinline__ void finish_conv1(const uint32_t* v, const float4* c4, const float4* s4, const int4* k4, int k_uni,
-                                             bool fast, bool relu, uint32_t* w) {
+                                             bool fast, bool relu, uint32_t* w, const float* res = nullptr) {
 #pragma unroll
   for (int g = 0; g < CH / 4; ++g) {
     float t[4];
     if (fast) scale4_fast(v + 4 * g, kUniK ? make_int4(k_uni, k_uni, k_uni, k_uni) : k4[g], c4[g], s4[g], t);
     else scale4(v + 4 * g, c4[g], s4[g], t);
+    if (res) {  // eltwise sum: one more separately rounded add (Params::res)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) t[i] = __fadd_rn(t[i], res[4 * g + i]);
+    }
     if (kDst == DF_U8) {
       w[g] = pack_u8x4<kDown, kNanSafe>(t);
     } else if (kDst == DF_S8) {
@@ -584,6 +592,33 @@ __device__ __forceinline__ void finish_conv1(const uint32_t* v, const float4* c4
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) w[4 * g + i] = (kDst == DF_F32) ? __float_as_uint(t[i]) : (uint32_t)cvt_x86<kDown>(t[i]);
+    }
+  }
+}
+
+// CH residual values of one destination row (type / layout of the destination) as f32: u8 / s8 extend exactly,
+// s32 converts like vcvtdq2ps, f32 as is
+template <int kDst, int CH>
+__device__ __forceinline__ void load_residual(const void* res, size_t elem, float* r) {
+  if constexpr (kDst == DF_F32 || kDst == DF_S32) {
+    const uint4* q = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(res) + elem * 4);
+#pragma unroll
+    for (int i = 0; i < CH / 4; ++i) {
+      const uint4 x = q[i];
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r[4 * i + e] = (kDst == DF_F32) ? __uint_as_float(xs[e]) : __int2float_rn((int)xs[e]);
+    }
+  } else {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(res) + elem);
+#pragma unroll
+    for (int i = 0; i < CH / 4; ++i) {
+      const uint32_t x = q[i];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t b = (x >> (8 * e)) & 0xffu;
+        r[4 * i + e] = (kDst == DF_U8) ? (float)b : (float)(int)(int8_t)b;
+      }
     }
   }
 }
@@ -838,7 +873,17 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
         uint32_t v[CH], w[ts == 1 ? CH / 4 : CH];
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = acc[ri >> 1][4 * (i / 2) + 2 * (ri & 1) + (i & 1)];
-        finish_conv1<kDst, kDown1, kNanSafe, CH, kUniK>(v, c4, s4, k4, k_add, fast1, relu1, w);
+        if (p.res != nullptr) {  // eltwise sum (never staged: rr is the pixel index)
+          float rs[CH];
+          if (rr >= 0) load_residual<kDst, CH>(p.res, (size_t)rr * p.dst_pitch + p.dst_ch0 + ch0, rs);
+          else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) rs[i] = 0.f;
+          }
+          finish_conv1<kDst, kDown1, kNanSafe, CH, kUniK>(v, c4, s4, k4, k_add, fast1, relu1, w, rs);
+        } else {
+          finish_conv1<kDst, kDown1, kNanSafe, CH, kUniK>(v, c4, s4, k4, k_add, fast1, relu1, w);
+        }
         if constexpr (ts == 1) {
           if (staged) {  // 16-byte unit XOR row-inside-the-1024-B-atom, as SWIZZLE_128B wants
             if (rr >= 0 && !dbg_flag(p, 4)) sts_bytes<CH>(saddr[ri], w);

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "df_last_error", "df_version", "df_device_count", "df_set_device", "df_get_device", "df_device_sm_count", "df_malloc",
     "df_free", "df_memset", "df_host_register", "df_host_unregister", "df_h2d", "df_d2h", "df_stream_create",
     "df_stream_sync", "df_stream_destroy", "df_event_create", "df_event_record", "df_stream_wait_event", "df_event_elapsed_ms",
-    "df_event_destroy", "df_concat_check", "df_concat_run", "df_conv_create", "df_conv_run", "df_conv_query", "df_conv_create_concat", "df_conv_run_concat",
+    "df_event_destroy", "df_concat_check", "df_concat_run", "df_conv_create", "df_conv_run", "df_conv_query", "df_conv_create_concat", "df_conv_run_concat", "df_conv_create_sum", "df_conv_run_sum", "df_pool_check", "df_pool_run",
     "df_conv_destroy", "df_conv_debug_trace", "df_graph_begin", "df_graph_end", "df_graph_launch", "df_graph_destroy",
     "df_wei_blocked_offset", "df_repack_oihw_to_blocked", "df_repack_blocked_to_oihw", "df_repack_goihw_to_blocked",
     "df_repack_blocked_to_goihw", "df_nchw_to_nhwc", "df_nhwc_to_nchw",
@@ -37,6 +37,13 @@ class ConvDesc(C.Structure):
     _fields_ = [(k, C.c_int) for k in (
         "n", "ih", "iw", "ic", "oc", "oc1", "kh", "kw", "sh", "sw", "ph", "pw", "dst_dt", "bia0_dt", "bia1_dt",
         "relu0", "relu1", "round0", "round1", "nscale0", "nscale1")]
+
+
+class PoolDesc(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("dtype", "kind", "n", "h", "w", "c", "kh", "kw", "sh", "sw", "ph", "pw", "oh", "ow", "round_mode")]
+
+
+POOL_MAX, POOL_AVG_INCLUDE, POOL_AVG_EXCLUDE = 0, 1, 2
 
 
 class ConvInfo(C.Structure):
@@ -94,6 +101,10 @@ def lib():
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.POINTER(C.c_void_p)]
         l.df_conv_run_concat.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_void_p]
+        l.df_conv_create_sum.argtypes = l.df_conv_create.argtypes
+        l.df_conv_run_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        l.df_pool_check.argtypes = [C.POINTER(PoolDesc)]
+        l.df_pool_run.argtypes = [C.POINTER(PoolDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         l.df_conv_query.argtypes = [C.c_void_p, C.POINTER(ConvInfo)]
         l.df_conv_destroy.argtypes = [C.c_void_p]
         l.df_conv_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -245,7 +256,7 @@ class Conv:
 
     def __init__(self, n, ih, iw, ic, oc, oc1, dst_dt, wei_blocked, wei1_blocked, bias0=None, bias1=None,
                  scale0=(1.0,), scale1=(1.0,), bia0_dt=UNDEF, bia1_dt=UNDEF, relu0=False, relu1=False,
-                 round0=NEAREST, round1=NEAREST, k=3, stride=1, pad=1):
+                 round0=NEAREST, round1=NEAREST, k=3, stride=1, pad=1, with_sum=False):
         scale0 = np.ascontiguousarray(scale0, dtype=np.float32)
         scale1 = np.ascontiguousarray(scale1, dtype=np.float32)
         kh, kw = (k, k) if isinstance(k, int) else k
@@ -255,8 +266,9 @@ class Conv:
                              int(relu0), int(relu1), round0, round1, scale0.size, scale1.size)
         h = C.c_void_p()
         keep = [np.ascontiguousarray(x) if x is not None else None for x in (wei_blocked, wei1_blocked, bias0, bias1)]
-        check(lib().df_conv_create(C.byref(self.desc), _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]),
-                                   scale0.ctypes.data, scale1.ctypes.data, C.byref(h)))
+        create = lib().df_conv_create_sum if with_sum else lib().df_conv_create
+        check(create(C.byref(self.desc), _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]),
+                     scale0.ctypes.data, scale1.ctypes.data, C.byref(h)))
         self.handle = h.value
         self.oh = (ih + 2 * ph - kh) // sh + 1
         self.ow = (iw + 2 * pw - kw) // sw + 1
@@ -274,7 +286,12 @@ class Conv:
         d = dst_dev.ptr if isinstance(dst_dev, DeviceBuffer) else dst_dev
         check(lib().df_conv_run(self.handle, s, d, self.desc.n if n is None else n, stream))
 
-    def __call__(self, src: np.ndarray) -> np.ndarray:
+    def run_sum(self, src_dev, res_dev, dst_dev, n=None, stream=None):
+        """df_conv_run_sum: the operator with an eltwise sum of `res_dev` (destination type / layout) before the ReLU."""
+        p = [b.ptr if isinstance(b, DeviceBuffer) else b for b in (src_dev, res_dev, dst_dev)]
+        check(lib().df_conv_run_sum(self.handle, p[0], p[1], p[2], self.desc.n if n is None else n, stream))
+
+    def __call__(self, src: np.ndarray, residual: np.ndarray = None) -> np.ndarray:
         """Host convenience: H2D, run, D2H."""
         n = src.shape[0]
         sbuf = DeviceBuffer.from_numpy(src)
@@ -282,7 +299,11 @@ class Conv:
         nbytes = int(np.prod(shape)) * np.dtype(NP_OF[self.dst_dt]).itemsize
         dbuf = DeviceBuffer(nbytes)
         dbuf.fill(0xCD)
-        self.run(sbuf, dbuf, n)
+        if residual is None:
+            self.run(sbuf, dbuf, n)
+        else:
+            rbuf = DeviceBuffer.from_numpy(residual)
+            self.run_sum(sbuf, rbuf, dbuf, n)
         sync()
         return dbuf.download(shape, NP_OF[self.dst_dt])
 
@@ -336,6 +357,22 @@ class ConcatConv(Conv):
         self.run(bufs, dbuf, n)
         sync()
         return dbuf.download(shape, NP_OF[self.dst_dt])
+
+
+def pool(src: np.ndarray, dtype, kind, k, stride, pad, out_hw=None, round_mode=NEAREST) -> np.ndarray:
+    """Host convenience around df_pool_run: NHWC numpy in, NHWC numpy out."""
+    n, h, w, c = src.shape
+    kh, kw = (k, k) if isinstance(k, int) else k
+    sh, sw = (stride, stride) if isinstance(stride, int) else stride
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    oh, ow = out_hw if out_hw else ((h + 2 * ph - kh) // sh + 1, (w + 2 * pw - kw) // sw + 1)
+    d = PoolDesc(dtype, kind, n, h, w, c, kh, kw, sh, sw, ph, pw, oh, ow, round_mode)
+    sbuf = DeviceBuffer.from_numpy(src)
+    out = DeviceBuffer(max(16, n * oh * ow * c * src.dtype.itemsize))
+    out.fill(0xCD)
+    check(lib().df_pool_run(C.byref(d), sbuf.ptr, out.ptr, n, None))
+    sync()
+    return out.download((n, oh, ow, c), src.dtype)
 
 
 class ConcatCall:

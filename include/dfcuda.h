@@ -123,11 +123,36 @@ int df_conv_create_concat(const df_conv_desc *desc, int n_src, const int *src_ic
                           const int8_t *wei_OIhw4i16o4i, const int8_t *wei1x1_OIhw4i16o4i, const void *bia0,
                           const void *bia1, const float *scale0, const float *scale1, df_conv **out);
 int df_conv_run_concat(df_conv *op, const void *const *src_dev, void *dst_dev, int n, void *stream);
+/* ---- eltwise-sum (+ReLU) fused into the operator's final stage: the "eltwise-sum + relu fused op" the reference
+ *      lists as planned (README.md:65; its yardstick is MKL-DNN's sum post-op, test/test_conv_relu_pooling.cc:118-123,
+ *      :148-151).  `residual_dev` has the destination's type and layout; per element
+ *          t = (float(acc) + bias) * scale;  t = t + float(residual);  ReLU / round / saturate as df_conv_run,
+ *      every step a separately rounded f32 operation.  Works for the conv-only and the fused operator. ---- */
+int df_conv_create_sum(const df_conv_desc *desc, const int8_t *wei_OIhw4i16o4i, const int8_t *wei1x1_OIhw4i16o4i,
+                       const void *bia0, const void *bia1, const float *scale0, const float *scale1, df_conv **out);
+int df_conv_run_sum(df_conv *op, const uint8_t *src_dev, const void *residual_dev, void *dst_dev, int n, void *stream);
 int df_conv_query(const df_conv *op, df_conv_info *info);
 int df_conv_destroy(df_conv *op);
 /* Diagnostic only (no reference counterpart): per-role clock64 timeline of the next launches
  * into dev_buf[grid * 4 * cap] (u64 words: tag << 48 | clock); NULL switches it off. */
 int df_conv_debug_trace(df_conv *op, void *dev_buf, int cap);
+
+/* ---- pooling stage of the "conv+relu+pooling fused op" the reference lists as planned (README.md:64; specified by
+ *      its MKL-DNN yardstick, test/test_conv_relu_pooling.cc:176-225, shapes :313-391): NHWC, zero padding, in the
+ *      conv's destination type.  max: largest in-image element of the window.  avg: sum of the in-image elements
+ *      over kh*kw (include padding) or over their count (exclude padding); integer types round the f32 quotient
+ *      with `round_mode`.  Launched behind the conv on the same stream, it reads the conv's output from L2. ---- */
+enum { DF_POOL_MAX = 0, DF_POOL_AVG_INCLUDE = 1, DF_POOL_AVG_EXCLUDE = 2 };
+typedef struct df_pool_desc {
+  int dtype;          /* DF_F32 / DF_S32 / DF_S8 / DF_U8                                   */
+  int kind;           /* DF_POOL_*                                                         */
+  int n, h, w, c;     /* input (maximum) batch, height, width, channels                    */
+  int kh, kw, sh, sw, ph, pw;
+  int oh, ow;         /* output size; windows may run past the bottom / right edge         */
+  int round_mode;     /* DF_ROUND_* for integer averages                                   */
+} df_pool_desc;
+int df_pool_check(const df_pool_desc *desc);
+int df_pool_run(const df_pool_desc *desc, const void *src_dev, void *dst_dev, int n, void *stream);
 
 /* ---- format tooling (host memory, no device work): the reference consumes OIhw4i16o4i /
  *      gOIhw4i16o4i weights (include/deepfusion.h:53-61, layout = jit_conv_kernel.cc:333-338) and

@@ -64,6 +64,16 @@ int dfo_conv(const dfo_conv_desc *d, const uint8_t *src, const int8_t *wei, cons
 int dfo_conv_intermediate(const dfo_conv_desc *d, const uint8_t *src, const int8_t *wei,
                           const void *bia0, const float *scale0, uint8_t *mid);
 
+/* the operator with an eltwise sum of `residual` (destination type and layout) between the scale and the ReLU:
+ * the reference's planned "eltwise-sum + relu fused op" (README.md:65) -- PARITY UNPINNED, see df_oracle.c */
+int dfo_conv_sum(const dfo_conv_desc *d, const uint8_t *src, const int8_t *wei, const void *bia0,
+                 const float *scale0, const int8_t *wei1, const void *bia1, const float *scale1,
+                 const void *residual, void *dst);
+/* NHWC pooling, kind 0 = max, 1 = avg (include padding), 2 = avg (exclude padding): the pooling stage of the
+ * reference's planned "conv+relu+pooling fused op" (README.md:64) -- PARITY UNPINNED, see df_oracle.c */
+int dfo_pool(int dt, int kind, const void *src, void *dst, int n, int h, int w, int c, int kh, int kw, int sh,
+             int sw, int ph, int pw, int oh, int ow, int round_mode);
+
 /* block size picked by jit_concat_kernel::init_conf (:157-176), 0 if rejected */
 int dfo_concat_block(int dt, int n_inputs, const int *ic);
 /* concat along channels of NHWC inputs with the literal ReLU of jit_concat_kernel.cc:43-51 */

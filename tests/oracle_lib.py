@@ -83,6 +83,40 @@ def replay_conv(d, src, wei, bia0, scale0, wei1=None, bia1=None, scale1=None, ou
     return _conv(lib().dfr_conv, d, src, wei, bia0, scale0, wei1, bia1, scale1, out)
 
 
+def conv_sum(d, src, wei, bia0, scale0, residual, wei1=None, bia1=None, scale1=None):
+    """dfo_conv_sum: the operator with an eltwise sum of `residual` (destination type / layout) before the ReLU."""
+    oh, ow = out_hw(d)
+    oc_out = d.oc1 if d.oc1 else d.oc
+    dst = np.zeros((d.n, oh, ow, oc_out), dtype=NP_OF[d.dst_dt])
+    residual = np.ascontiguousarray(residual)
+    assert residual.shape == dst.shape and residual.dtype == dst.dtype
+    scale0 = np.ascontiguousarray(scale0, dtype=np.float32)
+    scale1 = None if scale1 is None else np.ascontiguousarray(scale1, dtype=np.float32)
+    rc = lib().dfo_conv_sum(C.byref(d), _p(src), _p(wei), _p(bia0), _p(scale0), _p(wei1), _p(bia1), _p(scale1), _p(residual), _p(dst))
+    if rc:
+        raise RuntimeError(f"oracle conv_sum rejected: {rc}")
+    return dst
+
+
+POOL_MAX, POOL_AVG_INCLUDE, POOL_AVG_EXCLUDE = 0, 1, 2
+
+
+def pool(src, kind, k, stride, pad, out_hw_=None, round_mode=0):
+    """dfo_pool over an NHWC numpy array (u8 / s8 / s32 / f32)."""
+    src = np.ascontiguousarray(src)
+    dt = {np.dtype(np.uint8): U8, np.dtype(np.int8): S8, np.dtype(np.int32): S32, np.dtype(np.float32): F32}[src.dtype]
+    n, h, w, c = src.shape
+    kh, kw = (k, k) if isinstance(k, int) else k
+    sh, sw = (stride, stride) if isinstance(stride, int) else stride
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    oh, ow = out_hw_ if out_hw_ else ((h + 2 * ph - kh) // sh + 1, (w + 2 * pw - kw) // sw + 1)
+    dst = np.zeros((n, oh, ow, c), dtype=src.dtype)
+    rc = lib().dfo_pool(dt, kind, _p(src), _p(dst), n, h, w, c, kh, kw, sh, sw, ph, pw, oh, ow, round_mode)
+    if rc:
+        raise RuntimeError(f"oracle pool rejected: {rc}")
+    return dst
+
+
 def conv_intermediate(d, src, wei, bia0, scale0):
     oh, ow = out_hw(d)
     mid = np.zeros((d.n, oh, ow, d.oc), dtype=np.uint8)

@@ -494,3 +494,76 @@ def test_fused_conv_beyond_one_accumulator(df, case):
     assert got.shape == want.shape
     _assert_same(got, want, dst)
     assert want.any()
+
+
+# --------------------------------------------------- the reference's planned operators (README.md:64-65)
+# conv+relu+pooling and eltwise-sum+relu are listed, not implemented, in the reference; its test file only runs the
+# MKL-DNN yardstick (test/test_conv_relu_pooling.cc).  Semantics are defined in include/dfcuda.h and restated by the
+# oracle (dfo_pool / dfo_conv_sum, "parity unpinned" there); these tests hold the CUDA path to that restatement.
+def _pool_input(dt, shape, seed=31):
+    if dt == "f32":
+        a = (cases.synth.uniform_int(seed, shape, -100000, 100000, np.int32).astype(np.float32) / np.float32(7))
+        a.reshape(-1)[::97] = -0.0
+        return a
+    lo, hi = {"u8": (0, 255), "s8": (-128, 127), "s32": (-(2 ** 31), 2 ** 31 - 1)}[dt]
+    return cases.synth.uniform_int(seed, shape, lo, hi, cases.NPDT[dt])
+
+
+POOLS = [
+    # n, h, w, c, k, stride, pad, out_hw
+    (2, 4, 4, 16, 2, 2, 0, None),            # test_conv_relu_pooling.cc:314-315 after the conv: 2x2 -> 1x1 ...
+    (2, 14, 14, 64, 2, 2, 0, None),
+    (2, 7, 7, 128, 7, 7, 0, None),           # :341 global average
+    (2, 9, 11, 32, 3, 2, 1, None),
+    (2, 9, 11, 32, 3, 2, 1, (5, 6)),         # windows past the bottom / right edge (mkldnn padR)
+    (1, 5, 5, 16, (2, 3), (1, 2), (1, 0), None),
+]
+
+
+@pytest.mark.parametrize("round_mode", [0, 1], ids=["rn", "rd"])
+@pytest.mark.parametrize("kind", [0, 1, 2], ids=["max", "avg_incl", "avg_excl"])
+@pytest.mark.parametrize("dt", ["u8", "s8", "s32", "f32"])
+@pytest.mark.parametrize("case", POOLS, ids=lambda c: "x".join(str(v) for v in c[:7]).replace(" ", ""))
+def test_pool(df, case, dt, kind, round_mode):
+    n, h, w, c, k, stride, pad, out_hw = case
+    if kind == 0 and round_mode == 1:
+        pytest.skip("max pooling does not round")
+    src = _pool_input(dt, (n, h, w, c))
+    want = O.pool(src, kind, k, stride, pad, out_hw, round_mode)
+    got = df.pool(src, cases.DT[dt], kind, k, stride, pad, out_hw, round_mode)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
+@pytest.mark.parametrize("dst", ["u8", "s8", "s32", "f32"])
+@pytest.mark.parametrize("shape", [(2, 9, 7, 32, 48, 0, 3, 1), (2, 7, 7, 64, 320, 0, 1, 0), (2, 8, 8, 64, 64, 144, 3, 1),
+                                   (1, 7, 7, 32, 288, 272, 3, 1)], ids=lambda s: "x".join(str(v) for v in s))
+def test_conv_eltwise_sum(df, shape, dst):
+    """conv (+1x1) + residual + ReLU: conv-only, conv-only in channel groups, fused, fused as chained launches."""
+    n, h, w, ic, oc, oc1, k, pad = shape
+    src = cases.synth.src_u8(1, (n, h, w, ic))
+    wb = cases.layout.oihw_to_blocked(cases.synth.wei_s8(2, (oc, ic, k, k)))
+    b0 = cases.synth.bias(4, oc, "s32")
+    s0 = cases.synth.channel_scales(oc, int(np.ceil(np.log2(ic * k * k * 64.0))) - 4)
+    if oc1:
+        w1b = cases.layout.oihw_to_blocked(cases.synth.wei_s8(3, (oc1, oc)).reshape(oc1, oc, 1, 1))
+        b1 = cases.synth.bias(5, oc1, "s32")
+        s1 = cases.synth.channel_scales(oc1, int(np.ceil(np.log2(oc * 64.0 * 64))) - 6)
+    else:
+        w1b, b1, s1 = None, None, np.array([1.0], np.float32)
+    oh, ow = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    res = _pool_input(dst, (n, oh, ow, oc1 or oc), seed=41)
+    if dst == "s32":
+        res = (res >> 20).astype(np.int32)  # comparable in size to the conv's output, so the add matters
+    if dst == "f32":
+        res = (res / np.float32(64)).astype(np.float32)
+    d = O.make_desc(n, h, w, ic, oc, oc1, cases.DT[dst], O.S32, O.S32 if oc1 else O.UNDEF, k=k, pad=pad, relu0=1, relu1=1,
+                    nscale0=oc, nscale1=s1.size)
+    want = O.conv_sum(d, src, wb, b0, s0, res, w1b, b1, s1)
+    plain = O.conv(d, src, wb, b0, s0, w1b, b1, s1)
+    assert not np.array_equal(want, plain), "degenerate case: the residual does not change the result"
+    op = df.Conv(n, h, w, ic, oc, oc1, cases.DT[dst], wb, w1b, b0, b1, s0, s1, df.S32, df.S32 if oc1 else df.UNDEF,
+                 relu0=True, relu1=True, k=k, pad=pad, with_sum=True)
+    got = op(src, res)
+    op.close()
+    _assert_same(got, want, dst)
