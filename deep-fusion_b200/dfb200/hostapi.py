@@ -54,6 +54,14 @@ def lib():
         l.dfh_concat_conv_create.restype = C.c_void_p
         l.dfh_concat_conv_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int] + l.dfh_conv_create.argtypes[1:]
         l.dfh_concat_conv_is_fused.argtypes = [C.c_void_p]
+        l.dfh_conv_pool_create.restype = C.c_void_p
+        l.dfh_conv_pool_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
+                                           C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                           C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int]
+        l.dfh_conv_sum_create.restype = C.c_void_p
+        l.dfh_conv_sum_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int,
+                                          C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int]
         for f in ("dfh_sharded_upload", "dfh_sharded_sync", "dfh_sharded_download"):
             getattr(l, f).argtypes = [C.c_void_p]
             getattr(l, f).restype = None
@@ -166,6 +174,30 @@ def concat_conv(srcs, concat_relu, wei, bia, stride, padding, dst, wei1x1=None, 
                                      s0.ctypes.data_as(fp), s0.size, conv0_round_mode, int(conv1_relu),
                                      s1.ctypes.data_as(fp), s1.size, conv1_round_mode)
     return Op(h, (list(srcs), wei, bia, wei1x1, bia1x1, dst))
+
+
+def conv_pool(src, wei, bia, stride, padding, conv_dst, pool_dst, kind, pool_kernel, pool_stride, pool_padding, conv_relu=True,
+              conv_scales=(1.0,), conv_round_mode=NEAREST, pool_round_mode=NEAREST) -> Op:
+    """deepfusion::ext::conv_pool: conv (+ReLU) + pooling (kind 0 max, 1 avg incl. padding, 2 avg excl. padding)."""
+    s0 = np.ascontiguousarray(conv_scales, dtype=np.float32)
+    i2 = lambda v: (C.c_int * 2)(*v)
+    h = lib().dfh_conv_pool_create(src.h, wei.h, bia.h if bia else None, i2(stride), i2(padding), conv_dst.h, pool_dst.h, kind,
+                                   i2(pool_kernel), i2(pool_stride), i2(pool_padding), int(conv_relu),
+                                   s0.ctypes.data_as(C.POINTER(C.c_float)), s0.size, conv_round_mode, pool_round_mode)
+    return Op(h, (src, wei, bia, conv_dst, pool_dst))
+
+
+def conv_sum(src, wei, bia, stride, padding, residual, dst, wei1x1=None, bia1x1=None, conv0_relu=True, conv0_scales=(1.0,),
+             conv0_round_mode=NEAREST, conv1_relu=True, conv1_scales=(1.0,), conv1_round_mode=NEAREST) -> Op:
+    """deepfusion::ext::conv_sum: conv / fused conv + eltwise sum of `residual` + ReLU."""
+    s0 = np.ascontiguousarray(conv0_scales, dtype=np.float32)
+    s1 = np.ascontiguousarray(conv1_scales, dtype=np.float32)
+    i2 = lambda v: (C.c_int * 2)(*v)
+    fp = C.POINTER(C.c_float)
+    h = lib().dfh_conv_sum_create(src.h, wei.h, bia.h if bia else None, i2(stride), i2(padding), wei1x1.h if wei1x1 else None,
+                                  bia1x1.h if bia1x1 else None, residual.h, dst.h, int(conv0_relu), s0.ctypes.data_as(fp), s0.size,
+                                  conv0_round_mode, int(conv1_relu), s1.ctypes.data_as(fp), s1.size, conv1_round_mode)
+    return Op(h, (src, wei, bia, wei1x1, bia1x1, residual, dst))
 
 
 def concat_conv_is_fused(op: Op) -> bool:

@@ -711,6 +711,124 @@ private:
   bool relu_, fused_ = true;
 };
 
+// --------------------------------------------------- the reference's planned operators (README.md:64-65)
+// conv (+ReLU) + pooling: the planned jit_avx512_core_u8s8s32x_convolution_relu_pool_op
+// (test/test_conv_relu_pooling.cc:262-278 sketches its arguments: conv src / wei / bia / stride / padding / dst,
+// scales, relu, round mode, then pool dst / stride / padding / kernel / round mode).  The conv stage is the conv-only
+// operator writing `conv_dst`'s device mirror; the pooling kernel follows on the same stream and reads it from L2.
+// submit() uploads the source and downloads only the pooled result.
+class conv_pool_op : public conv_op {
+public:
+  conv_pool_op(const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei, const std::unique_ptr<memory> &bia,
+               std::array<int, 2> sz_stride, std::array<int, 2> sz_padding, std::unique_ptr<memory> &conv_dst,
+               std::unique_ptr<memory> &pool_dst, int kind, std::array<int, 2> pool_kernel, std::array<int, 2> pool_stride,
+               std::array<int, 2> pool_padding, bool conv_relu, const std::vector<float> &conv_scales, round_mode conv_round,
+               round_mode pool_round)
+      : conv_op(src, wei, bia, sz_stride, sz_padding, conv_dst, conv_scales, std::vector<float>{1.f}, nullptr, nullptr,
+                conv_relu, false, conv_round, round_mode::nearest),
+        pool_dst_(pool_dst.get()) {
+    if (!pool_dst || pool_dst->dim_format() != memory::format::nhwc || pool_dst->data_type() != conv_dst->data_type()) {
+      info("Pooling destination must be nhwc with the conv destination's data type");
+      error_and_exit("Init Pooling op failed!");
+    }
+    const memory::dims c = conv_dst->actual_dims(), o = pool_dst->actual_dims();  // nhwc
+    memset(&pd_, 0, sizeof pd_);
+    pd_.dtype = detail::dt_code(conv_dst->data_type());
+    pd_.kind = kind;
+    pd_.n = c[0];
+    pd_.h = c[1];
+    pd_.w = c[2];
+    pd_.c = c[3];
+    pd_.kh = pool_kernel[0];
+    pd_.kw = pool_kernel[1];
+    pd_.sh = pool_stride[0];
+    pd_.sw = pool_stride[1];
+    pd_.ph = pool_padding[0];
+    pd_.pw = pool_padding[1];
+    pd_.oh = o.size() == 4 ? o[1] : 0;
+    pd_.ow = o.size() == 4 ? o[2] : 0;
+    pd_.round_mode = pool_round == round_mode::down ? DF_ROUND_DOWN : DF_ROUND_NEAREST;
+    // output size: floor((h + 2p - k) / s) + 1, or one more where a last window still starts inside the image (padR)
+    const int oh0 = (pd_.h + 2 * pd_.ph - pd_.kh) / pd_.sh + 1, ow0 = (pd_.w + 2 * pd_.pw - pd_.kw) / pd_.sw + 1;
+    if (o.size() != 4 || o[0] != c[0] || o[3] != c[3] || (pd_.oh != oh0 && pd_.oh != oh0 + 1) || (pd_.ow != ow0 && pd_.ow != ow0 + 1) ||
+        df_pool_check(&pd_) != 0) {
+      info("Pooling output size do not match: %s", df_last_error());
+      error_and_exit("Init Pooling op failed!");
+    }
+  }
+  void launch(void *stream) override {
+    conv_op::launch(stream);
+    cuda_or_exit(df_pool_run(&pd_, mirror(*dst_), mirror(*pool_dst_), pd_.n, stream), "pool launch");
+  }
+  int launches() const override { return 2; }
+
+protected:
+  void infer() override {
+    cuda_or_exit(df_h2d(mirror(*src_), src_->data(), src_->buffer_size(), nullptr), "conv H2D");
+    launch(nullptr);
+    cuda_or_exit(df_d2h(pool_dst_->data(), mirror(*pool_dst_), pool_dst_->buffer_size(), nullptr), "pool D2H");
+    cuda_or_exit(df_stream_sync(nullptr), "conv+pool sync");
+  }
+  const char *name() override { return "conv+relu+pooling"; }
+
+private:
+  memory *pool_dst_;
+  df_pool_desc pd_;
+};
+
+// conv / fused conv + eltwise sum + ReLU (README.md:65): `residual` has dst's dims and type and is added to the scaled
+// result before the ReLU (df_conv_create_sum / df_conv_run_sum).
+class conv_sum_op : public conv_op {
+public:
+  conv_sum_op(const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei, const std::unique_ptr<memory> &bia,
+              std::array<int, 2> sz_stride, std::array<int, 2> sz_padding, const std::unique_ptr<memory> &wei1x1,
+              const std::unique_ptr<memory> &bia1x1, const std::unique_ptr<memory> &residual, std::unique_ptr<memory> &dst,
+              bool conv0_relu, const std::vector<float> &conv0_scales, round_mode r0, bool conv1_relu,
+              const std::vector<float> &conv1_scales, round_mode r1)
+      : conv_op(src, wei, bia, sz_stride, sz_padding, dst, conv0_scales, conv1_scales, wei1x1, bia1x1, conv0_relu, conv1_relu,
+                r0, r1, /*create_handle=*/false),
+        res_mem_(residual.get()) {
+    if (!residual || residual->data_type() != dst->data_type() || residual->dim_format() != memory::format::nhwc ||
+        residual->actual_dims() != dst->actual_dims()) {
+      info("Eltwise-sum input must have the destination's dims, format and data type");
+      error_and_exit("Init Conv op failed!");
+    }
+    sr_ = new sum_resources();
+    detail::adopt_resources(this, sr_);
+    int rc = df_conv_create_sum(&desc_, static_cast<const int8_t *>(wei->data()),
+                                wei1x1 ? static_cast<const int8_t *>(wei1x1->data()) : nullptr, bia ? bia->data() : nullptr,
+                                bia1x1 ? bia1x1->data() : nullptr, conv0_scales.data(), conv1_scales.data(), &sr_->handle);
+    if (rc == DF_E_UNSUPPORTED) error_and_exit("unsupported on B200 path: %s", df_last_error());
+    if (rc != 0) {
+      info("%s", df_last_error());
+      error_and_exit("Init Conv op failed!");
+    }
+  }
+  void launch(void *stream) override {
+    cuda_or_exit(df_conv_run_sum(sr_->handle, static_cast<const uint8_t *>(mirror(*src_)), mirror(*res_mem_), mirror(*dst_),
+                                 desc_.n, stream), "conv+sum launch");
+  }
+  int launches() const override { return 1; }
+
+protected:
+  void infer() override {
+    cuda_or_exit(df_h2d(mirror(*src_), src_->data(), src_->buffer_size(), nullptr), "conv H2D");
+    cuda_or_exit(df_h2d(mirror(*res_mem_), res_mem_->data(), res_mem_->buffer_size(), nullptr), "residual H2D");
+    launch(nullptr);
+    cuda_or_exit(df_d2h(dst_->data(), mirror(*dst_), dst_->buffer_size(), nullptr), "conv D2H");
+    cuda_or_exit(df_stream_sync(nullptr), "conv+sum sync");
+  }
+  const char *name() override { return "conv+eltwise-sum+relu"; }
+
+private:
+  struct sum_resources : detail::op_resources {
+    df_conv *handle = nullptr;
+    ~sum_resources() override { df_conv_destroy(handle); }
+  };
+  memory *res_mem_;
+  sum_resources *sr_ = nullptr;
+};
+
 }  // namespace
 
 // ---------------------------------------------------------------------------- factories
@@ -809,6 +927,24 @@ std::unique_ptr<op> concat_conv(const std::vector<std::unique_ptr<memory>> &srcs
   return std::unique_ptr<op>(new concat_conv_op(shape, srcs, concat_relu, wei, bia, sz_stride, sz_padding, dst, conv0_scales,
                                                 conv1_scales, wei1x1, bia1x1, conv0_relu, conv1_relu, conv0_round_mode,
                                                 conv1_round_mode));
+}
+std::unique_ptr<op> conv_pool(const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei,
+                              const std::unique_ptr<memory> &bia, std::array<int, 2> sz_stride, std::array<int, 2> sz_padding,
+                              std::unique_ptr<memory> &conv_dst, std::unique_ptr<memory> &pool_dst, pool_kind kind,
+                              std::array<int, 2> pool_kernel, std::array<int, 2> pool_stride, std::array<int, 2> pool_padding,
+                              bool conv_relu, std::vector<float> conv_scales, round_mode conv_round_mode,
+                              round_mode pool_round_mode) {
+  return std::unique_ptr<op>(new conv_pool_op(src, wei, bia, sz_stride, sz_padding, conv_dst, pool_dst, (int)kind, pool_kernel,
+                                              pool_stride, pool_padding, conv_relu, conv_scales, conv_round_mode, pool_round_mode));
+}
+std::unique_ptr<op> conv_sum(const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei,
+                             const std::unique_ptr<memory> &bia, std::array<int, 2> sz_stride, std::array<int, 2> sz_padding,
+                             const std::unique_ptr<memory> &wei1x1, const std::unique_ptr<memory> &bia1x1,
+                             const std::unique_ptr<memory> &residual, std::unique_ptr<memory> &dst, bool conv0_relu,
+                             std::vector<float> conv0_scales, round_mode conv0_round_mode, bool conv1_relu,
+                             std::vector<float> conv1_scales, round_mode conv1_round_mode) {
+  return std::unique_ptr<op>(new conv_sum_op(src, wei, bia, sz_stride, sz_padding, wei1x1, bia1x1, residual, dst, conv0_relu,
+                                             conv0_scales, conv0_round_mode, conv1_relu, conv1_scales, conv1_round_mode));
 }
 bool concat_conv_is_fused(op &o) {
   concat_conv_op *c = dynamic_cast<concat_conv_op *>(&o);

@@ -100,6 +100,32 @@ dfh_op *dfh_concat_conv_create(dfh_memory *const *srcs, int n, int concat_relu, 
   for (int i = 0; i < n; ++i) srcs[i]->m.reset(v[i].release());
   return h;
 }
+dfh_op *dfh_conv_pool_create(dfh_memory *src, dfh_memory *wei, dfh_memory *bia, const int stride[2], const int padding[2],
+                             dfh_memory *conv_dst, dfh_memory *pool_dst, int kind, const int pk[2], const int ps[2],
+                             const int pp[2], int conv_relu, const float *s0, int n0, int r0, int pool_round) {
+  static const std::unique_ptr<memory> none;
+  std::vector<float> sc0(s0, s0 + (n0 > 0 ? n0 : 0));
+  if (sc0.empty()) sc0.push_back(1.f);
+  dfh_op *h = new dfh_op();
+  h->o = ext::conv_pool(src->m, wei->m, bia ? bia->m : none, {stride[0], stride[1]}, {padding[0], padding[1]}, conv_dst->m,
+                        pool_dst->m, (ext::pool_kind)kind, {pk[0], pk[1]}, {ps[0], ps[1]}, {pp[0], pp[1]}, conv_relu != 0, sc0,
+                        (round_mode)r0, (round_mode)pool_round);
+  return h;
+}
+dfh_op *dfh_conv_sum_create(dfh_memory *src, dfh_memory *wei, dfh_memory *bia, const int stride[2], const int padding[2],
+                            dfh_memory *wei1x1, dfh_memory *bia1x1, dfh_memory *residual, dfh_memory *dst, int conv0_relu,
+                            const float *s0, int n0, int r0, int conv1_relu, const float *s1, int n1, int r1) {
+  static const std::unique_ptr<memory> none;
+  std::vector<float> sc0(s0, s0 + (n0 > 0 ? n0 : 0)), sc1;
+  if (sc0.empty()) sc0.push_back(1.f);
+  if (s1 && n1 > 0) sc1.assign(s1, s1 + n1);
+  if (sc1.empty()) sc1.push_back(1.f);
+  dfh_op *h = new dfh_op();
+  h->o = ext::conv_sum(src->m, wei->m, bia ? bia->m : none, {stride[0], stride[1]}, {padding[0], padding[1]},
+                       wei1x1 ? wei1x1->m : none, bia1x1 ? bia1x1->m : none, residual->m, dst->m, conv0_relu != 0, sc0,
+                       (round_mode)r0, conv1_relu != 0, sc1, (round_mode)r1);
+  return h;
+}
 int dfh_concat_conv_is_fused(dfh_op *op) { return ext::concat_conv_is_fused(*op->o) ? 1 : 0; }
 void dfh_sharded_upload(dfh_op *op) { ext::sharded_upload(*op->o); }
 void dfh_sharded_sync(dfh_op *op) { ext::sharded_sync(*op->o); }

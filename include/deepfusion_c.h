@@ -45,6 +45,16 @@ dfh_op *dfh_concat_conv_create(dfh_memory *const *srcs, int n_srcs, int concat_r
                                int conv0_round_mode, int conv1_relu, const float *conv1_scales, int n_conv1_scales,
                                int conv1_round_mode);
 int dfh_concat_conv_is_fused(dfh_op *op);
+/* ext::conv_pool(): conv (+ReLU) into conv_dst, pooled (kind 0 max / 1 avg incl. padding / 2 avg excl.) into pool_dst */
+dfh_op *dfh_conv_pool_create(dfh_memory *src, dfh_memory *wei, dfh_memory *bia, const int stride[2], const int padding[2],
+                             dfh_memory *conv_dst, dfh_memory *pool_dst, int kind, const int pool_kernel[2],
+                             const int pool_stride[2], const int pool_padding[2], int conv_relu, const float *conv_scales,
+                             int n_conv_scales, int conv_round_mode, int pool_round_mode);
+/* ext::conv_sum(): conv / fused conv + eltwise sum of `residual` + ReLU */
+dfh_op *dfh_conv_sum_create(dfh_memory *src, dfh_memory *wei, dfh_memory *bia, const int stride[2], const int padding[2],
+                            dfh_memory *wei1x1, dfh_memory *bia1x1, dfh_memory *residual, dfh_memory *dst, int conv0_relu,
+                            const float *conv0_scales, int n_conv0_scales, int conv0_round_mode, int conv1_relu,
+                            const float *conv1_scales, int n_conv1_scales, int conv1_round_mode);
 void dfh_sharded_upload(dfh_op *op);   /* slabs -> devices (device-resident timing) */
 void dfh_sharded_sync(dfh_op *op);     /* wait for every device */
 void dfh_sharded_download(dfh_op *op); /* devices -> host destination, synchronous */

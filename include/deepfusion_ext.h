@@ -48,6 +48,25 @@ std::unique_ptr<op> concat_conv(const std::vector<std::unique_ptr<memory>> &srcs
                                 bool conv1_relu = false, std::vector<float> conv1_scales = {1.f},
                                 round_mode conv1_round_mode = round_mode::nearest);
 bool concat_conv_is_fused(op &o);
+// The two operators the reference lists as planned (README.md:64-65; it ships only their MKL-DNN yardstick,
+// test/test_conv_relu_pooling.cc).  Semantics: include/dfcuda.h (df_pool_run, df_conv_run_sum).
+enum class pool_kind { max = 0, avg_include_padding = 1, avg_exclude_padding = 2 };
+// conv (+ReLU) + pooling: conv() writing `conv_dst` (kept on the device), pooled into `pool_dst` (same data type, nhwc).
+std::unique_ptr<op> conv_pool(const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei,
+                              const std::unique_ptr<memory> &bia, std::array<int, 2> sz_stride, std::array<int, 2> sz_padding,
+                              std::unique_ptr<memory> &conv_dst, std::unique_ptr<memory> &pool_dst, pool_kind kind,
+                              std::array<int, 2> pool_kernel, std::array<int, 2> pool_stride, std::array<int, 2> pool_padding,
+                              bool conv_relu = true, std::vector<float> conv_scales = {1.f},
+                              round_mode conv_round_mode = round_mode::nearest, round_mode pool_round_mode = round_mode::nearest);
+// conv() / fused conv() + eltwise sum + ReLU: `residual` (dst's dims, format, data type) is added before the ReLU.
+// wei1x1 == nullptr selects the conv-only operator.
+std::unique_ptr<op> conv_sum(const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei,
+                             const std::unique_ptr<memory> &bia, std::array<int, 2> sz_stride, std::array<int, 2> sz_padding,
+                             const std::unique_ptr<memory> &wei1x1, const std::unique_ptr<memory> &bia1x1,
+                             const std::unique_ptr<memory> &residual, std::unique_ptr<memory> &dst, bool conv0_relu = true,
+                             std::vector<float> conv0_scales = {1.f}, round_mode conv0_round_mode = round_mode::nearest,
+                             bool conv1_relu = true, std::vector<float> conv1_scales = {1.f},
+                             round_mode conv1_round_mode = round_mode::nearest);
 // device-resident use of a sharded op (timing): upload the slabs once, submit_device() launches the kernels on
 // every device, sharded_sync() waits for all of them, sharded_download() brings the result back
 void sharded_upload(op &o);

@@ -153,6 +153,71 @@ def test_concat_conv_submit(H, ics, fused):
     assert np.array_equal(dst.array(), want)
 
 
+@pytest.mark.parametrize("dst_dt", ["u8", "s8", "s32"])
+@pytest.mark.parametrize("shape", [
+    # src nchw, conv window / pad, conv dst nchw, pool window / stride, kind, dst nchw
+    ((1, 16, 4, 4), 3, 0, (1, 16, 2, 2), 2, 2, 0, (1, 16, 1, 1)),          # test_conv_relu_pooling.cc:314-315 (first VGG entry)
+    ((2, 64, 12, 12), 3, 1, (2, 128, 12, 12), 2, 2, 0, (2, 128, 6, 6)),    # :316-317 at a reduced image size
+    ((2, 32, 7, 7), 1, 0, (2, 320, 7, 7), 7, 7, 2, (2, 320, 1, 1)),        # :341-342 style: 1x1 conv + 7x7 average, excl. padding
+], ids=["vgg_first", "vgg_block", "global_avg"])
+def test_conv_relu_pool_submit(H, shape, dst_dt):
+    """ext::conv_pool through the C++ API on the reference's own shape list (reduced sizes): submit() == oracle conv
+    followed by oracle pooling."""
+    from dfb200 import synth, layout
+    sd, k, pad, cd, pk, ps, kind, od = shape
+    n, ic, h, w = sd
+    oc = cd[1]
+    src_a = synth.src_u8(1, (n, h, w, ic))
+    wb = layout.oihw_to_blocked(synth.wei_s8(2, (oc, ic, k, k)))
+    b0 = synth.bias(4, oc, "s32")
+    s0 = synth.channel_scales(oc, int(np.ceil(np.log2(ic * k * k * 64.0))) - 4)
+    src = H.Memory(sd, "nhwc", "u8"); src.set(src_a)
+    wei = H.Memory((oc, ic, k, k), "OIhw4i16o4i", "s8"); wei.array().reshape(-1)[...] = wb
+    bia = H.Memory((oc,), "x", "s32", nchw=False); bia.set(b0)
+    conv_dst = H.Memory(cd, "nhwc", dst_dt)
+    dst = H.Memory(od, "nhwc", dst_dt)
+    op = H.conv_pool(src, wei, bia, (1, 1), (pad, pad), conv_dst, dst, kind, (pk, pk), (ps, ps), (0, 0), conv_relu=True, conv_scales=s0)
+    assert op.launches() == 2
+    op.submit()
+    d = O.make_desc(n, h, w, ic, oc, 0, O.DT_OF[dst_dt], O.S32, O.UNDEF, k=k, pad=pad, relu0=1, nscale0=oc)
+    want = O.pool(O.conv(d, src_a, wb, b0, s0), kind, pk, ps, 0)
+    assert want.any()
+    assert np.array_equal(dst.array().view(np.uint8), want.view(np.uint8))
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["conv_only", "fused"])
+def test_conv_sum_submit(H, fused):
+    """ext::conv_sum through the C++ API: conv (+1x1) + residual + ReLU == the oracle's dfo_conv_sum."""
+    from dfb200 import synth, layout
+    n, h, w, ic, oc, oc1 = 2, 7, 7, 64, 64, (256 if fused else 0)
+    src_a = synth.src_u8(1, (n, h, w, ic))
+    wb = layout.oihw_to_blocked(synth.wei_s8(2, (oc, ic, 3, 3)))
+    b0 = synth.bias(4, oc, "s32")
+    s0 = synth.channel_scales(oc, 12)
+    out_c = oc1 or oc
+    res_a = synth.uniform_int(41, (n, h, w, out_c), 0, 255, np.uint8)
+    src = H.Memory((n, ic, h, w), "nhwc", "u8"); src.set(src_a)
+    wei = H.Memory((oc, ic, 3, 3), "OIhw4i16o4i", "s8"); wei.array().reshape(-1)[...] = wb
+    bia = H.Memory((oc,), "x", "s32", nchw=False); bia.set(b0)
+    res = H.Memory((n, out_c, h, w), "nhwc", "u8"); res.set(res_a)
+    dst = H.Memory((n, out_c, h, w), "nhwc", "u8")
+    if fused:
+        w1b = layout.oihw_to_blocked(synth.wei_s8(3, (oc1, oc)).reshape(oc1, oc, 1, 1))
+        b1 = synth.bias(5, oc1, "s32")
+        s1 = synth.channel_scales(oc1, 12)
+        wei1 = H.Memory((oc1, oc, 1, 1), "OIhw4i16o4i", "s8"); wei1.array().reshape(-1)[...] = w1b
+        bia1 = H.Memory((oc1,), "x", "s32", nchw=False); bia1.set(b1)
+        op = H.conv_sum(src, wei, bia, (1, 1), (1, 1), res, dst, wei1x1=wei1, bia1x1=bia1, conv0_scales=s0, conv1_scales=s1)
+        d = O.make_desc(n, h, w, ic, oc, oc1, O.U8, O.S32, O.S32, relu0=1, relu1=1, nscale0=oc, nscale1=oc1)
+        want = O.conv_sum(d, src_a, wb, b0, s0, res_a, w1b, b1, s1)
+    else:
+        op = H.conv_sum(src, wei, bia, (1, 1), (1, 1), res, dst, conv0_scales=s0)
+        d = O.make_desc(n, h, w, ic, oc, 0, O.U8, O.S32, O.UNDEF, relu0=1, nscale0=oc)
+        want = O.conv_sum(d, src_a, wb, b0, s0, res_a)
+    op.submit()
+    assert np.array_equal(dst.array(), want)
+
+
 def _conv_memories(H, c, n=None):
     n = n or c.n
     src_a, w0, w1, b0, b1, s0, s1 = cases.ConvCase(c.name, n, c.h, c.w, c.ic, c.oc, c.oc1, c.dst, c.b0, c.b1, c.r0, c.r1,
