@@ -303,6 +303,66 @@ def time_shape(df, st, wl, steps, peaks, rank=0):
     return out
 
 
+def time_concat_conv(df, st, steps, rank=0):
+    """concat+ReLU (BASELINE configs[1] shape) feeding a fused conv, four ways over the same rotating
+    buffer sets (> 2x L2), each a CUDA-graph replay: the concat kernel alone, the conv alone on the materialised
+    tensor, the two chained, and the ONE kernel whose halo loads read the concat's inputs directly."""
+    n, h, w, ics = CONCAT_CFG2
+    ic, oc, oc1 = sum(ics), 128, 512
+    w0b = layout.oihw_to_blocked(synth.wei_s8(2, (oc, ic, 3, 3)))
+    w1b = layout.oihw_to_blocked(synth.wei_s8(3, (oc1, oc)).reshape(oc1, oc, 1, 1))
+    b0, b1 = synth.bias(4, oc, "s32"), synth.bias(5, oc1, "s32")
+    s0, s1 = synth.channel_scales(oc, 13), synth.channel_scales(oc1, 12)
+    conv = df.Conv(n, h, w, ic, oc, oc1, df.U8, w0b, w1b, b0, b1, s0, s1, df.S32, df.S32)
+    fused = df.ConcatConv(n, h, w, ics, True, oc, oc1, df.U8, w0b, w1b, b0, b1, s0, s1, df.S32, df.S32)
+    px = n * h * w
+    per_set = px * (2 * ic + oc1)
+    n_sets = max(2, min(32, -(-2 * L2_BYTES // per_set)))
+    sets = []
+    for k in range(n_sets):
+        ins = [df.DeviceBuffer.from_numpy(synth.uniform_int(20 + i + 100 * rank, (n, h, w, c), 0, 127, np.uint8)) for i, c in enumerate(ics)]
+        sets.append((ins, df.DeviceBuffer(px * ic), df.DeviceBuffer(px * oc1)))
+    cats = [df.ConcatCall(df.U8, True, [b.ptr for b in ins], list(ics), cat.ptr, px, stream=st.ptr) for ins, cat, _ in sets]
+
+    def timed(body):
+        for k in range(3):
+            body(k % n_sets)
+        with df.Graph(st) as g:
+            for k in range(steps):
+                body(k % n_sets)
+        g.launch()
+        st.sync()
+        e0, e1 = df.Event(), df.Event()
+        e0.record(st.ptr)
+        g.launch()
+        e1.record(st.ptr)
+        st.sync()
+        us = e0.elapsed_ms(e1) / steps * 1e3
+        del g, e0, e1
+        return us
+
+    for k in range(n_sets):
+        cats[k]()  # materialise every set's concatenated tensor once (the conv-alone leg reads them)
+    st.sync()
+    us_cat = timed(lambda k: cats[k]())
+    us_conv = timed(lambda k: conv.run(sets[k][1], sets[k][2], stream=st.ptr))
+
+    def chained(k):
+        cats[k]()
+        conv.run(sets[k][1], sets[k][2], stream=st.ptr)
+    us_chain = timed(chained)
+    us_fused = timed(lambda k: fused.run(sets[k][0], sets[k][2], stream=st.ptr))
+    ops = 2.0 * px * (9 * ic * oc + oc * oc1)
+    out = {"workload": f"concat+ReLU u8 {h}x{w} C={'/'.join(map(str, ics))} batch {n} (BASELINE configs[1]) -> conv3x3+ReLU+conv1x1+ReLU {ic}->{oc}->{oc1}, u8 out",
+           "us_concat_alone": us_cat, "us_conv_alone": us_conv, "us_two_kernels": us_chain, "us_fused_one_kernel": us_fused,
+           "fused_tops": ops / us_fused / 1e6, "two_kernel_tops": ops / us_chain / 1e6,
+           "hbm_bytes_saved_per_launch": 2 * px * ic,
+           "cache": f"rotating {n_sets} buffer sets ({n_sets * per_set >> 20} MiB > 2x L2)", "steps": steps}
+    conv.close()
+    fused.close()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import dfb200 as df
     from dfb200 import hostapi as H
@@ -438,6 +498,9 @@ def run_ours(args, rank, world, local_rank):
     if not args.quick and world == 1:
         others = {wl: time_shape(df, st, wl, 50 if wl != "cfg1" else 200, peaks, rank) for wl in ("cfg1", "cfg1x64", "cfg4", "cfg4s32", "cfg4f32")}
 
+    # ---- concat fused into the conv's A-operand load
+    concat_conv = time_concat_conv(df, st, 50, rank) if (not args.quick and world == 1) else None
+
     # ---- end-to-end leg: the reference's API with host buffers (H2D + kernel + D2H per step)
     hsrc = H.Memory((n, ic, h, w), "nhwc", "u8")
     hsrc.set(base)
@@ -513,6 +576,7 @@ def run_ours(args, rank, world, local_rank):
                    "cache": f"rotating {c_sets} buffer sets ({c_sets * c_bytes >> 20} MiB > 2x L2)",
                    "large_footprint": big},
         "other_shapes": others,
+        "concat_conv": concat_conv,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_tops, "unit": "TOPS", "images_per_s": total_images / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": src_bytes, "d2h_bytes_per_step": dst_bytes, "steps": e2e_steps,

@@ -304,7 +304,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
       sum += src_ic[i];
     }
     if (sum != d->ic) return df::fail(DF_E_INVALID, "concat+conv: inputs have %ld channels, the conv expects %d", sum, d->ic);
-    if (d->ic / swb_cat > kMaxKBlocks) return df::fail(DF_E_UNSUPPORTED, "concat+conv: more than %d K-blocks", kMaxKBlocks);
+    if (d->ic / swb_cat > kMaxKBlocks) return df::fail(DF_E_UNSUPPORTED, "concat+conv: more than %d halo K-blocks", kMaxKBlocks);
   }
   if (!wei || !scale0) return df::fail(DF_E_INVALID, "conv: null weights / scales");
   if ((d->bia0_dt != DF_UNDEF && !bia0) || (d->oc1 != 0 && d->bia1_dt != DF_UNDEF && !bia1))
@@ -341,8 +341,10 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
 #else
   p.dbg_no_mma = 0;
 #endif
-  p.swb = fused_cat ? swb_cat : pick_swb(d->ic);
+  p.swb = pick_swb(d->ic);  // weight K-blocks
   p.nkb = (d->ic + p.swb - 1) / p.swb;
+  p.swa = fused_cat ? swb_cat : p.swb;  // halo K-blocks: never straddle two inputs of a fused concat
+  p.nka = (d->ic + p.swa - 1) / p.swa;
   p.n_src = fused_cat ? n_src : 1;
   p.concat_relu = fused_cat && concat_relu;
   op->n_src = p.n_src;
@@ -351,7 +353,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   if (fused_cat)
     for (int i = 0, kb = 0; i < n_src; ++i) {
       op->src_ic[i] = src_ic[i];
-      for (int c0 = 0; c0 < src_ic[i]; c0 += p.swb, ++kb) {
+      for (int c0 = 0; c0 < src_ic[i]; c0 += p.swa, ++kb) {
         p.kb_src[kb] = (unsigned char)i;
         p.kb_c0[kb] = (unsigned short)c0;
       }
@@ -372,7 +374,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   p.OWS = (d->iw + 2 * d->pw - d->kw) / d->sw + 1;
   p.ZR = d->ph > d->kh - 1 - d->ph ? d->ph : d->kh - 1 - d->ph;
   p.Hp = d->ih + p.ZR;
-  const int wp_align = 128 / p.swb;  // every halo row must start 128 B aligned for TMA
+  const int wp_align = 128 / p.swa;  // every halo row must start 128 B aligned for TMA
   p.Wp = (d->iw + zr_w + wp_align - 1) / wp_align * wp_align;
   p.n_box = (p.Wp + 255) / 256;  // TMA boxes are at most 256 positions wide
   p.box_w = ((p.Wp + p.n_box - 1) / p.n_box + wp_align - 1) / wp_align * wp_align;
@@ -501,8 +503,8 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
     p.off_mid = off;
     p.NM = nm;
     off += nm * p.mid_bytes;
-    p.a_kb_stride = (uint32_t)p.NR * p.Wp * p.swb;
-    p.a_stage_bytes = align_up(p.nkb * p.a_kb_stride, 1024);
+    p.a_kb_stride = (uint32_t)p.NR * p.Wp * p.swa;
+    p.a_stage_bytes = align_up(p.nka * p.a_kb_stride, 1024);
     p.w0_block_bytes = (uint32_t)p.OC * p.swb;
     p.w1_block_bytes = (uint32_t)p.nc1 * p.swb1;
     const uint32_t w0_bytes = align_up(taps * p.nkb * p.w0_block_bytes, 1024);
@@ -714,10 +716,10 @@ static int src_maps(df_conv* op, const Params& p, const void* const* ptrs, int n
     const cuuint64_t c = (cuuint64_t)op->src_ic[k];
     cuuint64_t gd[4] = {c, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)n};
     cuuint64_t gs[3] = {c, (cuuint64_t)p.W * c, (cuuint64_t)p.H * p.W * c};
-    cuuint32_t box[4] = {(cuuint32_t)p.swb, (cuuint32_t)p.box_w, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)p.swa, (cuuint32_t)p.box_w, 1, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&s.maps.m[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(ptrs[k]), gd, gs, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(p.swb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(p.swa), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return df::fail(DF_E_INTERNAL, "cuTensorMapEncodeTiled(src %d) failed: %d", k, (int)r);
   }

@@ -121,6 +121,11 @@ struct Params {
   // K-block never straddles two sources).  concat_relu: the reference's literal u8 ReLU (vpmaxsb: bytes >= 128
   // become 0, jit_concat_kernel.cc:43-51) is applied to the halo in shared memory before the tensor pipe reads it.
   int n_src, concat_relu;
+  // A-operand (halo) K-blocks of swa bytes, nka of them: equal to swb / nkb except for a fused concat, whose halo
+  // K-blocks are as narrow as the inputs' channel counts require (32 / 64 / 128 B) while the WEIGHTS keep the widest
+  // K-blocks -- the two operand descriptors of a tcgen05.mma carry their own swizzle mode, and weight blocks of 4 KB
+  // instead of 16 KB would quarter the bytes in flight of the weight ring
+  int swa, nka;
   unsigned char kb_src[kMaxKBlocks];
   unsigned short kb_c0[kMaxKBlocks];
 };
@@ -346,6 +351,7 @@ struct StaticGeom {
   static constexpr int n_chunks = (kOC1 + nc1 - 1) / nc1;
   static constexpr int n_acc0 = kOC <= 128 ? 2 : 1;
   static constexpr int KH = 3, KW = 3, PH = 1, PW = 1;
+  static constexpr int swa = swb, nka = nkb;
 };
 struct DynGeom {
   static constexpr bool is_static = false;
@@ -361,7 +367,7 @@ struct Geo {
   const Params& p;
   DF_GEO(IC) DF_GEO(OC) DF_GEO(OC1) DF_GEO(w0_res) DF_GEO(w1_res) DF_GEO(SB)
   DF_GEO(swb) DF_GEO(nkb) DF_GEO(ks_last) DF_GEO(swb1) DF_GEO(nkb1) DF_GEO(ks1_last)
-  DF_GEO(nc1) DF_GEO(n_chunks) DF_GEO(n_acc0) DF_GEO(KH) DF_GEO(KW) DF_GEO(PH) DF_GEO(PW)
+  DF_GEO(nc1) DF_GEO(n_chunks) DF_GEO(n_acc0) DF_GEO(KH) DF_GEO(KW) DF_GEO(PH) DF_GEO(PW) DF_GEO(swa) DF_GEO(nka)
   __device__ __forceinline__ uint32_t w0_block_bytes() const { return (uint32_t)(OC() * swb()); }
   __device__ __forceinline__ uint32_t w1_block_bytes() const { return (uint32_t)(nc1() * swb1()); }
   __device__ __forceinline__ uint32_t mid_kb_stride() const { return (uint32_t)(kTileM * swb1()); }
@@ -720,7 +726,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
   const int k_add = kSeed ? 0 : k_uni;  // what the epilogue still has to add to the accumulator
 
   // ---- conv0 epilogue of local tile `it`
-  auto unit_e0 = [&](int it) {
+  auto unit_e0 = [&](int it) __attribute__((always_inline)) {
     const int ab = it % g.n_acc0();
     const int mb = it % p.NM;  // intermediate tile buffer
     mbar_wait_warp(smem_u32(&bar->mid_empty[mb]), ((it / p.NM) & 1) ^ 1);
@@ -730,7 +736,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
     const uint32_t mid = sbase + p.off_mid + mb * p.mid_bytes;
     const uint32_t t_base = lane_addr + ab * g.OC();
     const int nb32 = g.OC() / 32, nblk = nb32 + (g.OC() - nb32 * 32) / 16;
-    auto block = [&](auto ch_c, int col0, bool last) {
+    auto block = [&](auto ch_c, int col0, bool last) __attribute__((always_inline)) {
       constexpr int CH = decltype(ch_c)::value;
       const int ch0 = col0 + CH * m4;  // this thread's CH consecutive conv0 channels
       uint32_t acc[2][2 * CH];
@@ -782,7 +788,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
   };
 
   // ---- conv1 chunk j of local tile `it` (c = global chunk counter of this CTA)
-  auto unit_c = [&](int it, int j, uint32_t c) {
+  auto unit_c = [&](int it, int j, uint32_t c) __attribute__((always_inline)) {
     if (row_it != it) {  // tiles come in increasing order (a group may have no conv1 unit in some tile)
       for (; pos_it < it; ++pos_it) {
         pos_step(p, pos_tile, p.ts_dw, p.ts_dn, p.ts_dh);
@@ -816,7 +822,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
     const uint32_t t_base = c0_only ? lane_addr + ab0 * g.OC() + j * g.nc1() : lane_addr + kAcc1Col + cb * kAcc1Stride;
     const uint32_t stage_buf = sbase + p.off_stage + cb * kStageBytes;
     const int nb32 = ncols / 32, nblk = nb32 + (ncols - nb32 * 32) / 16;
-    auto block = [&](auto ch_c, auto unik_c, int col0, bool last) {
+    auto block = [&](auto ch_c, auto unik_c, int col0, bool last) __attribute__((always_inline)) {
       constexpr int CH = decltype(ch_c)::value;
       constexpr bool kUniK = decltype(unik_c)::value;
       const int ccol = col0 + CH * m4;      // first of this thread's CH channels inside the chunk
@@ -1313,24 +1319,24 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
       const int nrows = g_hi - g_lo + 1;
       const uint32_t full = smem_u32(&bar->a_full[s]);
       const uint32_t stage = sbase + p.off_a + s * p.a_stage_bytes;
-      mbar_expect_tx(full, (uint32_t)(nrows * g.nkb() * p.Wp * g.swb()));
+      mbar_expect_tx(full, (uint32_t)(nrows * g.nka() * p.Wp * g.swa()));
       // row g >= 1 of the padded space is row hp = (g - 1) % Hp of image (g - 1) / Hp, i.e. source row h = hp - ZR
       // (negative: one of the zero rows above the image, filled by the TMA unit); g = 0 is all zero
       int n = (g_lo > 0) ? (g_lo - 1) / p.Hp : 0;
       int h = (g_lo > 0) ? (g_lo - 1) - n * p.Hp - p.ZR : -p.ZR - 1;  // -ZR - 1: the all-zero row above everything
       uint32_t dst = stage;
-      const uint32_t row_bytes = p.Wp * g.swb();
+      const uint32_t row_bytes = p.Wp * g.swa();
       for (int r = 0; r < nrows; ++r, dst += row_bytes) {
         if (multi_src) {
-          for (int kb = 0; kb < g.nkb(); ++kb)
+          for (int kb = 0; kb < g.nka(); ++kb)
             tma_load_4d(dst + kb * p.a_kb_stride, &tmS.m[p.kb_src[kb]], full, (int)p.kb_c0[kb], 0, h, n);
         } else if (!G::is_static && p.n_box > 1) {
-          for (int kb = 0; kb < g.nkb(); ++kb)
+          for (int kb = 0; kb < g.nka(); ++kb)
             for (int bx = 0; bx < p.n_box; ++bx)
-              tma_load_4d(dst + kb * p.a_kb_stride + bx * p.box_w * g.swb(), &tmS.m[0], full, kb * g.swb(), bx * p.box_w, h, n);
+              tma_load_4d(dst + kb * p.a_kb_stride + bx * p.box_w * g.swa(), &tmS.m[0], full, kb * g.swa(), bx * p.box_w, h, n);
         } else {
 #pragma unroll
-          for (int kb = 0; kb < g.nkb(); ++kb) tma_load_4d(dst + kb * p.a_kb_stride, &tmS.m[0], full, kb * g.swb(), 0, h, n);
+          for (int kb = 0; kb < g.nka(); ++kb) tma_load_4d(dst + kb * p.a_kb_stride, &tmS.m[0], full, kb * g.swa(), 0, h, n);
         }
         if (h == -p.ZR - 1) {
           h = -p.ZR;  // g = 1: first row (zero row, if any) of image 0
@@ -1471,7 +1477,9 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
       // descriptors differ only in their 14-bit start-address field (16 B units): constant part + adds
       const uint64_t desc0_hi = make_smem_desc(0, 16, 8 * g.swb(), layout_of(g.swb()));
       const uint64_t desc1_hi = make_smem_desc(0, 16, 8 * g.swb1(), layout_of(g.swb1()));
-      const uint32_t a_step_kw = g.swb() >> 4, a_step_kh = (p.Wp * g.swb()) >> 4, a_step_kb = p.a_kb_stride >> 4;
+      const uint64_t desca_hi = make_smem_desc(0, 16, 8 * g.swa(), layout_of(g.swa()));  // A operand: its own K-block width
+      const uint32_t a_step_kw = g.swa() >> 4, a_step_kh = (p.Wp * g.swa()) >> 4, a_step_kb = p.a_kb_stride >> 4;
+      const int a_ks_per_block = g.swa() >> 5;  // 32-byte K-steps per A K-block
       const uint32_t w0_step = g.w0_block_bytes() >> 4, w1_step = g.w1_block_bytes() >> 4;
       const uint32_t mid_step_kb = g.mid_kb_stride() >> 4, b_stage_step = p.b_stage_bytes >> 4;
       const uint64_t w0_desc = desc0_hi | ((sbase + p.off_w0) >> 4), w1_desc = desc1_hi | ((sbase + p.off_w1) >> 4);
@@ -1511,10 +1519,18 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
               tc_fence_after_sync();
               b_desc = bst0_desc + st * b_stage_step;
             }
-            const uint64_t a_desc = a_tile + kh * a_step_kh + kw * a_step_kw + kb * a_step_kb;
+            const uint64_t a_tap = a_tile + kh * a_step_kh + kw * a_step_kw;
             const int nks = (kb == g.nkb() - 1) ? g.ks_last() : nks_full;
+            if (G::is_static || g.swa() == g.swb()) {
+              const uint64_t a_desc = a_tap + kb * a_step_kb;
 #pragma unroll
-            for (int ks = 0; ks < nks; ++ks) if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+              for (int ks = 0; ks < nks; ++ks) if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+            } else {  // narrower A K-blocks (fused concat): K-step ks of weight block kb lives in A block k32 / a_ks_per_block
+              for (int ks = 0; ks < nks; ++ks) {
+                const int k32 = kb * nks_full + ks, ka = k32 / a_ks_per_block, kr = k32 - ka * a_ks_per_block;
+                if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_tap + ka * a_step_kb + 2 * kr, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+              }
+            }
             if (!g.w0_res()) {
               umma_commit(smem_u32(&bar->b_empty[st]));
               if (++bs == (uint32_t)g.SB()) { bs = 0; bph ^= 1; }
@@ -1566,7 +1582,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
           tc_fence_after_sync();
           tr.ev(10);
           const uint32_t d_tmem = tmem + ab * g.OC();
-          const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swb()) >> 4);
+          const uint64_t a_tile = desca_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swa()) >> 4);
 #pragma unroll
           for (int kh = 0; kh < g.KH(); ++kh) gemm1_taps(kh, 0, g.KW(), d_tmem, a_tile);
           umma_commit(smem_u32(&bar->a_empty[sa]));
@@ -1628,7 +1644,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
                 tc_fence_after_sync();
                 tr.ev(10);
                 d0 = tmem + ab * g.OC();
-                a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swb()) >> 4);
+                a_tile = desca_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swa()) >> 4);
               }
             }
             if (ok) {
@@ -1658,7 +1674,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
             tc_fence_after_sync();
             tr.ev(10);
             const uint32_t d_tmem = tmem + ab * g.OC();
-            const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swb()) >> 4);
+            const uint64_t a_tile = desca_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swa()) >> 4);
 #pragma unroll
             for (int kh = 0; kh < g.KH(); ++kh) gemm1_taps(kh, 0, g.KW(), d_tmem, a_tile);
             umma_commit(smem_u32(&bar->a_empty[sa]));

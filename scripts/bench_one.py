@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.join(ROOT, "scripts"))
 from gpu_quick import bench_conv
 import dfb200 as df
 
-SHAPES = {"cfg1": (56, 56, 64, 64, 256), "cfg3": (28, 28, 128, 128, 512), "cfg4": (14, 14, 256, 256, 1024)}
+SHAPES = {"cfg1": (56, 56, 64, 64, 256), "cfg3": (28, 28, 128, 128, 512), "cfg4": (14, 14, 256, 256, 1024), "cat": (28, 28, 256, 128, 512)}
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 64

@@ -56,3 +56,4 @@ if __name__ == "__main__":
     if which == "cfg1": run(nb, 56, 56, 64, 64, 256)
     elif which == "cfg3": run(nb, 28, 28, 128, 128, 512, skip=skip)
     elif which == "cfg4": run(256, 14, 14, 256, 256, 1024)
+    elif which == "cat": run(nb, 28, 28, 256, 128, 512, skip=skip, max_lines=260)  # the conv behind BASELINE configs[1]'s concat (run-time geometry)

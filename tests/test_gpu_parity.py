@@ -567,3 +567,24 @@ def test_conv_eltwise_sum(df, shape, dst):
     got = op(src, res)
     op.close()
     _assert_same(got, want, dst)
+
+
+# ------------------------------------------------------------------ geometry edges of the padded pixel space
+# (advisor, round 1: widths at the TMA box limit, Wp values for which 128 % Wp hits the halo-row edge, tall images,
+# many conv1 chunks)
+EDGE_GEOMETRY = [
+    # n, h, w, ic, oc, oc1
+    (2, 5, 2, 16, 16, 32), (1, 4, 42, 64, 32, 48), (1, 3, 128, 128, 32, 32), (1, 2, 253, 16, 32, 32), (1, 2, 254, 64, 16, 32),
+    (1, 2, 255, 128, 16, 16), (1, 3, 127, 16, 32, 32), (1, 3, 63, 32, 16, 16), (1, 70, 3, 16, 16, 16), (1, 5, 5, 32, 32, 1040),
+    (3, 1, 129, 16, 16, 32), (1, 3, 31, 128, 32, 32),
+]
+
+
+@pytest.mark.parametrize("g", EDGE_GEOMETRY, ids=lambda g: "x".join(map(str, g)))
+def test_fused_conv_geometry_edges(df, g):
+    n, h, w, ic, oc, oc1 = g
+    c = cases.ConvCase("edge", n, h, w, ic, oc, oc1, "u8", "s32", "s32")
+    got = _gpu_conv(df, c)
+    want = _oracle_conv(c, fast=False)
+    _assert_same(got, want, "u8")
+    assert want.any()
