@@ -565,7 +565,7 @@ def run_ours(args, rank, world, local_rank):
                      "peak_source": f"2 x bf16_tflops of MEASURED_PEAKS.json ({peaks['which']}); int8 dense rate = 2 x bf16",
                      "frac_of_i8_mma_probe": kernel_tops_this_rank / probe if probe else None,
                      "i8_mma_probe_tops": probe, "i8_mma_probe_source": (consts.get("i8_mma_probe") or {}).get("source"),
-                     "kernel": "conv_pair_kernel" if info.w0_resident == 2 else "conv_fused_kernel", "ops_per_launch": n * ops_per_image(p),
+                     "kernel": "conv_pair_kernel" if info.w0_resident >= 2 else "conv_fused_kernel", "ops_per_launch": n * ops_per_image(p),
                      "sustained": sustained},
         "concat": {"workload": "concat+ReLU u8, 28x28, C=64/128/32/32, batch 32 (BASELINE configs[1])", "value": concat_gbs,
                    "unit": "GB/s", "us_per_launch": c_ms * 1e3, "bytes_per_launch": c_bytes,

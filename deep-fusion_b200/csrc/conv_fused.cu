@@ -640,32 +640,52 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   // the maximum (a later handle with a smaller plan must not lower it under an earlier handle's launches)
   DF_TRY_CUDA(op->kernel.attr(kSmemLimit));
 
-  // ---- CTA-pair variant: BASELINE cfg3 with everything resident once the weights are split in two.
-  // Default for that shape (DF_PAIR=0 selects the single-CTA kernel, which has to stream 144 KB of
-  // 3x3 weights per 128-position tile -- more than the L2 delivers at tensor-pipe speed).
-  if (shape_id == 3 && static_ok && !(getenv("DF_PAIR") && atoi(getenv("DF_PAIR")) == 0)) {
+  // ---- CTA-pair variants (conv_pair_kernel; DF_PAIR=0 selects the single-CTA kernels).
+  //   cfg3: everything resident once the weights are split in two -- the single-CTA kernel has to stream 144 KB of
+  //         3x3 weights per 128-position tile, more than the L2 delivers at tensor-pipe speed;
+  //   cfg4: 832 KB of weights cannot be resident, but streaming HALVES per CTA halves the L2 traffic per tile and
+  //         doubles what one ring stage feeds (DF_PAIR4=0 keeps the single-CTA kernel for this shape only).
+  const bool pair_on = !(getenv("DF_PAIR") && atoi(getenv("DF_PAIR")) == 0);
+  const bool pair4_on = pair_on && !(getenv("DF_PAIR4") && atoi(getenv("DF_PAIR4")) == 0);
+  if (((shape_id == 3 && pair_on) || (shape_id == 4 && pair4_on)) && static_ok) {
     Params q = p;
-    q.w0_res = q.w1_res = 1;
-    q.SB = 1;
+    const bool resident = shape_id == 3;
+    q.w0_res = q.w1_res = resident ? 1 : 0;
     q.stage_out = 0;
     q.off_stage = 0;
-    q.NM = 2;
+    q.NM = resident ? 2 : 1;
     uint32_t off2 = p.off_mid + q.NM * q.mid_bytes;
-    q.off_w0 = off2;
-    off2 += align_up(9 * q.nkb * (q.w0_block_bytes / 2), 1024);
-    q.off_w1 = off2;
-    off2 += align_up(q.n_chunks * q.nkb1 * (q.w1_block_bytes / 2), 1024);
+    if (resident) {
+      q.off_w0 = off2;
+      off2 += align_up(9 * q.nkb * (q.w0_block_bytes / 2), 1024);
+      q.off_w1 = off2;
+      off2 += align_up(q.n_chunks * q.nkb1 * (q.w1_block_bytes / 2), 1024);
+    }
     q.off_a = off2;
     q.a_kb_stride = (uint32_t)(q.NR + 1) * q.Wp * q.swb;  // one extra row of slack before the tile origin
     q.a_stage_bytes = align_up(q.nkb * q.a_kb_stride, 1024);
-    const int sa = (int)((avail - q.off_a) / q.a_stage_bytes);
-    if (sa >= 2) {
+    bool ok;
+    if (resident) {
+      const int sa = (int)((avail - q.off_a) / q.a_stage_bytes);
+      ok = sa >= 2;
       q.SA = sa > kMaxAStages ? kMaxAStages : sa;
+      q.SB = 1;
       q.off_b = q.off_a + q.SA * q.a_stage_bytes;
       q.b_stage_bytes = 0;
-      op->pair_prm = q;
       op->pair_smem = q.off_b + 1024;
-      op->pair_kernel = pick_pair_cfg3(d->dst_dt);
+    } else {
+      q.SA = 2;
+      q.off_b = q.off_a + q.SA * q.a_stage_bytes;
+      const uint32_t half0 = q.w0_block_bytes / 2, half1 = q.w1_block_bytes / 2;
+      q.b_stage_bytes = align_up(half0 > half1 ? half0 : half1, 1024);
+      const int sb = q.off_b < avail ? (int)((avail - q.off_b) / q.b_stage_bytes) : 0;
+      ok = sb >= 2;
+      q.SB = sb > kMaxBStages ? kMaxBStages : sb;
+      op->pair_smem = q.off_b + q.SB * q.b_stage_bytes + 1024;
+    }
+    if (ok) {
+      op->pair_prm = q;
+      op->pair_kernel = resident ? pick_pair_cfg3(d->dst_dt) : pick_pair_cfg4(d->dst_dt);
       DF_TRY_CUDA(op->pair_kernel.attr(kSmemLimit));
       DF_TRY(encode_2d(&op->tmW0h, op->d_w0, q.swb, (long)9 * q.nkb * q.OC, q.OC / 2));
       DF_TRY(encode_2d(&op->tmW1h, op->d_w1, q.swb1, (long)q.n_chunks * q.nkb1 * q.nc1, q.nc1 / 2));
@@ -875,10 +895,10 @@ extern "C" int df_conv_query(const df_conv* op, df_conv_info* info) {
   info->grid = info->tiles_per_launch < op->sms ? info->tiles_per_launch : op->sms;
   info->block = kThreads;
   info->smem_bytes = (int)(op->pair ? op->pair_smem : op->smem_bytes);
-  info->w0_resident = op->pair ? 2 : p.w0_res;  // 2 = resident, split across a CTA pair
-  info->w1_resident = op->pair ? 2 : p.w1_res;
+  info->w0_resident = op->pair ? (op->pair_prm.w0_res ? 2 : 3) : p.w0_res;  // 2 = resident, split across a CTA pair; 3 = halves streamed by a CTA pair
+  info->w1_resident = op->pair ? (op->pair_prm.w1_res ? 2 : 3) : p.w1_res;
   info->a_stages = op->pair ? op->pair_prm.SA : p.SA;
-  info->b_stages = op->pair ? 0 : p.SB;
+  info->b_stages = op->pair ? (op->pair_prm.w0_res ? 0 : op->pair_prm.SB) : p.SB;
   info->padded_w = p.Wp;
   info->padded_h = p.Hp;
   info->macs_per_image = (double)p.OHS * p.OWS * ((double)p.KH * p.KW * p.IC * p.OC + (p.conv0_only ? 0.0 : (double)p.OC * p.OC1));

@@ -1,0 +1,13 @@
+// conv_inst_pair4.cu -- conv_pair_kernel instantiations (BASELINE cfg4 on CTA pairs, streamed weight halves), see conv_kernels.cuh
+#include "conv_kernels.cuh"
+namespace dfconv {
+KernelFn pick_pair_cfg4(int dst_dt) {
+  using G = GeoCfg4P;
+  switch (dst_dt) {
+    case DF_U8: return KernelFn{launch_pair<G, DF_U8>, attr_pair<G, DF_U8>};
+    case DF_S8: return KernelFn{launch_pair<G, DF_S8>, attr_pair<G, DF_S8>};
+    case DF_S32: return KernelFn{launch_pair<G, DF_S32>, attr_pair<G, DF_S32>};
+    default: return KernelFn{launch_pair<G, DF_F32>, attr_pair<G, DF_F32>};
+  }
+}
+}  // namespace dfconv

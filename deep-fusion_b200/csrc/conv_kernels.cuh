@@ -1362,6 +1362,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
       // the writes are made visible to the async proxy and a_ready[s] tells the MMA thread.  The next tile's
       // loads are issued BEFORE the clamp when their stage is already free, after it otherwise (the stage is
       // released by GEMM1 of tile it + 1 - SA, which itself may be waiting for this clamp).
+      Tracer tr(p, 0);
       griddep_wait();
       if (lane == 0 && n_local > 0) issue_halo(0);  // stage 0 is free at kernel start
       for (int it = 0; it < n_local; ++it) {
@@ -1375,26 +1376,30 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
         }
         const int s = it % p.SA;
         mbar_wait_warp(smem_u32(&bar->a_full[s]), (it / p.SA) & 1);
+        if (lane == 0) tr.ev(2);
         const uint32_t stage = sbase + p.off_a + s * p.a_stage_bytes;
-        for (uint32_t off = (uint32_t)lane * 16u; off < p.a_stage_bytes; off += 4 * 512u) {
-          uint32_t v[4][4];
+        // (a_stage_bytes is a multiple of 1024: two 16-byte vectors per lane and step, four steps in flight.  The
+        // clamp is two instructions per word: PRMT in sign-replicate mode builds 0xFF for every byte >= 128, LOP3
+        // clears those bytes -- the producer warp is alone with this work, so its issue rate is what bounds it.)
+#pragma unroll 4
+        for (uint32_t off = (uint32_t)lane * 16u; off < p.a_stage_bytes; off += 1024u) {
+          uint32_t v[2][4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (off + u * 512u < p.a_stage_bytes)
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3])
-                           : "r"(stage + off + u * 512u));
+          for (int u = 0; u < 2; ++u)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3])
+                         : "r"(stage + off + u * 512u));
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (off + u * 512u < p.a_stage_bytes) {
+          for (int u = 0; u < 2; ++u) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) v[u][i] = __vmaxs4(v[u][i], 0u);
-              sts128(stage + off + u * 512u, v[u]);
-            }
+            for (int i = 0; i < 4; ++i) v[u][i] &= ~__byte_perm(v[u][i], 0u, 0xba98);  // == __vmaxs4(x, 0)
+            sts128(stage + off + u * 512u, v[u]);
+          }
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to tcgen05.mma (async proxy)
         __syncwarp();
         if (lane == 0) {
+          tr.ev(3);
           mbar_arrive(smem_u32(&bar->a_ready[s]));
           if (!issued) {
             mbar_wait(smem_u32(&bar->a_empty[(it + 1) % p.SA]), (((it + 1) / p.SA) & 1) ^ 1);
@@ -1480,6 +1485,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
       const uint64_t desca_hi = make_smem_desc(0, 16, 8 * g.swa(), layout_of(g.swa()));  // A operand: its own K-block width
       const uint32_t a_step_kw = g.swa() >> 4, a_step_kh = (p.Wp * g.swa()) >> 4, a_step_kb = p.a_kb_stride >> 4;
       const int a_ks_per_block = g.swa() >> 5;  // 32-byte K-steps per A K-block
+      const int a_ks_shift = a_ks_per_block == 4 ? 2 : (a_ks_per_block == 2 ? 1 : 0);
       const uint32_t w0_step = g.w0_block_bytes() >> 4, w1_step = g.w1_block_bytes() >> 4;
       const uint32_t mid_step_kb = g.mid_kb_stride() >> 4, b_stage_step = p.b_stage_bytes >> 4;
       const uint64_t w0_desc = desc0_hi | ((sbase + p.off_w0) >> 4), w1_desc = desc1_hi | ((sbase + p.off_w1) >> 4);
@@ -1526,9 +1532,13 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
 #pragma unroll
               for (int ks = 0; ks < nks; ++ks) if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
             } else {  // narrower A K-blocks (fused concat): K-step ks of weight block kb lives in A block k32 / a_ks_per_block
+              // (swa divides swb, both powers of two: A block / step inside it by shift and mask, descriptors by addition)
+              uint64_t a_blk = a_tap + (uint64_t)(((kb * nks_full) >> a_ks_shift) * a_step_kb);
+              int kr = 0;
+#pragma unroll 4
               for (int ks = 0; ks < nks; ++ks) {
-                const int k32 = kb * nks_full + ks, ka = k32 / a_ks_per_block, kr = k32 - ka * a_ks_per_block;
-                if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_tap + ka * a_step_kb + 2 * kr, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+                if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_blk + 2 * kr, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+                if (++kr == a_ks_per_block) { kr = 0; a_blk += a_step_kb; }
               }
             }
             if (!g.w0_res()) {
@@ -1741,6 +1751,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
 struct PairBarriers {
   uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
   uint64_t res_full[4], peer_ready[4];  // resident weights arrive in four parts: W0 tap rows 0..2, W1
+  uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];  // streamed weight halves (G::w0_res == 0): ring of stages
   uint64_t acc0_full[2], acc0_empty[2];
   uint64_t mid_full[2], mid_empty[2];
   uint64_t acc1_full[2], acc1_empty[2];
@@ -1754,7 +1765,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ DstMaps tmD,
                  const __grid_constant__ Params p) {
-  static_assert(G::is_static && G::n_acc0 == 2 && G::nc1 == 128 && G::OC % 64 == 0, "pair kernel: unsupported geometry");
+  static_assert(G::is_static && G::nc1 == 128 && G::OC % 64 == 0 && G::w0_res == G::w1_res, "pair kernel: unsupported geometry");
+  // G::w0_res == 1: the weight halves are resident for the whole kernel (BASELINE cfg3).
+  // G::w0_res == 0: they stream through a ring of stages (BASELINE cfg4: 576 + 256 KB of weights).  Each CTA loads
+  //   ITS half of every block (rows [r * N/2, (r+1) * N/2)), so a pair pulls every weight byte out of the L2 once
+  //   per 256 positions instead of once per 128 -- the single-CTA kernel is bound by exactly that traffic -- and a
+  //   stage of S bytes feeds twice the MMA work, so the latency-bound ring delivers twice the rate.  One thread of
+  //   the leader issues both GEMMs in the ring's fixed order: GEMM1(it), then GEMM2(it - 1).
+  constexpr bool kResident = G::w0_res != 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   PairBarriers* bar = reinterpret_cast<PairBarriers*>(smem);
@@ -1790,6 +1808,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&bar->stage_empty[i]), 1);
     }
     for (int i = 0; i < kG1Ahead; ++i) mbar_init(smem_u32(&bar->g1_prog[i]), 1);
+    for (int i = 0; i < kMaxBStages; ++i) {
+      mbar_init(smem_u32(&bar->b_full[i]), 2);   // one expect_tx arrival per CTA of the pair (leader's copy is used)
+      mbar_init(smem_u32(&bar->b_empty[i]), 1);  // multicast commit of the MMAs that read the stage
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW0);
@@ -1835,6 +1857,24 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ++n;
           }
         }
+      }
+    }
+  } else if (warp == 2 && !kResident) {
+    // ============================ streamed weight halves (both CTAs) ===========================
+    if (elect_one()) {
+      uint32_t s = 0, ph = 1;  // stage cursor and the parity to wait for on this CTA's b_empty
+      auto load_half = [&](const CUtensorMap* tm, uint32_t bytes, int row) __attribute__((always_inline)) {
+        mbar_wait(smem_u32(&bar->b_empty[s]), ph);
+        const uint32_t leader_full = mapa_u32(smem_u32(&bar->b_full[s]), 0);
+        mbar_expect_tx_cluster(leader_full, bytes);
+        tma_load_2d_pair(sbase + p.off_b + s * p.b_stage_bytes, tm, leader_full, 0, row);
+        if (++s == (uint32_t)p.SB) { s = 0; ph ^= 1; }
+      };
+      for (int it = 0; it <= n_local; ++it) {  // same order as the MMA thread below
+        if (it < n_local)
+          for (int b = 0; b < kNW0; ++b) load_half(&tmW0, kW0Half, b * G::OC + (int)rank * kHalfRows0);
+        if (it >= 1)
+          for (int b = 0; b < kNW1; ++b) load_half(&tmW1, kW1Half, b * G::nc1 + (int)rank * kHalfRows1);
       }
     }
   } else if (warp == 2) {
@@ -1890,6 +1930,86 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int ks = 0; ks < nks; ++ks)
                 if (!dbg_flag(p, 1)) umma_i8_pair(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, seeded_acc1<G>() || (kb | ks) != 0);
+            }
+            umma_commit_pair(smem_u32(&bar->acc1_full[cb]));
+            tr.ev(13);
+          }
+          umma_commit_pair(smem_u32(&bar->mid_empty[mb]));
+        }
+      }
+    }
+  } else if (warp == 1 && !kResident) {
+    // ====================== MMA issuer, streamed weights (leader only): GEMM1(it), GEMM2(it - 1) ======================
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc0 = make_idesc_i8(2 * kTileM, G::OC, 0, 1), idesc1 = make_idesc_i8(2 * kTileM, G::nc1, 0, 1);
+      const uint64_t desc0_hi = make_smem_desc(0, 16, 8 * G::swb, layout_of(G::swb));
+      const uint64_t desc1_hi = make_smem_desc(0, 16, 8 * G::swb1, layout_of(G::swb1));
+      const uint32_t a_step_kw = G::swb >> 4, a_step_kh = (p.Wp * G::swb) >> 4, a_step_kb = p.a_kb_stride >> 4;
+      const uint64_t bst0_desc = desc0_hi | ((sbase + p.off_b) >> 4), bst1_desc = desc1_hi | ((sbase + p.off_b) >> 4);
+      const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid) >> 4);
+      const uint32_t b_stage_step = p.b_stage_bytes >> 4;
+      Tracer tr(p, 1);
+      tr.ev(9);
+      uint32_t sa = 0, a_par = 0, bs = 0, bph = 0, c1count = 0;
+      for (int it = 0; it <= n_local; ++it) {
+        if (it < n_local) {
+          const int ab = it % G::n_acc0;
+          mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / G::n_acc0) & 1) ^ 1);
+          mbar_wait(smem_u32(&bar->a_full[sa]), a_par);
+          tc_fence_after_sync();
+          tr.ev(10);
+          const uint32_t d0 = tmem + ab * G::OC;
+          const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_origin) >> 4);
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll
+              for (int kb = 0; kb < G::nkb; ++kb) {
+                const int blk = (kh * 3 + kw) * G::nkb + kb;
+                mbar_wait(smem_u32(&bar->b_full[bs]), bph);
+                tc_fence_after_sync();
+                const uint64_t b_desc = bst0_desc + (uint64_t)(bs * b_stage_step);
+                const uint64_t a_desc = a_tile + kh * a_step_kh + kw * a_step_kw + kb * a_step_kb;
+                constexpr int nks_full = G::swb >> 5;
+                const int nks = (kb == G::nkb - 1) ? G::ks_last : nks_full;
+#pragma unroll
+                for (int ks = 0; ks < nks; ++ks)
+                  if (!dbg_flag(p, 1)) umma_i8_pair(d0, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+                umma_commit_pair(smem_u32(&bar->b_empty[bs]));
+                if (++bs == (uint32_t)p.SB) { bs = 0; bph ^= 1; }
+              }
+            }
+          }
+          umma_commit_pair(smem_u32(&bar->a_empty[sa]));
+          umma_commit_pair(smem_u32(&bar->acc0_full[ab]));
+          tr.ev(11);
+          if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
+        }
+        if (it >= 1) {
+          const int jt = it - 1, mb = jt % p.NM;
+          mbar_wait(smem_u32(&bar->mid_full[mb]), (jt / p.NM) & 1);
+          tc_fence_after_sync();
+          tr.ev(12);
+          const uint64_t mid_it = mid_desc + (uint64_t)((mb * p.mid_bytes) >> 4);
+          for (int j = 0; j < G::n_chunks; ++j, ++c1count) {
+            const uint32_t cb = c1count & 1;
+            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ (seeded_acc1<G>() ? 0 : 1));
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
+#pragma unroll
+            for (int kb = 0; kb < G::nkb1; ++kb) {
+              mbar_wait(smem_u32(&bar->b_full[bs]), bph);
+              tc_fence_after_sync();
+              const uint64_t b_desc = bst1_desc + (uint64_t)(bs * b_stage_step);
+              const uint64_t a_desc = mid_it + kb * ((kTileM * G::swb1) >> 4);
+              constexpr int nks_full = G::swb1 >> 5;
+              const int nks = (kb == G::nkb1 - 1) ? G::ks1_last : nks_full;
+#pragma unroll
+              for (int ks = 0; ks < nks; ++ks)
+                if (!dbg_flag(p, 1)) umma_i8_pair(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, seeded_acc1<G>() || (kb | ks) != 0);
+              umma_commit_pair(smem_u32(&bar->b_empty[bs]));
+              if (++bs == (uint32_t)p.SB) { bs = 0; bph ^= 1; }
             }
             umma_commit_pair(smem_u32(&bar->acc1_full[cb]));
             tr.ev(13);
@@ -2030,9 +2150,11 @@ using GeoCfg1 = StaticGeom<64, 64, 256, 1, 1, 1>;      // 56x56  64->64->256 : e
 using GeoCfg3 = StaticGeom<128, 128, 512, 0, 1, 3>;    // 28x28 128->128->512: W1 resident, W0 through 3 stages
 using GeoCfg4 = StaticGeom<256, 256, 1024, 0, 0, 2>;   // 14x14 256->256->1024: all weights through 2 stages
 using GeoCfg3P = StaticGeom<128, 128, 512, 1, 1, 1>;   // cfg3 on CTA pairs: weight halves resident (conv_pair_kernel)
+using GeoCfg4P = StaticGeom<256, 256, 1024, 0, 0, 2>;  // cfg4 on CTA pairs: weight halves streamed (conv_pair_kernel)
 
 // defined in conv_inst_*.cu
 KernelFn pick_pair_cfg3(int dst_dt);                                             // conv_pair_kernel<GeoCfg3P, dst>
+KernelFn pick_pair_cfg4(int dst_dt);                                             // conv_pair_kernel<GeoCfg4P, dst>
 KernelFn pick_static_geom(int geom_id, int dst_dt);                              // conv_fused_kernel<GeoCfg{1,3,4}, dst>
 KernelFn pick_dynamic_u8(bool down0, bool down1, bool nan_safe);                 // conv_fused_kernel<DynGeom, ...>
 KernelFn pick_dynamic_s8(bool down0, bool down1, bool nan_safe);
