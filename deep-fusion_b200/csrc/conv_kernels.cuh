@@ -1392,7 +1392,11 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[u][i] &= ~__byte_perm(v[u][i], 0u, 0xba98);  // == __vmaxs4(x, 0)
+            for (int i = 0; i < 4; ++i) {  // == __vmaxs4(x, 0); (__byte_perm masks the selector's replicate bits: PTX)
+              uint32_t neg;
+              asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(neg) : "r"(v[u][i]));
+              v[u][i] &= ~neg;
+            }
             sts128(stage + off + u * 512u, v[u]);
           }
         }

@@ -6,17 +6,21 @@
  * --impl reference legs may link or call it; the product path (deep-fusion_b200/) never does.
  *
  * PARITY PINNING STATUS
- *   conv  : *parity unpinned* -- the reference holds no golden vector or working test for the
- *           fused conv (test/test_conv.cc:63-82 and benchmark/bench_conv.cc:41-44 are stubs)
- *           and the reference itself cannot be built here (needs Xbyak, un-vendored).  The
- *           oracle is cross-checked by an independent numpy int64 model (tests/) and by
- *           oracle/df_replay_avx512.c, which replays the emitted x86 instruction sequence
- *           with intrinsics.
- *   concat: pinned to the reference's own test shape list and data ranges
- *           (test/test_concat.cc:122-153, test/test_utils.h:49-63) on which copy+ReLU is
- *           unambiguous; the literal signed-max quirks outside that range follow
- *           src/jit_concat_kernel.cc:43-51.
- *   helpers: dividable_of / find_dividable pinned by test/test_misc.cc:25-36.
+ *   conv, concat: PINNED TO THE REFERENCE EXECUTING.  oracle/_ref/libdfref.so is the reference's own
+ *           generator sources (src/jit_conv_kernel.cc, src/jit_concat_kernel.cc, src/op_concat.cc,
+ *           src/deepfusion.cc ...), compiled unmodified from /root/reference against a recording stand-in
+ *           for the un-vendored Xbyak (oracle/xbyak_shim/) and executed instruction by instruction with the
+ *           host's AVX-512 units (oracle/ref_driver.cc, recipe: oracle/Makefile target _ref).
+ *           tests/test_ref_pin.py asserts this oracle == that library, bit for bit, on every fused case of
+ *           tests/cases.py, the conv-only operator, 16 other windows / strides / paddings, 4 fused windows,
+ *           and the reference's own concat test list (test/test_concat.cc:122-153) on its data range and
+ *           on full-range data.  The reference holds no golden vectors of its own (test/test_conv.cc:63-82
+ *           and benchmark/bench_conv.cc:41-44 are stubs).  Further cross-checks: an independent numpy int64
+ *           model (tests/np_model.py) and oracle/df_replay_avx512.c (intrinsics replay, also the timed CPU arm).
+ *   helpers: dividable_of / find_dividable pinned by test/test_misc.cc:25-36; the blocking picked by
+ *           jit_conv_kernel::init_conf is compared with dfo_conv_blocking in tests/test_ref_pin.py.
+ *   dfo_conv_sum, dfo_pool: PARITY UNPINNED -- the reference lists these operators as planned (README.md:64-65)
+ *           and has no implementation; see the comments at their definitions.
  */
 #ifndef DF_ORACLE_H_
 #define DF_ORACLE_H_
