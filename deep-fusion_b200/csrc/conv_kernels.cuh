@@ -197,6 +197,9 @@ __device__ __forceinline__ void trace_wallclock(const Params& p, int slot) {
 #define DF_G1_AHEAD 2
 #endif
 constexpr int kG1Ahead = DF_G1_AHEAD;
+#ifndef DF_G1_FREE_FIRST
+#define DF_G1_FREE_FIRST 1  // A/B knob: 1 = the first tile's GEMM1 is not throttled (CTA-pair kernel)
+#endif
 
 // Build knobs for A/B measurements (defaults = the production configuration):
 //   DF_SEED        1: the static kernels keep the conv1 accumulators pre-seeded with the offset-magic constant
@@ -2049,7 +2052,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
-            if (tap_i >= (uint32_t)kG1Ahead)  // throttle, see kG1Ahead
+            // throttle, see kG1Ahead.  Not for the first tile: no conv1 chunk can be waiting behind it, and the waits
+            // stretch its GEMM1 -- the whole pipeline's fill -- from 2304 to ~3300 cycles.  (Skipped waits leave
+            // the two progress barriers a phase behind for a tap or two; the throttle is advisory, not a dependency.)
+            if (DF_G1_FREE_FIRST ? (it > 0 && tap_i >= (uint32_t)kG1Ahead) : (tap_i >= (uint32_t)kG1Ahead))
               mbar_wait(smem_u32(&bar->g1_prog[tap_i % kG1Ahead]), ((tap_i / kG1Ahead) - 1) & 1);
 #pragma unroll
             for (int kb = 0; kb < G::nkb; ++kb) {

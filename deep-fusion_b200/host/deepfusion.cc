@@ -306,7 +306,8 @@ public:
     cuda_or_exit(df_conv_run(handle_, static_cast<const uint8_t *>(mirror(*src_)), mirror(*dst_), desc_.n, stream),
                  "conv launch");
   }
-  int launches() const override { return desc_.n >= 8 ? 4 : 1; }  // slabs of the pipelined submit()
+  static int submit_slabs(int n) { return n >= 32 ? 8 : (n >= 8 ? 4 : 1); }
+  int launches() const override { return submit_slabs(desc_.n); }  // slabs of the pipelined submit()
 
 protected:
   // op_conv<T>::init_conf (src/op_conv.cc:262-365) + the format gate of
@@ -415,7 +416,7 @@ protected:
   // what bounds this path -- the kernel itself is ~4 % of it.
   void infer() override {
     const int n = desc_.n;
-    const int slabs = n >= 8 ? 4 : 1;
+    const int slabs = submit_slabs(n);
     uint8_t *d_src = static_cast<uint8_t *>(mirror(*src_)), *d_dst = static_cast<uint8_t *>(mirror(*dst_));
     const uint8_t *h_src = static_cast<const uint8_t *>(src_->data());
     uint8_t *h_dst = static_cast<uint8_t *>(dst_->data());
@@ -433,13 +434,58 @@ protected:
       if (!ds->pinned && df_host_register(dst_->data(), dst_->buffer_size()) == 0) ds->pinned = true;
       streams_.resize(3);
       for (void *&st : streams_) cuda_or_exit(df_stream_create(&st), "stream create");
-      events_.resize(2 * slabs);
+      events_.resize(2 * slabs + 2);
       for (void *&e : events_) cuda_or_exit(df_event_create(&e), "event create");
     }
+    // The pipeline is the same every time (the op's memories are fixed for its lifetime, src/op_conv.h:82-95), so
+    // it is captured ONCE into a CUDA graph -- copies, kernels and the cross-stream dependencies -- and every
+    // submit() is one graph launch instead of ~7 runtime calls per slab (their host cost was a fifth of the step).
+    if (!res_->graph && !res_->graph_failed) {
+      if (df_graph_begin(streams_[0]) == 0) {
+        enqueue_pipeline(slabs);
+        // join the kernel and download streams back into the capture's origin stream
+        cuda_or_exit(df_event_record(events_[2 * slabs], streams_[1]), "event record");
+        cuda_or_exit(df_stream_wait_event(streams_[0], events_[2 * slabs]), "stream wait");
+        cuda_or_exit(df_event_record(events_[2 * slabs + 1], streams_[2]), "event record");
+        cuda_or_exit(df_stream_wait_event(streams_[0], events_[2 * slabs + 1]), "stream wait");
+        if (df_graph_end(streams_[0], &res_->graph) != 0) res_->graph_failed = true;
+      } else {
+        res_->graph_failed = true;
+      }
+    }
+    if (res_->graph) {
+      cuda_or_exit(df_graph_launch(res_->graph, streams_[0]), "conv graph launch");
+      cuda_or_exit(df_stream_sync(streams_[0]), "conv sync");
+      return;
+    }
+    enqueue_pipeline(slabs);
+    cuda_or_exit(df_stream_sync(streams_[2]), "conv sync");
+  }
+
+  // upload of slab i+1 | kernel of slab i | download of slab i-1 on three streams
+  void enqueue_pipeline(int slabs) {
+    const int n = desc_.n;
+    uint8_t *d_src = static_cast<uint8_t *>(mirror(*src_)), *d_dst = static_cast<uint8_t *>(mirror(*dst_));
+    const uint8_t *h_src = static_cast<const uint8_t *>(src_->data());
+    uint8_t *h_dst = static_cast<uint8_t *>(dst_->data());
     const size_t src_img = src_->buffer_size() / n, dst_img = dst_->buffer_size() / n;
-    const int per = (n + slabs - 1) / slabs;
-    for (int i = 0, first = 0; i < slabs && first < n; ++i, first += per) {
-      const int cnt = first + per <= n ? per : n - first;
+    // slab sizes: a small first slab (the downloads -- the long pole, 4x the upload bytes for u8 in / u8 out at
+    // OC1 = 4 IC -- start as early as possible), the rest in equal parts
+    static const char *plan_env = getenv("DF_SUBMIT_PLAN");  // development knob: "e" = equal slabs
+    const bool progressive = !(plan_env && plan_env[0] == 'e') && slabs >= 4 && n >= 4 * slabs;
+    const int first_cnt = progressive ? std::max(1, n / (4 * slabs)) : 0;
+    const int per = progressive ? (n - first_cnt + slabs - 2) / (slabs - 1) : (n + slabs - 1) / slabs;
+    for (int i = 0, first = 0; i < slabs && first < n; ++i) {
+      const int want = (progressive && i == 0) ? first_cnt : per;
+      const int cnt = first + want <= n ? want : n - first;
+      enqueue_slab(i, first, cnt, d_src, d_dst, h_src, h_dst, src_img, dst_img);
+      first += cnt;
+    }
+  }
+  void enqueue_slab(int i, int first, int cnt, uint8_t *d_src, uint8_t *d_dst, const uint8_t *h_src, uint8_t *h_dst,
+                    size_t src_img, size_t dst_img) {
+    std::vector<void *> &streams_ = res_->streams, &events_ = res_->events;
+    {
       cuda_or_exit(df_h2d(d_src + first * src_img, h_src + first * src_img, cnt * src_img, streams_[0]), "conv H2D");
       cuda_or_exit(df_event_record(events_[2 * i], streams_[0]), "event record");
       cuda_or_exit(df_stream_wait_event(streams_[1], events_[2 * i]), "stream wait");
@@ -448,7 +494,6 @@ protected:
       cuda_or_exit(df_stream_wait_event(streams_[2], events_[2 * i + 1]), "stream wait");
       cuda_or_exit(df_d2h(h_dst + first * dst_img, d_dst + first * dst_img, cnt * dst_img, streams_[2]), "conv D2H");
     }
-    cuda_or_exit(df_stream_sync(streams_[2]), "conv sync");
   }
   const char *name() override { return "conv"; }
 
@@ -457,7 +502,10 @@ private:
   struct resources : detail::op_resources {
     df_conv *handle = nullptr;
     std::vector<void *> streams, events;  // created on the first pipelined submit()
+    void *graph = nullptr;                // the captured pipeline (see infer())
+    bool graph_failed = false;
     ~resources() override {
+      if (graph) df_graph_destroy(graph);
       df_conv_destroy(handle);
       for (void *e : events) df_event_destroy(e);
       for (void *st : streams) df_stream_destroy(st);
