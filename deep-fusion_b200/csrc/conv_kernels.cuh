@@ -197,6 +197,9 @@ __device__ __forceinline__ void trace_wallclock(const Params& p, int slot) {
 #define DF_G1_AHEAD 2
 #endif
 constexpr int kG1Ahead = DF_G1_AHEAD;
+#ifndef DF_WIDE_ST
+#define DF_WIDE_ST 1  // A/B knob: 256-bit stores for 4-byte destinations in the static epilogue
+#endif
 #ifndef DF_G1_FREE_FIRST
 #define DF_G1_FREE_FIRST 1  // A/B knob: 1 = the first tile's GEMM1 is not throttled (CTA-pair kernel)
 #endif
@@ -215,6 +218,27 @@ template <class G>
 constexpr bool seeded_acc1() { return G::is_static && DF_SEED != 0; }
 template <class G>
 constexpr bool static_epilogue() { return G::is_static && DF_STATIC_EPI != 0; }
+// DF_SEED_CP 1: the seed is written by the tensor pipe itself -- the GEMM2 issuer puts 32 tcgen05.cp (smem -> TMEM,
+// 32 x 128 bit broadcast to the four lane quarters, source = the K vector in shared memory) in front of a chunk's
+// MMAs; tcgen05.cp and tcgen05.mma execute in issue order, so no wait is needed and the epilogue's tcgen05.st +
+// tcgen05.wait::st (150..250 cycles of every conv1 unit's latency chain) disappear.  0: the epilogue warps re-seed.
+#ifndef DF_SEED_CP
+#define DF_SEED_CP 0
+#endif
+template <class G>
+constexpr bool seed_by_cp() { return seeded_acc1<G>() && DF_SEED_CP != 0; }
+template <class G>
+constexpr bool epilogue_seeds() { return seeded_acc1<G>() && DF_SEED_CP == 0; }  // then it also hands the buffers over first
+template <bool kPair>
+__device__ __forceinline__ void seed_chunk_cp(uint32_t d_tmem, uint64_t k_desc) {
+#pragma unroll
+  for (int i = 0; i < kAcc1Stride / 4; ++i) {
+    if constexpr (kPair)
+      asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(d_tmem + 4 * i), "l"(k_desc) : "memory");
+    else
+      asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(d_tmem + 4 * i), "l"(k_desc) : "memory");
+  }
+}
 
 struct Barriers {
   uint64_t a_full[kMaxAStages], a_empty[kMaxAStages];
@@ -560,6 +584,15 @@ __device__ __forceinline__ void stg256_if(void* ptr, const uint32_t* w, bool on)
       "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"((int)on)
       : "memory");
 }
+// the same 32 bytes as ONE 256-bit store (sm_100: st.global.v8.b32, SASS STG.256; the address must be 32-byte
+// aligned): a quad then writes a whole 128-byte line per instruction, and the 4-byte destinations -- whose stores
+// are what the LSU is busiest with -- need half the store instructions
+__device__ __forceinline__ void stg256_wide_if(void* ptr, const uint32_t* w, bool on) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %9, 0;\n\t@p st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n\t}\n" ::"l"(ptr),
+      "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"((int)on)
+      : "memory");
+}
 // CH packed bytes (CH / 4 words) -> shared memory
 template <int CH>
 __device__ __forceinline__ void sts_bytes(uint32_t addr, const uint32_t* packed) {
@@ -706,7 +739,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
   // (re)seeds the columns it reads, right after its tcgen05.ld has landed and before it hands the
   // accumulator back: tcgen05.st -> tcgen05.wait::st -> fence -> arrive on acc1_empty.  TMEM writes run at
   // four times the read rate (B300_MICROARCH.md), the eight registers holding K stay live for the whole role.
-  constexpr bool kSeed = seeded_acc1<G>();
+  constexpr bool kSeed = epilogue_seeds<G>();
   [[maybe_unused]] uint32_t kseed[8];
   auto seed_block = [&](uint32_t taddr32) {  // 32 lanes (this warp's quarter) x 32 columns at taddr32
 #pragma unroll
@@ -726,7 +759,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
       arrive(a_acc1_empty + 8);
     }
   }
-  const int k_add = kSeed ? 0 : k_uni;  // what the epilogue still has to add to the accumulator
+  const int k_add = seeded_acc1<G>() ? 0 : k_uni;  // what the epilogue still has to add to the accumulator
 
   // ---- conv0 epilogue of local tile `it`
   auto unit_e0 = [&](int it) __attribute__((always_inline)) {
@@ -903,8 +936,12 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem, Ba
           }
         } else if (rr >= 0) {
           uint4* out = reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.dst) + ((size_t)rr * p.dst_pitch + p.dst_ch0 + ch0) * 4);
+          if (CH == 8 && (reinterpret_cast<uintptr_t>(out) & 31) == 0) {
+            stg256_wide_if(out, w, true);  // one 256-bit store (see stg256_wide_if)
+          } else {
 #pragma unroll
-          for (int i = 0; i < CH / 4; ++i) out[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+            for (int i = 0; i < CH / 4; ++i) out[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          }
         }
       }
     };
@@ -1014,8 +1051,9 @@ __device__ __forceinline__ void epilogue_static(const Params& p, const DstMaps&,
   griddep_wait();  // earlier kernels in the stream may still be using the destination
 
   // ---- pre-seeded conv1 accumulators: this warp's 32 lanes x 32 columns of both buffers
-  constexpr bool kSeed = seeded_acc1<G>();
-  const int k_add = kSeed ? 0 : p.k1_uniform;
+  constexpr bool kSeed = epilogue_seeds<G>();
+  const int k_add = seeded_acc1<G>() ? 0 : p.k1_uniform;
+  const bool wide_st = DF_WIDE_ST && (reinterpret_cast<uintptr_t>(p.dst) & 31) == 0;  // 4-byte destinations: 256-bit stores
   [[maybe_unused]] uint32_t kseed[8];
   const uint32_t t_acc1 = lane_addr + kAcc1Col + cbi * 32;  // buffer 0; buffer 1: + kAcc1Stride
   auto seed_block = [&](uint32_t taddr32) {
@@ -1040,13 +1078,17 @@ __device__ __forceinline__ void epilogue_static(const Params& p, const DstMaps&,
   // ---- position bookkeeping: lane l tracks tile row quarter * 32 + l (see PosState); the valid rows of the
   //      warp's 32 are the contiguous pixel range [f0, f0 + popc(mask)), row r is pixel f0 + popc(mask below r)
   PosState pos_lane = pos_of(p, q_first + tile0 * kTileM + quarter * 32 + lane);
-  int pos_it = 0;
+  // pixel index of this lane's row in the NEXT tile tile_rows() will be asked for, computed one tile ahead: the
+  // carries and constant-bank loads behind it are a ~500-cycle dependent chain, which sat between the last unit of a
+  // tile and the first of the next (profiles/r02_variants_tile_rows.log); issued a tile early, nobody waits for it
+  int pix_next = pos_pixel(p, pos_lane);
   uint8_t* rptr[4];  // where the thread's rows r8 + 8 ri go (its 8 channels of chunk 0)
   uint32_t rvalid = 0;  // bit ri: row is a real pixel.  (Sending padding rows to a scratch area instead of predicating
                         // the stores was 3.5x slower: every SM hammering the same few L2 lines.)
-  auto tile_rows = [&](int it) {
-    for (; pos_it < it; ++pos_it) pos_step(p, pos_lane, p.ts_dw, p.ts_dn, p.ts_dh);
-    const int pix = pos_pixel(p, pos_lane);
+  auto tile_rows = [&](int) {  // called once per local tile, in order
+    const int pix = pix_next;
+    pos_step(p, pos_lane, p.ts_dw, p.ts_dn, p.ts_dh);
+    pix_next = pos_pixel(p, pos_lane);
     const uint32_t mask = __ballot_sync(0xffffffffu, pix >= 0);
     const int f0 = __shfl_sync(0xffffffffu, pix, mask ? __ffs(mask) - 1 : 0);
 #pragma unroll
@@ -1110,6 +1152,7 @@ __device__ __forceinline__ void epilogue_static(const Params& p, const DstMaps&,
       __syncwarp();
       if (lane == 0) arrive(a_acc0_empty + 8 * ab);
     }
+    tr.ev(34);
     fence_proxy_async_smem();  // intermediate tile -> visible to the tensor pipe (async proxy)
     __syncwarp();
     if (lane == 0) arrive(a_mid_full + 8 * mb);
@@ -1160,6 +1203,7 @@ __device__ __forceinline__ void epilogue_static(const Params& p, const DstMaps&,
       finish_conv1<kDst, false, false, 8, true>(v, c4, s4, nullptr, k_add, true, relu1, w);
       uint8_t* out = rptr[ri] + j * (128 * ts);
       if constexpr (ts == 1) stg64_if(out, w, ((rvalid >> ri) & 1u) && !dbg_flag(p, 4));
+      else if (wide_st) stg256_wide_if(out, w, ((rvalid >> ri) & 1u) && !dbg_flag(p, 4));
       else stg256_if(out, w, ((rvalid >> ri) & 1u) && !dbg_flag(p, 4));
     }
     tr.ev(33);
@@ -1180,6 +1224,10 @@ __device__ __forceinline__ void epilogue_static(const Params& p, const DstMaps&,
   // profiles/r02_variants_seed_epilogue_design.log.)
   uint32_t c = 0;
   if (n_local > 0) unit_e0(0);
+  // (Tried: tile_rows under the first chunk's TMEM load instead of between the tiles -- the row pointers are the address
+  // registers of the previous tile's last stores, and overwriting them waits ~600 cycles for the LSU to take those
+  // stores; inside the unit that wait delays the accumulator's release: 10 % slower on cfg1,
+  // profiles/r02_variants_tile_rows.log.)
   for (int it = 0; it < n_local; ++it) {
     tile_rows(it);
     static_for<G::n_chunks>([&](auto j_c) {
@@ -1464,9 +1512,10 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
           const uint64_t mid_it = mid_desc + (uint64_t)((mb * p.mid_bytes) >> 4);
           for (int j = 0; j < g.n_chunks(); ++j, ++c) {
             const uint32_t cb = c & 1;
-            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c >> 1) & 1) ^ (seeded_acc1<G>() ? 0 : 1));  // seeded: handed over by the epilogue first
+            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c >> 1) & 1) ^ (epilogue_seeds<G>() ? 0 : 1));  // seeded: handed over by the epilogue first
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
+            if constexpr (seed_by_cp<G>()) seed_chunk_cp<false>(d_tmem, make_smem_desc(sbase + p.off_k1, 16, 128, kLayoutNone));
 #pragma unroll
             for (int kb = 0; kb < g.nkb1(); ++kb) {
               const uint64_t b_desc = w1_desc + (uint64_t)((j * g.nkb1() + kb) * w1_step);
@@ -1561,6 +1610,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
       };
       // ---- one N-chunk of GEMM2 with W1 either resident or from the ring
       auto gemm2_chunk = [&](int j, uint32_t d_tmem, uint64_t mid_desc) {
+        if constexpr (seed_by_cp<G>()) seed_chunk_cp<false>(d_tmem, make_smem_desc(sbase + p.off_k1, 16, 128, kLayoutNone));
 #pragma unroll
         for (int kb = 0; kb < g.nkb1(); ++kb) {
           const int blk = j * g.nkb1() + kb;
@@ -1633,7 +1683,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
             }
             if (g2_open) {
               const int cb = c1count & 1;
-              if (mbar_test_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ (seeded_acc1<G>() ? 0 : 1))) {
+              if (mbar_test_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ (epilogue_seeds<G>() ? 0 : 1))) {
                 tc_fence_after_sync();
                 const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid + mb * p.mid_bytes) >> 4);
                 gemm2_chunk(g2_j, tmem + kAcc1Col + cb * kAcc1Stride, mid_desc);
@@ -1709,7 +1759,7 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
             const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid + mb * p.mid_bytes) >> 4);
             for (int j = 0; j < g.n_chunks(); ++j, ++c1count) {
               const int cb = c1count & 1;
-              mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ (seeded_acc1<G>() ? 0 : 1));
+              mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ (epilogue_seeds<G>() ? 0 : 1));
               tc_fence_after_sync();
               gemm2_chunk(j, tmem + kAcc1Col + cb * kAcc1Stride, mid_desc);
               umma_commit(smem_u32(&bar->acc1_full[cb]));
@@ -1925,9 +1975,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < G::n_chunks; ++j, ++c) {
             const uint32_t cb = c & 1;
-            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c >> 1) & 1) ^ (seeded_acc1<G>() ? 0 : 1));  // seeded: handed over by the epilogue first
+            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c >> 1) & 1) ^ (epilogue_seeds<G>() ? 0 : 1));  // seeded: handed over by the epilogue first
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
+            if constexpr (seed_by_cp<G>()) seed_chunk_cp<true>(d_tmem, make_smem_desc(sbase + p.off_k1, 16, 128, kLayoutNone));
 #pragma unroll
             for (int kb = 0; kb < G::nkb1; ++kb) {
               const uint64_t b_desc = w1_desc + (uint64_t)((j * G::nkb1 + kb) * (kW1Half >> 4));
@@ -2001,9 +2052,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t mid_it = mid_desc + (uint64_t)((mb * p.mid_bytes) >> 4);
           for (int j = 0; j < G::n_chunks; ++j, ++c1count) {
             const uint32_t cb = c1count & 1;
-            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ (seeded_acc1<G>() ? 0 : 1));
+            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ (epilogue_seeds<G>() ? 0 : 1));
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
+            if constexpr (seed_by_cp<G>()) seed_chunk_cp<true>(d_tmem, make_smem_desc(sbase + p.off_k1, 16, 128, kLayoutNone));
 #pragma unroll
             for (int kb = 0; kb < G::nkb1; ++kb) {
               mbar_wait(smem_u32(&bar->b_full[bs]), bph);

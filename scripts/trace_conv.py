@@ -7,7 +7,7 @@ import dfb200 as df
 from dfb200 import synth, layout
 
 TAGS = {1: "A.issue", 2: "A.landed", 3: "A.clamped", 8: "M.begin", 9: "M.start", 10: "M.g1_go", 11: "M.g1_issued", 12: "M.g2_go", 13: "M.g2_chunk", 14: "M.tap", 20: "B.iter",
-        30: "E.acc0_ready", 31: "E.epi0_done", 32: "E.acc1_ready", 33: "E.chunk_done", 36: "E.unit_begin", 34: "E.stage_free", 35: "E.math_done", 37: "E.ld_issued", 38: "E.ld_landed", 39: "E.released",
+        30: "E.acc0_ready", 31: "E.epi0_done", 32: "E.acc1_ready", 33: "E.chunk_done", 36: "E.unit_begin", 34: "E.e0_math_done", 35: "E.math_done", 37: "E.ld_issued", 38: "E.ld_landed", 39: "E.released",
         40: "S.full", 41: "S.issued", 42: "S.read_done"}
 
 def run(n, h, w, ic, oc, oc1, dst="u8", cta=0, cap=512, max_lines=120, skip=0, ics=None):
