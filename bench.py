@@ -303,11 +303,12 @@ def time_shape(df, st, wl, steps, peaks, rank=0):
     return out
 
 
-def time_concat_conv(df, st, steps, rank=0):
+def time_concat_conv(df, st, steps, rank=0, batch=None):
     """concat+ReLU (BASELINE configs[1] shape) feeding a fused conv, four ways over the same rotating
     buffer sets (> 2x L2), each a CUDA-graph replay: the concat kernel alone, the conv alone on the materialised
     tensor, the two chained, and the ONE kernel whose halo loads read the concat's inputs directly."""
     n, h, w, ics = CONCAT_CFG2
+    n = batch or n
     ic, oc, oc1 = sum(ics), 128, 512
     w0b = layout.oihw_to_blocked(synth.wei_s8(2, (oc, ic, 3, 3)))
     w1b = layout.oihw_to_blocked(synth.wei_s8(3, (oc1, oc)).reshape(oc1, oc, 1, 1))
@@ -320,7 +321,8 @@ def time_concat_conv(df, st, steps, rank=0):
     n_sets = max(2, min(32, -(-2 * L2_BYTES // per_set)))
     sets = []
     for k in range(n_sets):
-        ins = [df.DeviceBuffer.from_numpy(synth.uniform_int(20 + i + 100 * rank, (n, h, w, c), 0, 127, np.uint8)) for i, c in enumerate(ics)]
+        ins = [df.DeviceBuffer.from_numpy(np.tile(synth.uniform_int(20 + i + 100 * rank, (min(n, 32), h, w, c), 0, 127, np.uint8), (-(-n // 32), 1, 1, 1))[:n])
+               for i, c in enumerate(ics)]
         sets.append((ins, df.DeviceBuffer(px * ic), df.DeviceBuffer(px * oc1)))
     cats = [df.ConcatCall(df.U8, True, [b.ptr for b in ins], list(ics), cat.ptr, px, stream=st.ptr) for ins, cat, _ in sets]
 
@@ -357,7 +359,8 @@ def time_concat_conv(df, st, steps, rank=0):
            "us_concat_alone": us_cat, "us_conv_alone": us_conv, "us_two_kernels": us_chain, "us_fused_one_kernel": us_fused,
            "fused_tops": ops / us_fused / 1e6, "two_kernel_tops": ops / us_chain / 1e6,
            "hbm_bytes_saved_per_launch": 2 * px * ic,
-           "cache": f"rotating {n_sets} buffer sets ({n_sets * per_set >> 20} MiB > 2x L2)", "steps": steps}
+           "cache": f"rotating {n_sets} buffer sets ({n_sets * per_set >> 20} MiB > 2x L2)", "steps": steps,
+           "concatenated_tensor_mib": px * ic / 2 ** 20}
     conv.close()
     fused.close()
     return out
