@@ -218,6 +218,25 @@ template <class G>
 constexpr bool seeded_acc1() { return G::is_static && DF_SEED != 0; }
 template <class G>
 constexpr bool static_epilogue() { return G::is_static && DF_STATIC_EPI != 0; }
+// DF_STATIC_GROUPS 2: the static epilogue runs as TWO independent groups of eight warps (epilogue_static2): group g
+// owns conv1 accumulator g and the chunks that land in it, the conv0 epilogues alternate between the groups.  The
+// groups drift apart, so one group's barrier / TMEM-load / re-seed latency chain runs under the other's arithmetic
+// instead of all 16 warps walking every unit in lock-step.  1: one group of 16 (epilogue_static).
+// 0 (default): two groups only where they measured faster -- conv0 accumulators of <= 64 columns (BASELINE cfg1:
+// +1.3 .. 2.9 %; cfg3 -3.5 %, cfg4 -4 .. 7 %, profiles/r02_variants_two_group_epilogue.log).
+#ifndef DF_STATIC_GROUPS
+#define DF_STATIC_GROUPS 0
+#endif
+template <class G>
+constexpr bool static_two_groups() {
+  if constexpr (G::is_static)
+    return static_epilogue<G>() && G::n_chunks % 2 == 0 && (DF_STATIC_GROUPS == 2 || (DF_STATIC_GROUPS == 0 && G::OC <= 64));
+  else
+    return false;
+}
+// epilogue warps that arrive on a unit's hand-off barriers
+template <class G>
+constexpr int unit_warps() { return static_two_groups<G>() ? kEpiWarps / 2 : kUnitWarps; }
 // DF_SEED_CP 1: the seed is written by the tensor pipe itself -- the GEMM2 issuer puts 32 tcgen05.cp (smem -> TMEM,
 // 32 x 128 bit broadcast to the four lane quarters, source = the K vector in shared memory) in front of a chunk's
 // MMAs; tcgen05.cp and tcgen05.mma execute in issue order, so no wait is needed and the epilogue's tcgen05.st +
@@ -1239,6 +1258,220 @@ __device__ __forceinline__ void epilogue_static(const Params& p, const DstMaps&,
   }
 }
 
+
+// ------------------------------------------------------------- epilogue role, static geometries, two groups
+// Same units, same hand-offs and the same arithmetic as epilogue_static, but the 16 warps form two groups of eight
+// that never wait for each other (DF_STATIC_GROUPS == 2, n_chunks even):
+//   * group g reads conv1 accumulator g: chunk c of the CTA's chunk stream goes to buffer c & 1, and with an even
+//     number of chunks per tile that is chunk index j & 1 -- group 0 takes C_0, C_2, ..., group 1 takes C_1, C_3, ...;
+//   * E0(t) belongs to group t & 1 and sits in that group's sequence in front of its first chunk j >= e0_pos of tile
+//     t - 1 (E0(0) comes first);
+//   * a warp owns its lane quarter's 32 rows x TWO 32-column blocks of a unit (blocks cbi and cbi + 2).  The two blocks
+//     go through ONE set of 32 accumulator registers: the second block's TMEM loads are issued into the halves the
+//     first block's arithmetic has already consumed, so their latency runs under that arithmetic; the accumulator is
+//     re-seeded and released once, after both blocks have landed.
+template <class G, int kDst, bool kPair, class Bar>
+__device__ __forceinline__ void epilogue_static2(const Params& p, uint8_t* smem, Bar* bar, uint32_t tmem, int warp, int lane,
+                                                 int n_local, int tile0, int tile_stride) {
+  static_assert(G::is_static && G::nc1 == 128 && G::OC % 32 == 0 && G::n_chunks % 2 == 0, "epilogue_static2: unsupported geometry");
+  const uint32_t sbase = smem_u32(smem);
+  const int e = warp - kEpiWarp0;               // 0 .. 15
+  const int grp = e >> 3;                       // group = conv1 accumulator buffer
+  const int quarter = e & 3;                    // TMEM lane quarter (= warp & 3)
+  const int cbi = (e >> 2) & 1;                 // first of this warp's 32-column blocks; the other one is cbi + 2
+  const int m4 = lane & 3, r8 = lane >> 2;
+  const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+  constexpr int ts = (kDst == DF_F32 || kDst == DF_S32) ? 4 : 1;
+  const bool relu1 = p.relu1 != 0;
+  const int q_first = p.q_first;
+  const int chl = cbi * 32 + 8 * m4;            // this thread's 8 channels inside block cbi of a chunk (+64: block cbi + 2)
+  const uint32_t sb1 = sbase + p.off_bias1 + 4 * chl, ss1 = sbase + p.off_scale1 + 4 * chl;
+  const uint32_t bar_acc1_full = smem_u32(&bar->acc1_full[grp]), bar_acc0_full = smem_u32(&bar->acc0_full[0]);
+  const uint32_t bar_mid_empty = smem_u32(&bar->mid_empty[0]);
+  uint32_t a_acc0_empty = smem_u32(&bar->acc0_empty[0]), a_acc1_empty = smem_u32(&bar->acc1_empty[grp]);
+  uint32_t a_mid_full = smem_u32(&bar->mid_full[0]);
+  if constexpr (kPair) {
+    a_acc0_empty = mapa_u32(a_acc0_empty, 0);
+    a_acc1_empty = mapa_u32(a_acc1_empty, 0);
+    a_mid_full = mapa_u32(a_mid_full, 0);
+  }
+  auto arrive = [&](uint32_t a) {
+    if constexpr (kPair) mbar_arrive_cluster(a);
+    else mbar_arrive(a);
+  };
+  griddep_wait();  // earlier kernels in the stream may still be using the destination
+
+  constexpr bool kSeed = epilogue_seeds<G>();
+  const int k_add = seeded_acc1<G>() ? 0 : p.k1_uniform;
+  const bool wide_st = DF_WIDE_ST && (reinterpret_cast<uintptr_t>(p.dst) & 31) == 0;
+  [[maybe_unused]] uint32_t kseed[8];
+  const uint32_t t_acc1 = lane_addr + kAcc1Col + grp * kAcc1Stride + cbi * 32;  // block cbi of this group's buffer; block cbi + 2: + 64
+  auto seed_block = [&](uint32_t taddr32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tmem_st_32x32b_x8(taddr32 + 8 * i, kseed);
+  };
+  if constexpr (kSeed) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(kseed[i]) : "r"(sbase + p.off_k1 + 4 * i));
+    seed_block(t_acc1);
+    seed_block(t_acc1 + 64);
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) arrive(a_acc1_empty);
+  }
+
+  PosState pos_lane = pos_of(p, q_first + tile0 * kTileM + quarter * 32 + lane);
+  int pix_next = pos_pixel(p, pos_lane);
+  uint8_t* rptr[4];
+  uint32_t rvalid = 0;
+  auto tile_rows = [&]() {  // once per local tile, in order
+    const int pix = pix_next;
+    pos_step(p, pos_lane, p.ts_dw, p.ts_dn, p.ts_dh);
+    pix_next = pos_pixel(p, pos_lane);
+    const uint32_t mask = __ballot_sync(0xffffffffu, pix >= 0);
+    const int f0 = __shfl_sync(0xffffffffu, pix, mask ? __ffs(mask) - 1 : 0);
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) {
+      const int r = r8 + 8 * ri;
+      const int rho = __popc(mask & ((1u << r) - 1u));
+      rptr[ri] = static_cast<uint8_t*>(p.dst) + ((size_t)(f0 + rho) * G::OC1 + chl) * ts;
+      rvalid = (rvalid & ~(1u << ri)) | (((mask >> r) & 1u) << ri);
+    }
+  };
+
+  // ---- conv0 epilogue of local tile `it` (this group's turn): blocks cbi, cbi + 2, ... of the conv0 accumulator
+  constexpr uint32_t swz_mask1 = (uint32_t)(G::swb1 / 16 - 1);
+  constexpr int nb0 = G::OC / 32;
+  constexpr int kbw = G::swb1;
+  auto unit_e0 = [&](int it) __attribute__((always_inline)) {
+    const int ab = it % G::n_acc0;
+    const int mb = it % p.NM;
+    mbar_wait_warp(bar_mid_empty + 8 * mb, ((it / p.NM) & 1) ^ 1);
+    mbar_wait_warp(bar_acc0_full + 8 * ab, (it / G::n_acc0) & 1);
+    tc_fence_after_sync();
+    const uint32_t mid = sbase + p.off_mid + mb * p.mid_bytes;
+    const uint32_t t_base = lane_addr + ab * G::OC;
+    bool released = false;
+#pragma unroll
+    for (int b = cbi; b < nb0; b += 2) {
+      const int ch0 = b * 32 + 8 * m4;
+      uint32_t acc[2][16];
+      tmem_ld_frag<8>(t_base + b * 32, acc[0]);
+      tmem_ld_frag<8>(t_base + (16u << 16) + b * 32, acc[1]);
+      float4 b4[2], s4[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        b4[i] = lds128f(sbase + p.off_bias0 + 4 * (ch0 + 4 * i));
+        s4[i] = lds128f(sbase + p.off_scale0 + 4 * (ch0 + 4 * i));
+      }
+      const int kb = ch0 / kbw;
+      const uint32_t off0 = (uint32_t)(quarter * 32 + r8) * kbw + (uint32_t)(ch0 - kb * kbw);
+      const uint32_t mid_kb = mid + kb * (uint32_t)(kTileM * kbw);
+      tmem_ld_wait();
+      if (b + 2 >= nb0) {  // last block of this warp: the accumulator is in registers
+        tc_fence_before_sync();
+        if (lane == 0) arrive(a_acc0_empty + 8 * ab);
+        released = true;
+      }
+#pragma unroll
+      for (int ri = 0; ri < 4; ++ri) {
+        uint32_t v[8], packed[2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = acc[ri >> 1][4 * (i / 2) + 2 * (ri & 1) + (i & 1)];
+        uint32_t off = off0 + (uint32_t)(ri * 8) * kbw;
+        off ^= ((off >> 7) & swz_mask1) << 4;
+        finish_conv0<false, false, 8>(v, b4, s4, packed);
+        sts_bytes<8>(mid_kb + off, packed);
+      }
+    }
+    if (!released) {  // warps without a conv0 block (OC < 64)
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) arrive(a_acc0_empty + 8 * ab);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) arrive(a_mid_full + 8 * mb);
+  };
+
+  // ---- conv1 chunk j (compile time) of the current tile; u = how many chunks this group has read before it
+  auto rows2 = [&](const uint32_t* a16, int half, const float4* c4, const float4* s4, int col_off) __attribute__((always_inline)) {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int ri = 2 * half + rr;
+      uint32_t v[8], w[ts == 1 ? 2 : 8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = a16[4 * (i / 2) + 2 * rr + (i & 1)];
+      finish_conv1<kDst, false, false, 8, true>(v, c4, s4, nullptr, k_add, true, relu1, w);
+      uint8_t* out = rptr[ri] + col_off;
+      if constexpr (ts == 1) stg64_if(out, w, (rvalid >> ri) & 1u);
+      else if (wide_st) stg256_wide_if(out, w, (rvalid >> ri) & 1u);
+      else stg256_if(out, w, (rvalid >> ri) & 1u);
+    }
+  };
+  uint32_t pre = 0;
+  auto unit_c = [&](auto j_c, uint32_t u) __attribute__((always_inline)) {
+    constexpr int j = decltype(j_c)::value;
+    if (!__all_sync(0xffffffffu, pre != 0)) mbar_wait_warp(bar_acc1_full, u & 1);
+    tc_fence_after_sync();
+    uint32_t acc[2][16];
+    tmem_ld_frag<8>(t_acc1, acc[0]);
+    tmem_ld_frag<8>(t_acc1 + (16u << 16), acc[1]);
+    float4 c4[2], s4[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      c4[i] = lds128f(sb1 + 4 * (j * 128 + 4 * i));
+      s4[i] = lds128f(ss1 + 4 * (j * 128 + 4 * i));
+    }
+    tmem_ld_wait();
+    // block cbi: rows 0..15 -> then their registers take block cbi + 2's rows 0..15; likewise the upper rows
+    rows2(acc[0], 0, c4, s4, j * (128 * ts));
+    tmem_ld_frag<8>(t_acc1 + 64, acc[0]);
+    rows2(acc[1], 1, c4, s4, j * (128 * ts));
+    tmem_ld_frag<8>(t_acc1 + 64 + (16u << 16), acc[1]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      c4[i] = lds128f(sb1 + 4 * (j * 128 + 64 + 4 * i));
+      s4[i] = lds128f(ss1 + 4 * (j * 128 + 64 + 4 * i));
+    }
+    tmem_ld_wait();
+    if constexpr (kSeed) {
+      seed_block(t_acc1);
+      seed_block(t_acc1 + 64);
+      tmem_st_wait();
+    }
+    tc_fence_before_sync();
+    if (lane == 0) arrive(a_acc1_empty);  // both blocks are in registers: the tensor pipe may overwrite the accumulator
+    pre = mbar_test_wait(bar_acc1_full, (u + 1) & 1) ? 1u : 0u;  // this group's next chunk
+    rows2(acc[0], 0, c4, s4, j * (128 * ts) + 64 * ts);
+    rows2(acc[1], 1, c4, s4, j * (128 * ts) + 64 * ts);
+  };
+
+#ifndef DF_E0_POS
+#define DF_E0_POS (G::n_chunks / 2)
+#endif
+  const int e0_pos = p.NM >= 2 ? ((DF_E0_POS) < G::n_chunks ? (DF_E0_POS) : G::n_chunks - 1) : G::n_chunks - 1;
+  uint32_t u = 0;  // chunks this group has read
+  if (n_local > 0 && grp == 0) unit_e0(0);
+  for (int it = 0; it < n_local; ++it) {
+    tile_rows();
+    bool e0_done = !(it + 1 < n_local && ((it + 1) & 1) == grp);  // is E0(it + 1) ours, and still to do?
+    static_for<G::n_chunks>([&](auto j_c) {
+      constexpr int j = decltype(j_c)::value;
+      if ((j & 1) == grp) {
+        if (!e0_done && j >= e0_pos) {
+          unit_e0(it + 1);
+          e0_done = true;
+        }
+        unit_c(j_c, u);
+        ++u;
+      }
+    });
+    if (!e0_done) unit_e0(it + 1);  // (no chunk of ours at or after e0_pos)
+  }
+}
+
 // ---- store thread of the staged output path (one elected thread of warp 3): sends every staged conv1
 // chunk to the destination (store_staged_chunk) in the order the epilogue produces them
 template <class G, class Bar>
@@ -1326,11 +1559,11 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
     mbar_init(smem_u32(&bar->res_full), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar->acc0_full[i]), 1);
-      mbar_init(smem_u32(&bar->acc0_empty[i]), kUnitWarps);
-      mbar_init(smem_u32(&bar->mid_full[i]), kUnitWarps);
+      mbar_init(smem_u32(&bar->acc0_empty[i]), unit_warps<G>());
+      mbar_init(smem_u32(&bar->mid_full[i]), unit_warps<G>());
       mbar_init(smem_u32(&bar->mid_empty[i]), 1);
       mbar_init(smem_u32(&bar->acc1_full[i]), 1);
-      mbar_init(smem_u32(&bar->acc1_empty[i]), kUnitWarps);
+      mbar_init(smem_u32(&bar->acc1_empty[i]), unit_warps<G>());
       mbar_init(smem_u32(&bar->stage_full[i]), kUnitWarps);
       mbar_init(smem_u32(&bar->stage_empty[i]), 1);
     }
@@ -1773,7 +2006,9 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
   } else if (warp >= kEpiWarp0) {
     // ====================================== epilogue =======================================
     load_epilogue_constants<G>(p, smem);
-    if constexpr (static_epilogue<G>())
+    if constexpr (static_two_groups<G>())
+      epilogue_static2<G, kDst, false>(p, smem, bar, tmem, warp, lane, n_local, (int)blockIdx.x, (int)gridDim.x);
+    else if constexpr (static_epilogue<G>())
       epilogue_static<G, kDst, false>(p, tmD, smem, bar, tmem, warp, lane, n_local, (int)blockIdx.x, (int)gridDim.x);
     else
       epilogue_role<G, kDst, kDown0, kDown1, kNanSafe, false>(p, smem, bar, tmem, warp, lane, n_local, (int)blockIdx.x,
@@ -1856,11 +2091,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar->acc0_full[i]), 1);
-      mbar_init(smem_u32(&bar->acc0_empty[i]), 2 * kUnitWarps);
-      mbar_init(smem_u32(&bar->mid_full[i]), 2 * kUnitWarps);
+      mbar_init(smem_u32(&bar->acc0_empty[i]), 2 * unit_warps<G>());
+      mbar_init(smem_u32(&bar->mid_full[i]), 2 * unit_warps<G>());
       mbar_init(smem_u32(&bar->mid_empty[i]), 1);
       mbar_init(smem_u32(&bar->acc1_full[i]), 1);
-      mbar_init(smem_u32(&bar->acc1_empty[i]), 2 * kUnitWarps);
+      mbar_init(smem_u32(&bar->acc1_empty[i]), 2 * unit_warps<G>());
       mbar_init(smem_u32(&bar->stage_full[i]), kUnitWarps);
       mbar_init(smem_u32(&bar->stage_empty[i]), 1);
     }
@@ -2133,7 +2368,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= kEpiWarp0) {
     // ================================== epilogue (both CTAs) ===================================
     load_epilogue_constants<G>(p, smem);
-    if constexpr (static_epilogue<G>())
+    if constexpr (static_two_groups<G>())
+      epilogue_static2<G, kDst, true>(p, smem, bar, tmem, warp, lane, n_local, 2 * cid + (int)rank, 2 * ncl);
+    else if constexpr (static_epilogue<G>())
       epilogue_static<G, kDst, true>(p, tmD, smem, bar, tmem, warp, lane, n_local, 2 * cid + (int)rank, 2 * ncl);
     else
       epilogue_role<G, kDst, false, false, false, true>(p, smem, bar, tmem, warp, lane, n_local, 2 * cid + (int)rank, 2 * ncl);
