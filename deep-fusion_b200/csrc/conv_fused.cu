@@ -233,8 +233,8 @@ static int conv_create_composite(const df_conv_desc* d, const int8_t* wei, const
       df_conv* part = nullptr;
       rc = conv_create_impl(&g, 0, nullptr, 0, w, nullptr, b, nullptr, scale0 + (d->nscale0 > 1 ? o0 : 0), nullptr, &part, with_sum);
       if (rc) break;
-      part->prm.dst_pitch = d->oc;
-      part->prm.dst_ch0 = o0;
+      part->prm.dst_pitch = part->pair_prm.dst_pitch = d->oc;
+      part->prm.dst_ch0 = part->pair_prm.dst_ch0 = o0;
       op->parts.push_back(part);
     }
   } else {
@@ -645,11 +645,18 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   //         3x3 weights per 128-position tile, more than the L2 delivers at tensor-pipe speed;
   //   cfg4: 832 KB of weights cannot be resident, but streaming HALVES per CTA halves the L2 traffic per tile and
   //         doubles what one ring stage feeds (DF_PAIR4=0 keeps the single-CTA kernel for this shape only).
+  //   run-time geometry: any shape whose weights have to stream (w0_res == 0) runs the streamed pair form too, for the
+  //         same reason as cfg4 (DF_PAIR_DYN=0 keeps the single-CTA kernel); round-to-nearest and finite constants
+  //         only (the pair kernel instantiates one rounding variant), one TMA box per halo row, 128-byte K-blocks
+  //         (ic > 64), no fused concat.
   const bool pair_on = !(getenv("DF_PAIR") && atoi(getenv("DF_PAIR")) == 0);
   const bool pair4_on = pair_on && !(getenv("DF_PAIR4") && atoi(getenv("DF_PAIR4")) == 0);
-  if (((shape_id == 3 && pair_on) || (shape_id == 4 && pair4_on)) && static_ok) {
+  const bool pair_dyn = pair_on && !(getenv("DF_PAIR_DYN") && atoi(getenv("DF_PAIR_DYN")) == 0) && op->geom_id == 0 && !fused_cat &&
+                        p.w0_res == 0 && p.n_box == 1 && !p.nan_safe && p.round0 == DF_ROUND_NEAREST && p.round1 == DF_ROUND_NEAREST &&
+                        p.swb == 128;  // (the pair kernel shifts the TMA destination by whole positions: 128-byte K-blocks only)
+  if ((((shape_id == 3 && pair_on) || (shape_id == 4 && pair4_on)) && static_ok) || pair_dyn) {
     Params q = p;
-    const bool resident = shape_id == 3;
+    const bool resident = shape_id == 3 && !pair_dyn;
     q.w0_res = q.w1_res = resident ? 1 : 0;
     q.stage_out = 0;
     q.off_stage = 0;
@@ -681,13 +688,28 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
       const int sb = q.off_b < avail ? (int)((avail - q.off_b) / q.b_stage_bytes) : 0;
       ok = sb >= 2;
       q.SB = sb > kMaxBStages ? kMaxBStages : sb;
-      op->pair_smem = q.off_b + q.SB * q.b_stage_bytes + 1024;
+      uint32_t end = q.off_b + q.SB * q.b_stage_bytes;
+      if (pair_dyn) {  // staged 1-byte output (generic epilogue) when two staging buffers fit behind >= 3 ring stages
+        const bool want_stage = (d->dst_dt == DF_U8 || d->dst_dt == DF_S8) && q.nc1 == 128 && !with_sum &&
+                                !(getenv("DF_NO_STAGED_STORE") && atoi(getenv("DF_NO_STAGED_STORE")) != 0);
+        const uint32_t need = kStageBufs * kStageBytes;
+        if (want_stage) {
+          while (q.SB > 3 && q.off_b + q.SB * q.b_stage_bytes + need > avail) --q.SB;
+          end = q.off_b + q.SB * q.b_stage_bytes;
+          if (end + need <= avail) {
+            q.stage_out = 1;
+            q.off_stage = end;
+            end += need;
+          }
+        }
+      }
+      op->pair_smem = end + 1024;
     }
     if (ok) {
       op->pair_prm = q;
-      op->pair_kernel = resident ? pick_pair_cfg3(d->dst_dt) : pick_pair_cfg4(d->dst_dt);
+      op->pair_kernel = pair_dyn ? pick_pair_dyn(d->dst_dt) : (resident ? pick_pair_cfg3(d->dst_dt) : pick_pair_cfg4(d->dst_dt));
       DF_TRY_CUDA(op->pair_kernel.attr(kSmemLimit));
-      DF_TRY(encode_2d(&op->tmW0h, op->d_w0, q.swb, (long)9 * q.nkb * q.OC, q.OC / 2));
+      DF_TRY(encode_2d(&op->tmW0h, op->d_w0, q.swb, (long)taps * q.nkb * q.OC, q.OC / 2));
       DF_TRY(encode_2d(&op->tmW1h, op->d_w1, q.swb1, (long)q.n_chunks * q.nkb1 * q.nc1, q.nc1 / 2));
       op->pair = true;
     }

@@ -2057,14 +2057,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ DstMaps tmD,
                  const __grid_constant__ Params p) {
-  static_assert(G::is_static && G::nc1 == 128 && G::OC % 64 == 0 && G::w0_res == G::w1_res, "pair kernel: unsupported geometry");
+  // Static geometries: BASELINE cfg3 (resident) / cfg4 (streamed).  Run-time geometry (DynGeom): any shape of the
+  // single-CTA kernel's stride-1-window family whose weights have to stream -- always the streamed form, generic
+  // epilogue (epilogue_role), taps / K-blocks / chunk counts from Params.
   // G::w0_res == 1: the weight halves are resident for the whole kernel (BASELINE cfg3).
   // G::w0_res == 0: they stream through a ring of stages (BASELINE cfg4: 576 + 256 KB of weights).  Each CTA loads
   //   ITS half of every block (rows [r * N/2, (r+1) * N/2)), so a pair pulls every weight byte out of the L2 once
   //   per 256 positions instead of once per 128 -- the single-CTA kernel is bound by exactly that traffic -- and a
   //   stage of S bytes feeds twice the MMA work, so the latency-bound ring delivers twice the rate.  One thread of
   //   the leader issues both GEMMs in the ring's fixed order: GEMM1(it), then GEMM2(it - 1).
-  constexpr bool kResident = G::w0_res != 0;
+  constexpr bool kResident = [] {
+    if constexpr (G::is_static) return G::w0_res != 0;
+    else return false;
+  }();
+  const Geo<G> g{p};
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   PairBarriers* bar = reinterpret_cast<PairBarriers*>(smem);
@@ -2076,9 +2082,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   const int n_pair_tiles = (p.n_tiles + 1) >> 1;
   const int n_local = (n_pair_tiles - cid + ncl - 1) / ncl;
-  constexpr int kHalfRows0 = G::OC / 2, kHalfRows1 = G::nc1 / 2;
-  constexpr uint32_t kW0Half = kHalfRows0 * G::swb, kW1Half = kHalfRows1 * G::swb1;
-  constexpr int kNW0 = 9 * G::nkb, kNW1 = G::n_chunks * G::nkb1;
+  const int kHalfRows0 = g.OC() / 2, kHalfRows1 = g.nc1() / 2;
+  const uint32_t kW0Half = kHalfRows0 * g.swb(), kW1Half = kHalfRows1 * g.swb1();
+  const bool c0_only = !G::is_static && p.conv0_only != 0;  // conv-only operator: no GEMM2 at all
+  const int kNW0 = g.KH() * g.KW() * g.nkb(), kNW1 = c0_only ? 0 : g.n_chunks() * g.nkb1();
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxAStages; ++i) {
@@ -2116,7 +2123,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after_sync();
   const uint32_t tmem = bar->tmem_base;
   const int q_first = p.q_first;
-  const uint32_t a_origin = (uint32_t)p.Wp * G::swb;  // tile origin inside a halo stage (same in both CTAs)
+  const uint32_t a_origin = (uint32_t)p.Wp * g.swb();  // tile origin inside a halo stage (same in both CTAs)
 
   if (warp == 0) {
     // ================================ halo producer (both CTAs) ================================
@@ -2129,29 +2136,31 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(smem_u32(&bar->a_empty[s]), ((it / p.SA) & 1) ^ 1);
         tr.ev(1);
         const int q0 = q_first + tile * kTileM;
-        const int g_lo = (q0 - p.Wp - 1) / p.Wp;
-        const int g_hi = (q0 + kTileM + p.Wp) / p.Wp;
+        const int q_halo = q0 - g.PH() * p.Wp - g.PW();  // first position the tile's taps read
+        const int g_lo = q_halo / p.Wp;
+        const int g_hi = (q0 + kTileM - 1 + (g.KH() - 1 - g.PH()) * p.Wp + (g.KW() - 1 - g.PW())) / p.Wp;
         const int nrows = g_hi - g_lo + 1;
-        const int a_off_px = (q0 - p.Wp - 1) - g_lo * p.Wp;
+        const int a_off_px = q_halo - g_lo * p.Wp;
         const uint32_t leader_full = mapa_u32(smem_u32(&bar->a_full[s]), 0);
-        mbar_expect_tx_cluster(leader_full, (uint32_t)(nrows * G::nkb * p.Wp * G::swb));
+        mbar_expect_tx_cluster(leader_full, (uint32_t)(nrows * g.nkb() * p.Wp * g.swb()));
         int n = (g_lo > 0) ? (g_lo - 1) / p.Hp : 0;
-        int h = (g_lo > 0) ? (g_lo - 1) - n * p.Hp - 1 : -2;
-        uint32_t dst = sbase + p.off_a + s * p.a_stage_bytes + a_origin - (uint32_t)a_off_px * G::swb;
-        const uint32_t row_bytes = p.Wp * G::swb;
+        int h = (g_lo > 0) ? (g_lo - 1) - n * p.Hp - p.ZR : -p.ZR - 1;  // see conv_fused_kernel's halo producer
+        uint32_t dst = sbase + p.off_a + s * p.a_stage_bytes + a_origin - (uint32_t)a_off_px * g.swb();
+        const uint32_t row_bytes = p.Wp * g.swb();
         for (int r = 0; r < nrows; ++r, dst += row_bytes) {
 #pragma unroll
-          for (int kb = 0; kb < G::nkb; ++kb) tma_load_4d_pair(dst + kb * p.a_kb_stride, &tmA, leader_full, kb * G::swb, 0, h, n);
-          if (h == -2) {
-            h = -1;
+          for (int kb = 0; kb < g.nkb(); ++kb) tma_load_4d_pair(dst + kb * p.a_kb_stride, &tmA, leader_full, kb * g.swb(), 0, h, n);
+          if (h == -p.ZR - 1) {
+            h = -p.ZR;
           } else if (++h == p.H) {
-            h = -1;
+            h = -p.ZR;
             ++n;
           }
         }
       }
     }
-  } else if (warp == 2 && !kResident) {
+  } else if (warp == 2) {
+   if constexpr (!kResident) {
     // ============================ streamed weight halves (both CTAs) ===========================
     if (elect_one()) {
       uint32_t s = 0, ph = 1;  // stage cursor and the parity to wait for on this CTA's b_empty
@@ -2164,12 +2173,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
       for (int it = 0; it <= n_local; ++it) {  // same order as the MMA thread below
         if (it < n_local)
-          for (int b = 0; b < kNW0; ++b) load_half(&tmW0, kW0Half, b * G::OC + (int)rank * kHalfRows0);
+          for (int b = 0; b < kNW0; ++b) load_half(&tmW0, kW0Half, b * g.OC() + (int)rank * kHalfRows0);
         if (it >= 1)
-          for (int b = 0; b < kNW1; ++b) load_half(&tmW1, kW1Half, b * G::nc1 + (int)rank * kHalfRows1);
+          for (int b = 0; b < kNW1; ++b) load_half(&tmW1, kW1Half, b * g.nc1() + (int)rank * kHalfRows1);
       }
     }
-  } else if (warp == 2) {
+   } else {
     // ============================ resident weight halves (both CTAs) ===========================
     if (elect_one()) {
       // four parts with their own barriers, so that GEMM1 of the first tile starts after a third of W0
@@ -2231,13 +2240,15 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1 && !kResident) {
+   }
+  } else if (warp == 1) {
+   if constexpr (!kResident) {
     // ====================== MMA issuer, streamed weights (leader only): GEMM1(it), GEMM2(it - 1) ======================
     if (rank == 0 && elect_one()) {
-      const uint32_t idesc0 = make_idesc_i8(2 * kTileM, G::OC, 0, 1), idesc1 = make_idesc_i8(2 * kTileM, G::nc1, 0, 1);
-      const uint64_t desc0_hi = make_smem_desc(0, 16, 8 * G::swb, layout_of(G::swb));
-      const uint64_t desc1_hi = make_smem_desc(0, 16, 8 * G::swb1, layout_of(G::swb1));
-      const uint32_t a_step_kw = G::swb >> 4, a_step_kh = (p.Wp * G::swb) >> 4, a_step_kb = p.a_kb_stride >> 4;
+      const uint32_t idesc0 = make_idesc_i8(2 * kTileM, g.OC(), 0, 1), idesc1 = make_idesc_i8(2 * kTileM, g.nc1(), 0, 1);
+      const uint64_t desc0_hi = make_smem_desc(0, 16, 8 * g.swb(), layout_of(g.swb()));
+      const uint64_t desc1_hi = make_smem_desc(0, 16, 8 * g.swb1(), layout_of(g.swb1()));
+      const uint32_t a_step_kw = g.swb() >> 4, a_step_kh = (p.Wp * g.swb()) >> 4, a_step_kb = p.a_kb_stride >> 4;
       const uint64_t bst0_desc = desc0_hi | ((sbase + p.off_b) >> 4), bst1_desc = desc1_hi | ((sbase + p.off_b) >> 4);
       const uint64_t mid_desc = desc1_hi | ((sbase + p.off_mid) >> 4);
       const uint32_t b_stage_step = p.b_stage_bytes >> 4;
@@ -2246,26 +2257,26 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t sa = 0, a_par = 0, bs = 0, bph = 0, c1count = 0;
       for (int it = 0; it <= n_local; ++it) {
         if (it < n_local) {
-          const int ab = it % G::n_acc0;
-          mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / G::n_acc0) & 1) ^ 1);
+          const int ab = it % g.n_acc0();
+          mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / g.n_acc0()) & 1) ^ 1);
           mbar_wait(smem_u32(&bar->a_full[sa]), a_par);
           tc_fence_after_sync();
           tr.ev(10);
-          const uint32_t d0 = tmem + ab * G::OC;
+          const uint32_t d0 = tmem + ab * g.OC();
           const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_origin) >> 4);
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh) {
+          for (int kh = 0; kh < g.KH(); ++kh) {
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
+            for (int kw = 0; kw < g.KW(); ++kw) {
 #pragma unroll
-              for (int kb = 0; kb < G::nkb; ++kb) {
-                const int blk = (kh * 3 + kw) * G::nkb + kb;
+              for (int kb = 0; kb < g.nkb(); ++kb) {
+                const int blk = (kh * g.KW() + kw) * g.nkb() + kb;
                 mbar_wait(smem_u32(&bar->b_full[bs]), bph);
                 tc_fence_after_sync();
                 const uint64_t b_desc = bst0_desc + (uint64_t)(bs * b_stage_step);
                 const uint64_t a_desc = a_tile + kh * a_step_kh + kw * a_step_kw + kb * a_step_kb;
-                constexpr int nks_full = G::swb >> 5;
-                const int nks = (kb == G::nkb - 1) ? G::ks_last : nks_full;
+                const int nks_full = g.swb() >> 5;
+                const int nks = (kb == g.nkb() - 1) ? g.ks_last() : nks_full;
 #pragma unroll
                 for (int ks = 0; ks < nks; ++ks)
                   if (!dbg_flag(p, 1)) umma_i8_pair(d0, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
@@ -2279,26 +2290,26 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tr.ev(11);
           if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
         }
-        if (it >= 1) {
+        if (it >= 1 && !c0_only) {
           const int jt = it - 1, mb = jt % p.NM;
           mbar_wait(smem_u32(&bar->mid_full[mb]), (jt / p.NM) & 1);
           tc_fence_after_sync();
           tr.ev(12);
           const uint64_t mid_it = mid_desc + (uint64_t)((mb * p.mid_bytes) >> 4);
-          for (int j = 0; j < G::n_chunks; ++j, ++c1count) {
+          for (int j = 0; j < g.n_chunks(); ++j, ++c1count) {
             const uint32_t cb = c1count & 1;
             mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ (epilogue_seeds<G>() ? 0 : 1));
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
             if constexpr (seed_by_cp<G>()) seed_chunk_cp<true>(d_tmem, make_smem_desc(sbase + p.off_k1, 16, 128, kLayoutNone));
 #pragma unroll
-            for (int kb = 0; kb < G::nkb1; ++kb) {
+            for (int kb = 0; kb < g.nkb1(); ++kb) {
               mbar_wait(smem_u32(&bar->b_full[bs]), bph);
               tc_fence_after_sync();
               const uint64_t b_desc = bst1_desc + (uint64_t)(bs * b_stage_step);
-              const uint64_t a_desc = mid_it + kb * ((kTileM * G::swb1) >> 4);
-              constexpr int nks_full = G::swb1 >> 5;
-              const int nks = (kb == G::nkb1 - 1) ? G::ks1_last : nks_full;
+              const uint64_t a_desc = mid_it + kb * ((kTileM * g.swb1()) >> 4);
+              const int nks_full = g.swb1() >> 5;
+              const int nks = (kb == g.nkb1() - 1) ? g.ks1_last() : nks_full;
 #pragma unroll
               for (int ks = 0; ks < nks; ++ks)
                 if (!dbg_flag(p, 1)) umma_i8_pair(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, seeded_acc1<G>() || (kb | ks) != 0);
@@ -2312,7 +2323,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
+   } else {
     // ================================ GEMM1 issuer (leader only) ================================
     if (rank == 0 && elect_one()) {
       const uint32_t idesc0 = make_idesc_i8(2 * kTileM, G::OC, 0, 1);
@@ -2365,6 +2376,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
       }
     }
+   }
   } else if (warp >= kEpiWarp0) {
     // ================================== epilogue (both CTAs) ===================================
     load_epilogue_constants<G>(p, smem);
@@ -2454,6 +2466,7 @@ using GeoCfg4P = StaticGeom<256, 256, 1024, 0, 0, 2>;  // cfg4 on CTA pairs: wei
 // defined in conv_inst_*.cu
 KernelFn pick_pair_cfg3(int dst_dt);                                             // conv_pair_kernel<GeoCfg3P, dst>
 KernelFn pick_pair_cfg4(int dst_dt);                                             // conv_pair_kernel<GeoCfg4P, dst>
+KernelFn pick_pair_dyn(int dst_dt);                                              // conv_pair_kernel<DynGeom, dst>
 KernelFn pick_static_geom(int geom_id, int dst_dt);                              // conv_fused_kernel<GeoCfg{1,3,4}, dst>
 KernelFn pick_dynamic_u8(bool down0, bool down1, bool nan_safe);                 // conv_fused_kernel<DynGeom, ...>
 KernelFn pick_dynamic_s8(bool down0, bool down1, bool nan_safe);

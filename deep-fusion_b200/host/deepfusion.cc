@@ -706,13 +706,26 @@ public:
     const int8_t *w0 = static_cast<const int8_t *>(wei->data());
     const int8_t *w1 = wei1x1 ? static_cast<const int8_t *>(wei1x1->data()) : nullptr;
     const void *b0 = bia ? bia->data() : nullptr, *b1 = bia1x1 ? bia1x1->data() : nullptr;
-    int rc = df_conv_create_concat(&desc_, (int)cc_->ic.size(), cc_->ic.data(), concat_relu, w0, w1, b0, b1,
-                                   conv0_scales.data(), conv1_scales.data(), &cc_->handle);
-    if (rc == DF_E_UNSUPPORTED) {  // two kernels, concatenated tensor in a device buffer
-      fused_ = false;
-      rc = df_conv_create(&desc_, w0, w1, b0, b1, conv0_scales.data(), conv1_scales.data(), &cc_->handle);
-      if (rc == DF_E_UNSUPPORTED) error_and_exit("unsupported on B200 path: %s", df_last_error());
-      if (rc == 0) cuda_or_exit(df_malloc(cc_->shape->buffer_size(), &cc_->d_cat), "device allocation");
+    // Which route: the plain conv of this shape tells.  Where its weights have to stream it runs on CTA pairs, and the
+    // fused load (32 / 64-byte halo K-blocks, single-CTA kernel) is slower than concat + that kernel (measured,
+    // 48.7 vs 33.3 us on BASELINE configs[1]'s shape) -- the op then runs the two kernels back to back,
+    // the concatenated tensor staying in the L2.  DEEPFUSION_CONCAT_FUSE=1 / =0 forces the route.
+    df_conv *plain = nullptr;
+    int rc = df_conv_create(&desc_, w0, w1, b0, b1, conv0_scales.data(), conv1_scales.data(), &plain);
+    if (rc == DF_E_UNSUPPORTED) error_and_exit("unsupported on B200 path: %s", df_last_error());
+    if (rc == 0) {
+      df_conv_info ci;
+      const char *force = getenv("DEEPFUSION_CONCAT_FUSE");
+      const bool pair_route = df_conv_query(plain, &ci) == 0 && ci.w0_resident == 3;
+      const bool want_fused = force ? atoi(force) != 0 : !pair_route;
+      if (want_fused && df_conv_create_concat(&desc_, (int)cc_->ic.size(), cc_->ic.data(), concat_relu, w0, w1, b0, b1,
+                                              conv0_scales.data(), conv1_scales.data(), &cc_->handle) == 0) {
+        df_conv_destroy(plain);
+      } else {  // two kernels, concatenated tensor in a device buffer
+        fused_ = false;
+        cc_->handle = plain;
+        cuda_or_exit(df_malloc(cc_->shape->buffer_size(), &cc_->d_cat), "device allocation");
+      }
     }
     if (rc != 0) {
       info("%s", df_last_error());

@@ -588,3 +588,45 @@ def test_fused_conv_geometry_edges(df, g):
     want = _oracle_conv(c, fast=False)
     _assert_same(got, want, "u8")
     assert want.any()
+
+
+# ------------------------------------------- run-time geometry on CTA pairs (weights that have to stream)
+PAIR_DYN = [
+    # n, h, w, ic, oc, oc1, k, stride, pad, dst
+    (3, 28, 28, 256, 128, 512, 3, 1, 1, "u8"),     # the conv behind BASELINE configs[1]'s concat
+    (5, 14, 14, 256, 256, 0, 3, 1, 1, "u8"),       # conv-only, 576 KB of weights
+    (2, 14, 14, 256, 256, 0, 3, 1, 1, "s32"),
+    (3, 12, 12, 128, 128, 272, 5, 1, 2, "s8"),     # 5x5 window, ragged last conv1 chunk
+    (2, 20, 20, 128, 64, 144, 7, 2, 3, "u8"),      # 7x7 stride 2
+    (7, 7, 7, 256, 208, 528, 3, 1, 1, "f32"),      # odd tile count (one tile of the last pair is empty), oc not a multiple of 32
+    (1, 9, 40, 192, 96, 0, 3, 1, 1, "u8"),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_DYN, ids=lambda c: "x".join(str(v) for v in c))
+def test_dynamic_geometry_on_cta_pairs(df, case):
+    """Shapes whose weights do not fit one CTA's shared memory run conv_pair_kernel<DynGeom> (weight halves streamed by
+    a CTA pair); bit-exact like everything else."""
+    n, h, w, ic, oc, oc1, k, stride, pad, dst = case
+    src = cases.synth.src_u8(1, (n, h, w, ic))
+    wb = cases.layout.oihw_to_blocked(cases.synth.wei_s8(2, (oc, ic, k, k)))
+    b0 = cases.synth.bias(4, oc, "s32")
+    s0 = cases.synth.channel_scales(oc, int(np.ceil(np.log2(ic * k * k * 64.0))) - 4)
+    if oc1:
+        w1b = cases.layout.oihw_to_blocked(cases.synth.wei_s8(3, (oc1, oc)).reshape(oc1, oc, 1, 1))
+        b1 = cases.synth.bias(5, oc1, "s32")
+        s1 = cases.synth.channel_scales(oc1, int(np.ceil(np.log2(oc * 64.0 * 64))) - 6)
+    else:
+        w1b, b1, s1 = None, None, np.array([1.0], np.float32)
+    d = O.make_desc(n, h, w, ic, oc, oc1, cases.DT[dst], O.S32, O.S32 if oc1 else O.UNDEF, k=k, stride=stride, pad=pad, relu0=1,
+                    nscale0=oc, nscale1=s1.size)
+    want = O.conv(d, src, wb, b0, s0, w1b, b1, s1)
+    op = df.Conv(n, h, w, ic, oc, oc1, cases.DT[dst], wb, w1b, b0, b1, s0, s1, df.S32, df.S32 if oc1 else df.UNDEF, relu0=True,
+                 k=k, stride=stride, pad=pad)
+    assert op.info().w0_resident == 3, "expected the CTA-pair kernel with streamed weight halves"
+    got = op(src)
+    got2 = op(src)
+    op.close()
+    _assert_same(got, want, dst)
+    _assert_same(got2, want, dst)
+    assert want.any()
