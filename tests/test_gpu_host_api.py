@@ -125,10 +125,13 @@ def test_concat_feeds_conv_on_device(H):
     assert np.array_equal(dst.array(), want)
 
 
-@pytest.mark.parametrize("ics,fused", [((64, 128, 32, 32), True), ((16, 48, 64), False)], ids=["fused", "two_kernels"])
+@pytest.mark.parametrize("ics,fused", [((32, 64), True), ((64, 128, 32, 32), False), ((16, 48, 64), False)],
+                         ids=["fused", "two_kernels_pair_route", "two_kernels_channel_split"])
 def test_concat_conv_submit(H, ics, fused):
-    """ext::concat_conv through the C++ API: submit() == oracle concat followed by oracle conv; channel splits the
-    fused load cannot take (multiples of 16 that are not multiples of 32) run as two kernels with the same result."""
+    """ext::concat_conv through the C++ API: submit() == oracle concat followed by oracle conv.  The op fuses the concat
+    into the conv's halo load where that is the faster route; where the plain conv runs on CTA pairs (weights that have
+    to stream) or the channel split cannot be loaded fused (multiples of 16 that are not multiples of 32) it runs the
+    two kernels back to back -- same result."""
     from dfb200 import synth
     n, h, w, ic = 2, 14, 14, sum(ics)
     ins = [synth.uniform_int(20 + i, (n, h, w, c), 0, 255, np.uint8) for i, c in enumerate(ics)]
