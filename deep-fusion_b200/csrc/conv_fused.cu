@@ -485,7 +485,10 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   const uint32_t avail = kSmemLimit - 1024;  // base alignment slack
   // sa_min: halo stages when the weights stream (2; 1 as a last resort for shapes whose halo alone is > 100 KB --
   // loads and MMAs of successive tiles then alternate instead of overlapping)
+  int ks_split = 1;  // halo K-slices per tile (Params::n_ks): > 1 only when an unsliced halo stage cannot fit
   auto plan = [&](int nm, bool stage, int sa_min = 2) -> bool {
+    p.n_ks = ks_split;
+    p.nkb_s = p.nka / ks_split;
     uint32_t off = 1024;  // barriers
     p.off_bias0 = off;
     off += align_up(p.OC * 4, 128);
@@ -504,13 +507,13 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
     p.NM = nm;
     off += nm * p.mid_bytes;
     p.a_kb_stride = (uint32_t)p.NR * p.Wp * p.swa;
-    p.a_stage_bytes = align_up(p.nka * p.a_kb_stride, 1024);
+    p.a_stage_bytes = align_up((p.nka / ks_split) * p.a_kb_stride, 1024);
     p.w0_block_bytes = (uint32_t)p.OC * p.swb;
     p.w1_block_bytes = (uint32_t)p.nc1 * p.swb1;
     const uint32_t w0_bytes = align_up(taps * p.nkb * p.w0_block_bytes, 1024);
     const uint32_t w1_bytes = conv0_only ? 0 : align_up(p.n_chunks * p.nkb1 * p.w1_block_bytes, 1024);
     const uint32_t fixed = off;
-    if (fixed + 2 * p.a_stage_bytes + w0_bytes + w1_bytes <= avail) {
+    if (ks_split == 1 && fixed + 2 * p.a_stage_bytes + w0_bytes + w1_bytes <= avail) {
       p.w0_res = p.w1_res = 1;
       p.off_w0 = fixed;
       p.off_w1 = fixed + w0_bytes;
@@ -524,7 +527,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
       const uint32_t stage_w0 = align_up(p.w0_block_bytes, 1024);
       const uint32_t stage_both = align_up(p.w0_block_bytes > p.w1_block_bytes ? p.w0_block_bytes : p.w1_block_bytes, 1024);
       p.SA = sa_min;
-      if (fixed + p.SA * p.a_stage_bytes + w1_bytes + 3 * stage_w0 <= avail) {
+      if (ks_split == 1 && fixed + p.SA * p.a_stage_bytes + w1_bytes + 3 * stage_w0 <= avail) {
         p.w0_res = 0;
         p.w1_res = 1;
         p.off_w1 = fixed;
@@ -581,7 +584,15 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   if (!op->geom_id) {
     const bool can_stage = (d->dst_dt == DF_U8 || d->dst_dt == DF_S8) && p.nc1 == 128 && !with_sum &&
                            !(getenv("DF_NO_STAGED_STORE") && atoi(getenv("DF_NO_STAGED_STORE")) != 0);
-    if (!plan(1, can_stage) && !plan(1, can_stage, 1) && !plan(1, false, 1)) {
+    bool planned = plan(1, can_stage) || plan(1, can_stage, 1) || plan(1, false, 1);
+    // an input too deep for any halo stage: K-slice it (the fewest slices that fit two stages); not for a fused concat
+    for (int ks = 2; !planned && !fused_cat && ks <= p.nka; ++ks)
+      if (p.nka % ks == 0) {
+        ks_split = ks;
+        planned = plan(1, can_stage) || plan(1, false);
+      }
+    if (!planned) {
+      ks_split = 1;
       delete op;
       if (!conv0_only && !fused_cat)  // the two stages as two launches need less shared memory each
         return conv_create_composite(d, wei, wei1, bia0, bia1, scale0, scale1, out, with_sum);
@@ -652,7 +663,7 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   const bool pair_on = !(getenv("DF_PAIR") && atoi(getenv("DF_PAIR")) == 0);
   const bool pair4_on = pair_on && !(getenv("DF_PAIR4") && atoi(getenv("DF_PAIR4")) == 0);
   const bool pair_dyn = pair_on && !(getenv("DF_PAIR_DYN") && atoi(getenv("DF_PAIR_DYN")) == 0) && op->geom_id == 0 && !fused_cat &&
-                        p.w0_res == 0 && p.n_box == 1 && !p.nan_safe && p.round0 == DF_ROUND_NEAREST && p.round1 == DF_ROUND_NEAREST &&
+                        p.w0_res == 0 && p.n_box == 1 && p.n_ks == 1 && !p.nan_safe && p.round0 == DF_ROUND_NEAREST && p.round1 == DF_ROUND_NEAREST &&
                         p.swb == 128;  // (the pair kernel shifts the TMA destination by whole positions: 128-byte K-blocks only)
   if ((((shape_id == 3 && pair_on) || (shape_id == 4 && pair4_on)) && static_ok) || pair_dyn) {
     Params q = p;

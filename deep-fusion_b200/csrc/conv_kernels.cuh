@@ -126,6 +126,10 @@ struct Params {
   // K-blocks -- the two operand descriptors of a tcgen05.mma carry their own swizzle mode, and weight blocks of 4 KB
   // instead of 16 KB would quarter the bytes in flight of the weight ring
   int swa, nka;
+  // K-slicing of the halo (single-CTA run-time-geometry kernel): an input too deep for a halo stage (e.g. 7x7 x 2048
+  // channels: 286 KB) goes through the stages in n_ks slices of nkb_s K-blocks; GEMM1 accumulates over the slices of
+  // a tile in TMEM, weights stream in that order.  n_ks == 1 everywhere else.
+  int n_ks, nkb_s;
   unsigned char kb_src[kMaxKBlocks];
   unsigned short kb_c0[kMaxKBlocks];
 };
@@ -1594,16 +1598,19 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
   if (warp == 0) {
     // =============================== TMA producer: halo rows ===============================
     // one thread issues the per-row, per-K-block loads of local tile `it` into stage it % SA
-    auto issue_halo = [&](int it) {
+    const int n_ks = G::is_static ? 1 : p.n_ks;            // halo K-slices per tile
+    const int nkb_s = G::is_static ? g.nka() : p.nkb_s;    // halo K-blocks per slice (= all of them when n_ks == 1)
+    auto issue_halo = [&](int si) {                        // si = it * n_ks + slice
+      const int it = si / n_ks, kslice = si - it * n_ks;
       const int tile = blockIdx.x + it * gridDim.x;
-      const int s = it % p.SA;
+      const int s = si % p.SA;
       const int q0 = q_first + tile * kTileM;
       const int g_lo = (q0 - g.PH() * p.Wp - g.PW()) / p.Wp;
       const int g_hi = (q0 + kTileM - 1 + (g.KH() - 1 - g.PH()) * p.Wp + (g.KW() - 1 - g.PW())) / p.Wp;
       const int nrows = g_hi - g_lo + 1;
       const uint32_t full = smem_u32(&bar->a_full[s]);
       const uint32_t stage = sbase + p.off_a + s * p.a_stage_bytes;
-      mbar_expect_tx(full, (uint32_t)(nrows * g.nka() * p.Wp * g.swa()));
+      mbar_expect_tx(full, (uint32_t)(nrows * nkb_s * p.Wp * g.swa()));
       // row g >= 1 of the padded space is row hp = (g - 1) % Hp of image (g - 1) / Hp, i.e. source row h = hp - ZR
       // (negative: one of the zero rows above the image, filled by the TMA unit); g = 0 is all zero
       int n = (g_lo > 0) ? (g_lo - 1) / p.Hp : 0;
@@ -1615,12 +1622,12 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
           for (int kb = 0; kb < g.nka(); ++kb)
             tma_load_4d(dst + kb * p.a_kb_stride, &tmS.m[p.kb_src[kb]], full, (int)p.kb_c0[kb], 0, h, n);
         } else if (!G::is_static && p.n_box > 1) {
-          for (int kb = 0; kb < g.nka(); ++kb)
+          for (int kb = 0; kb < nkb_s; ++kb)
             for (int bx = 0; bx < p.n_box; ++bx)
-              tma_load_4d(dst + kb * p.a_kb_stride + bx * p.box_w * g.swa(), &tmS.m[0], full, kb * g.swa(), bx * p.box_w, h, n);
+              tma_load_4d(dst + kb * p.a_kb_stride + bx * p.box_w * g.swa(), &tmS.m[0], full, (kslice * nkb_s + kb) * g.swa(), bx * p.box_w, h, n);
         } else {
 #pragma unroll
-          for (int kb = 0; kb < g.nka(); ++kb) tma_load_4d(dst + kb * p.a_kb_stride, &tmS.m[0], full, kb * g.swa(), 0, h, n);
+          for (int kb = 0; kb < nkb_s; ++kb) tma_load_4d(dst + kb * p.a_kb_stride, &tmS.m[0], full, (kslice * nkb_s + kb) * g.swa(), 0, h, n);
         }
         if (h == -p.ZR - 1) {
           h = -p.ZR;  // g = 1: first row (zero row, if any) of image 0
@@ -1634,10 +1641,10 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
       if (elect_one()) {
         Tracer tr(p, 0);
         griddep_wait();  // the source may have been written by the previous kernel in the stream
-        for (int it = 0; it < n_local; ++it) {
-          mbar_wait(smem_u32(&bar->a_empty[it % p.SA]), ((it / p.SA) & 1) ^ 1);
+        for (int si = 0; si < n_local * n_ks; ++si) {
+          mbar_wait(smem_u32(&bar->a_empty[si % p.SA]), ((si / p.SA) & 1) ^ 1);
           tr.ev(1);
-          issue_halo(it);
+          issue_halo(si);
         }
       }
     } else {
@@ -1714,7 +1721,12 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
         uint32_t s = 0, ph = 1;  // stage cursor and the parity to wait for on b_empty
         for (int it = 0; it <= n_local; ++it) {  // same interleaving as the MMA thread below
           if (it < n_local && !g.w0_res())
-            for (int b = 0; b < n_w0; ++b) {
+            for (int i = 0; i < n_w0; ++i) {
+              int b = i;  // block id = tap * nkb + kb; with a K-sliced halo the MMA thread goes slice, tap, kb-in-slice
+              if (!G::is_static && p.n_ks > 1) {
+                const int per = n_w0 / p.n_ks, ksl = i / per, r = i - ksl * per, tap = r / p.nkb_s;
+                b = tap * g.nkb() + ksl * p.nkb_s + (r - tap * p.nkb_s);
+              }
               mbar_wait(smem_u32(&bar->b_empty[s]), ph);
               mbar_expect_tx(smem_u32(&bar->b_full[s]), g.w0_block_bytes());
               tma_load_2d(sbase + p.off_b + s * p.b_stage_bytes, &tmW0, smem_u32(&bar->b_full[s]), 0, b * g.OC());
@@ -1797,13 +1809,16 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
       //      weights in order
       uint32_t tap_i = 0;  // taps issued so far (GEMM1 throttle, all-resident plan only: see kG1Ahead)
       const bool throttle = g.w0_res() && g.w1_res();
-      auto gemm1_taps = [&](int kh, int kw0, int kw1, uint32_t d_tmem, uint64_t a_tile) {
+      const int n_ks = G::is_static ? 1 : p.n_ks, nkb_s = g.nkb() / n_ks;  // halo K-slices (Params::n_ks): weight K-blocks per slice
+      auto gemm1_taps = [&](int kh, int kw0, int kw1, uint32_t d_tmem, uint64_t a_tile, int kslice = 0) {
         for (int kw = kw0; kw < kw1; ++kw) {
           if (throttle && tap_i >= (uint32_t)kG1Ahead)
             mbar_wait(smem_u32(&bar->g1_prog[tap_i % kG1Ahead]), ((tap_i / kG1Ahead) - 1) & 1);
 #pragma unroll
-          for (int kb = 0; kb < g.nkb(); ++kb) {
-            const int blk = (kh * g.KW() + kw) * g.nkb() + kb;  // block index inside the tile
+          for (int kbl = 0; kbl < nkb_s; ++kbl) {
+            const int kb = kslice * nkb_s + kbl;                // K-block of the reduction; kbl: its place in the halo stage
+            const int blk = (kh * g.KW() + kw) * g.nkb() + kb;  // weight block index inside the tile
+            const int first = (kh * g.KW() + kw) | kbl | kslice;  // 0 only for the tile's very first block
             uint64_t b_desc;
             uint32_t st = 0;
             if (g.w0_res()) {
@@ -1817,16 +1832,16 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
             const uint64_t a_tap = a_tile + kh * a_step_kh + kw * a_step_kw;
             const int nks = (kb == g.nkb() - 1) ? g.ks_last() : nks_full;
             if (G::is_static || g.swa() == g.swb()) {
-              const uint64_t a_desc = a_tap + kb * a_step_kb;
+              const uint64_t a_desc = a_tap + kbl * a_step_kb;
 #pragma unroll
-              for (int ks = 0; ks < nks; ++ks) if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+              for (int ks = 0; ks < nks; ++ks) if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (first | ks) != 0);
             } else {  // narrower A K-blocks (fused concat): K-step ks of weight block kb lives in A block k32 / a_ks_per_block
               // (swa divides swb, both powers of two: A block / step inside it by shift and mask, descriptors by addition)
               uint64_t a_blk = a_tap + (uint64_t)(((kb * nks_full) >> a_ks_shift) * a_step_kb);
               int kr = 0;
 #pragma unroll 4
               for (int ks = 0; ks < nks; ++ks) {
-                if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_blk + 2 * kr, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+                if (!dbg_flag(p, 1)) umma_i8(d_tmem, a_blk + 2 * kr, b_desc + 2 * ks, idesc0, (first | ks) != 0);
                 if (++kr == a_ks_per_block) { kr = 0; a_blk += a_step_kb; }
               }
             }
@@ -1878,17 +1893,19 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
         for (int it = 0; it < n_local; ++it) {
           const int ab = it % g.n_acc0();
           mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / g.n_acc0()) & 1) ^ 1);
-          mbar_wait(a_go + 8 * sa, a_par);
-          tc_fence_after_sync();
-          tr.ev(10);
           const uint32_t d_tmem = tmem + ab * g.OC();
-          const uint64_t a_tile = desca_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swa()) >> 4);
+          for (int kslice = 0; kslice < n_ks; ++kslice) {  // (one pass unless the halo is K-sliced)
+            mbar_wait(a_go + 8 * sa, a_par);
+            tc_fence_after_sync();
+            tr.ev(10);
+            const uint64_t a_tile = desca_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swa()) >> 4);
 #pragma unroll
-          for (int kh = 0; kh < g.KH(); ++kh) gemm1_taps(kh, 0, g.KW(), d_tmem, a_tile);
-          umma_commit(smem_u32(&bar->a_empty[sa]));
+            for (int kh = 0; kh < g.KH(); ++kh) gemm1_taps(kh, 0, g.KW(), d_tmem, a_tile, kslice);
+            umma_commit(smem_u32(&bar->a_empty[sa]));
+            if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
+          }
           umma_commit(smem_u32(&bar->acc0_full[ab]));
           tr.ev(11);
-          if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
           a_off_px += p.tile_step_mod;
           if (a_off_px >= p.Wp) a_off_px -= p.Wp;
         }
@@ -1970,17 +1987,19 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
           if (it < n_local) {
             const int ab = it % g.n_acc0();
             mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / g.n_acc0()) & 1) ^ 1);
-            mbar_wait(a_go + 8 * sa, a_par);
-            tc_fence_after_sync();
-            tr.ev(10);
             const uint32_t d_tmem = tmem + ab * g.OC();
-            const uint64_t a_tile = desca_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swa()) >> 4);
+            for (int kslice = 0; kslice < n_ks; ++kslice) {  // (one pass unless the halo is K-sliced)
+              mbar_wait(a_go + 8 * sa, a_par);
+              tc_fence_after_sync();
+              tr.ev(10);
+              const uint64_t a_tile = desca_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_off_px * g.swa()) >> 4);
 #pragma unroll
-            for (int kh = 0; kh < g.KH(); ++kh) gemm1_taps(kh, 0, g.KW(), d_tmem, a_tile);
-            umma_commit(smem_u32(&bar->a_empty[sa]));
+              for (int kh = 0; kh < g.KH(); ++kh) gemm1_taps(kh, 0, g.KW(), d_tmem, a_tile, kslice);
+              umma_commit(smem_u32(&bar->a_empty[sa]));
+              if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
+            }
             umma_commit(smem_u32(&bar->acc0_full[ab]));
             tr.ev(11);
-            if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
             a_off_px += p.tile_step_mod;
             if (a_off_px >= p.Wp) a_off_px -= p.Wp;
           }

@@ -630,3 +630,37 @@ def test_dynamic_geometry_on_cta_pairs(df, case):
     _assert_same(got, want, dst)
     _assert_same(got2, want, dst)
     assert want.any()
+
+
+# --------------------------------------------------------------- inputs too deep for one halo stage (K-sliced)
+DEEP = [
+    # n, h, w, ic, oc, oc1, k, pad, dst
+    (2, 7, 7, 2048, 256, 0, 1, 0, "u8"),        # ResNet stage-4 1x1: a 7x7 x 2048 halo is 286 KB
+    (1, 7, 7, 2048, 2048, 0, 1, 0, "s32"),      # test/test_conv_relu_pooling.cc:341 (1x1 2048 -> 2048), eight channel groups
+    (2, 14, 14, 1024, 64, 0, 3, 1, "u8"),
+    (2, 9, 9, 1536, 64, 144, 3, 1, "u8"),       # fused, three K-slices
+]
+
+
+@pytest.mark.parametrize("case", DEEP, ids=lambda c: "x".join(str(v) for v in c))
+def test_deep_inputs_are_k_sliced(df, case):
+    n, h, w, ic, oc, oc1, k, pad, dst = case
+    src = cases.synth.src_u8(1, (n, h, w, ic))
+    wb = cases.layout.oihw_to_blocked(cases.synth.wei_s8(2, (oc, ic, k, k)))
+    b0 = cases.synth.bias(4, oc, "s32")
+    s0 = cases.synth.channel_scales(oc, int(np.ceil(np.log2(ic * k * k * 64.0))) - 4)
+    if oc1:
+        w1b = cases.layout.oihw_to_blocked(cases.synth.wei_s8(3, (oc1, oc)).reshape(oc1, oc, 1, 1))
+        b1 = cases.synth.bias(5, oc1, "s32")
+        s1 = cases.synth.channel_scales(oc1, 12)
+    else:
+        w1b, b1, s1 = None, None, np.array([1.0], np.float32)
+    d = O.make_desc(n, h, w, ic, oc, oc1, cases.DT[dst], O.S32, O.S32 if oc1 else O.UNDEF, k=k, pad=pad, relu0=1, nscale0=oc,
+                    nscale1=s1.size)
+    want = O.conv(d, src, wb, b0, s0, w1b, b1, s1)
+    op = df.Conv(n, h, w, ic, oc, oc1, cases.DT[dst], wb, w1b, b0, b1, s0, s1, df.S32, df.S32 if oc1 else df.UNDEF, relu0=True,
+                 k=k, pad=pad)
+    got = op(src)
+    op.close()
+    _assert_same(got, want, dst)
+    assert want.any()
