@@ -58,6 +58,8 @@ def lib():
         l.dfh_conv_pool_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
                                            C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                            C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int]
+        l.dfh_pool_create.restype = C.c_void_p
+        l.dfh_pool_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
         l.dfh_conv_sum_create.restype = C.c_void_p
         l.dfh_conv_sum_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int,
@@ -185,6 +187,12 @@ def conv_pool(src, wei, bia, stride, padding, conv_dst, pool_dst, kind, pool_ker
                                    i2(pool_kernel), i2(pool_stride), i2(pool_padding), int(conv_relu),
                                    s0.ctypes.data_as(C.POINTER(C.c_float)), s0.size, conv_round_mode, pool_round_mode)
     return Op(h, (src, wei, bia, conv_dst, pool_dst))
+
+
+def pool(src, dst, kind, pool_kernel, pool_stride, pool_padding, pool_round_mode=NEAREST) -> Op:
+    """deepfusion::ext::pool: the pooling stage on its own."""
+    i2 = lambda v: (C.c_int * 2)(*v)
+    return Op(lib().dfh_pool_create(src.h, dst.h, kind, i2(pool_kernel), i2(pool_stride), i2(pool_padding), pool_round_mode), (src, dst))
 
 
 def conv_sum(src, wei, bia, stride, padding, residual, dst, wei1x1=None, bia1x1=None, conv0_relu=True, conv0_scales=(1.0,),

@@ -837,6 +837,51 @@ private:
   df_pool_desc pd_;
 };
 
+// the pooling stage alone (df_pool_run) as an operator of its own: what follows a conv_sum in the reference's ResNet entry
+// (test/test_conv_relu_pooling.cc:341-342: 1x1 conv + eltwise sum + ReLU + 7x7 average pooling)
+class pool_op : public detail::device_op {
+public:
+  pool_op(const std::unique_ptr<memory> &src, std::unique_ptr<memory> &dst, int kind, std::array<int, 2> k, std::array<int, 2> st,
+          std::array<int, 2> pad, round_mode rm)
+      : src_(src.get()), dst_(dst.get()) {
+    if (!src || !dst || src->dim_format() != memory::format::nhwc || dst->dim_format() != memory::format::nhwc ||
+        src->data_type() != dst->data_type()) {
+      info("Pooling needs nhwc source and destination of one data type");
+      error_and_exit("Init Pooling op failed!");
+    }
+    const memory::dims c = src->actual_dims(), o = dst->actual_dims();
+    memset(&pd_, 0, sizeof pd_);
+    pd_.dtype = detail::dt_code(src->data_type());
+    pd_.kind = kind;
+    pd_.n = c[0]; pd_.h = c[1]; pd_.w = c[2]; pd_.c = c[3];
+    pd_.kh = k[0]; pd_.kw = k[1]; pd_.sh = st[0]; pd_.sw = st[1]; pd_.ph = pad[0]; pd_.pw = pad[1];
+    pd_.oh = o.size() == 4 ? o[1] : 0;
+    pd_.ow = o.size() == 4 ? o[2] : 0;
+    pd_.round_mode = rm == round_mode::down ? DF_ROUND_DOWN : DF_ROUND_NEAREST;
+    if (o.size() != 4 || o[0] != c[0] || o[3] != c[3] || df_pool_check(&pd_) != 0) {
+      info("Pooling output size do not match: %s", df_last_error());
+      error_and_exit("Init Pooling op failed!");
+    }
+  }
+  void launch(void *stream) override {
+    cuda_or_exit(df_pool_run(&pd_, mirror(*src_), mirror(*dst_), pd_.n, stream), "pool launch");
+  }
+  int launches() const override { return 1; }
+
+protected:
+  void infer() override {
+    cuda_or_exit(df_h2d(mirror(*src_), src_->data(), src_->buffer_size(), nullptr), "pool H2D");
+    launch(nullptr);
+    cuda_or_exit(df_d2h(dst_->data(), mirror(*dst_), dst_->buffer_size(), nullptr), "pool D2H");
+    cuda_or_exit(df_stream_sync(nullptr), "pool sync");
+  }
+  const char *name() override { return "pooling"; }
+
+private:
+  memory *src_, *dst_;
+  df_pool_desc pd_;
+};
+
 // conv / fused conv + eltwise sum + ReLU (README.md:65): `residual` has dst's dims and type and is added to the scaled
 // result before the ReLU (df_conv_create_sum / df_conv_run_sum).
 class conv_sum_op : public conv_op {
@@ -997,6 +1042,11 @@ std::unique_ptr<op> conv_pool(const std::unique_ptr<memory> &src, const std::uni
                               round_mode pool_round_mode) {
   return std::unique_ptr<op>(new conv_pool_op(src, wei, bia, sz_stride, sz_padding, conv_dst, pool_dst, (int)kind, pool_kernel,
                                               pool_stride, pool_padding, conv_relu, conv_scales, conv_round_mode, pool_round_mode));
+}
+std::unique_ptr<op> pool(const std::unique_ptr<memory> &src, std::unique_ptr<memory> &dst, pool_kind kind,
+                         std::array<int, 2> pool_kernel, std::array<int, 2> pool_stride, std::array<int, 2> pool_padding,
+                         round_mode pool_round_mode) {
+  return std::unique_ptr<op>(new pool_op(src, dst, (int)kind, pool_kernel, pool_stride, pool_padding, pool_round_mode));
 }
 std::unique_ptr<op> conv_sum(const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei,
                              const std::unique_ptr<memory> &bia, std::array<int, 2> sz_stride, std::array<int, 2> sz_padding,

@@ -112,6 +112,11 @@ dfh_op *dfh_conv_pool_create(dfh_memory *src, dfh_memory *wei, dfh_memory *bia, 
                         (round_mode)r0, (round_mode)pool_round);
   return h;
 }
+dfh_op *dfh_pool_create(dfh_memory *src, dfh_memory *dst, int kind, const int pk[2], const int ps[2], const int pp[2], int pool_round) {
+  dfh_op *h = new dfh_op();
+  h->o = ext::pool(src->m, dst->m, (ext::pool_kind)kind, {pk[0], pk[1]}, {ps[0], ps[1]}, {pp[0], pp[1]}, (round_mode)pool_round);
+  return h;
+}
 dfh_op *dfh_conv_sum_create(dfh_memory *src, dfh_memory *wei, dfh_memory *bia, const int stride[2], const int padding[2],
                             dfh_memory *wei1x1, dfh_memory *bia1x1, dfh_memory *residual, dfh_memory *dst, int conv0_relu,
                             const float *s0, int n0, int r0, int conv1_relu, const float *s1, int n1, int r1) {

@@ -50,6 +50,9 @@ dfh_op *dfh_conv_pool_create(dfh_memory *src, dfh_memory *wei, dfh_memory *bia, 
                              dfh_memory *conv_dst, dfh_memory *pool_dst, int kind, const int pool_kernel[2],
                              const int pool_stride[2], const int pool_padding[2], int conv_relu, const float *conv_scales,
                              int n_conv_scales, int conv_round_mode, int pool_round_mode);
+/* ext::pool(): the pooling stage on its own */
+dfh_op *dfh_pool_create(dfh_memory *src, dfh_memory *dst, int kind, const int pool_kernel[2], const int pool_stride[2],
+                        const int pool_padding[2], int pool_round_mode);
 /* ext::conv_sum(): conv / fused conv + eltwise sum of `residual` + ReLU */
 dfh_op *dfh_conv_sum_create(dfh_memory *src, dfh_memory *wei, dfh_memory *bia, const int stride[2], const int padding[2],
                             dfh_memory *wei1x1, dfh_memory *bia1x1, dfh_memory *residual, dfh_memory *dst, int conv0_relu,

@@ -58,6 +58,10 @@ std::unique_ptr<op> conv_pool(const std::unique_ptr<memory> &src, const std::uni
                               std::array<int, 2> pool_kernel, std::array<int, 2> pool_stride, std::array<int, 2> pool_padding,
                               bool conv_relu = true, std::vector<float> conv_scales = {1.f},
                               round_mode conv_round_mode = round_mode::nearest, round_mode pool_round_mode = round_mode::nearest);
+// the pooling stage on its own (any of the four data types), e.g. behind a conv_sum:
+std::unique_ptr<op> pool(const std::unique_ptr<memory> &src, std::unique_ptr<memory> &dst, pool_kind kind,
+                         std::array<int, 2> pool_kernel, std::array<int, 2> pool_stride, std::array<int, 2> pool_padding,
+                         round_mode pool_round_mode = round_mode::nearest);
 // conv() / fused conv() + eltwise sum + ReLU: `residual` (dst's dims, format, data type) is added before the ReLU.
 // wei1x1 == nullptr selects the conv-only operator.
 std::unique_ptr<op> conv_sum(const std::unique_ptr<memory> &src, const std::unique_ptr<memory> &wei,

@@ -221,6 +221,36 @@ def test_conv_sum_submit(H, fused):
     assert np.array_equal(dst.array(), want)
 
 
+def test_resnet_entry_of_the_reference_list(H):
+    """test/test_conv_relu_pooling.cc:341-342: 1x1 conv 2048 -> 2048 @7x7 + eltwise sum + ReLU + 7x7 average pooling
+    (excluding padding), at batch 2: ext::conv_sum (K-sliced halo, eight channel groups) chained with ext::pool on the
+    device == the oracle's dfo_conv_sum followed by dfo_pool."""
+    from dfb200 import synth, layout
+    n, c = 2, 2048
+    src_a = synth.src_u8(1, (n, 7, 7, c))
+    wb = layout.oihw_to_blocked(synth.wei_s8(2, (c, c, 1, 1)))
+    b0 = synth.bias(4, c, "s32")
+    s0 = synth.channel_scales(c, 13)
+    res_a = synth.uniform_int(41, (n, 7, 7, c), 0, 255, np.uint8)
+    src = H.Memory((n, c, 7, 7), "nhwc", "u8"); src.set(src_a); src.to_device()
+    wei = H.Memory((c, c, 1, 1), "OIhw4i16o4i", "s8"); wei.array().reshape(-1)[...] = wb
+    bia = H.Memory((c,), "x", "s32", nchw=False); bia.set(b0)
+    res = H.Memory((n, c, 7, 7), "nhwc", "u8"); res.set(res_a); res.to_device()
+    mid = H.Memory((n, c, 7, 7), "nhwc", "u8")
+    dst = H.Memory((n, c, 1, 1), "nhwc", "u8")
+    conv = H.conv_sum(src, wei, bia, (1, 1), (0, 0), res, mid, conv0_scales=s0)
+    pool = H.pool(mid, dst, 2, (7, 7), (7, 7), (0, 0))
+    conv.submit_device()
+    pool.submit_device()
+    H.sync()
+    dst.to_host()
+    H.sync()
+    d = O.make_desc(n, 7, 7, c, c, 0, O.U8, O.S32, O.UNDEF, k=1, pad=0, relu0=1, nscale0=c)
+    want = O.pool(O.conv_sum(d, src_a, wb, b0, s0, res_a), 2, 7, 7, 0)
+    assert want.any() and (want < 255).any()
+    assert np.array_equal(dst.array(), want)
+
+
 def _conv_memories(H, c, n=None):
     n = n or c.n
     src_a, w0, w1, b0, b1, s0, s1 = cases.ConvCase(c.name, n, c.h, c.w, c.ic, c.oc, c.oc1, c.dst, c.b0, c.b1, c.r0, c.r1,
