@@ -1240,6 +1240,12 @@ __device__ __forceinline__ void epilogue_static(const Params& p, const DstMaps&,
   // chunk is only issued once C_{n-3}(t) has released an accumulator: anything earlier than n - 1 deadlocks.
   const int e0_pos = p.NM >= 2 ? ((DF_E0_POS) < G::n_chunks ? (DF_E0_POS) : G::n_chunks - 1) : G::n_chunks - 1;
 
+  // (Tried and dropped in the last session of round 2, each parity-green on cfg3 and with its log under profiles/:
+  //  the unit stream as a software pipeline of half units, tcgen05.ld of half x + 1 in flight under the arithmetic of
+  //  half x: 3..4 % slower, 9..14 % when the accumulator is also released after the arithmetic
+  //  (r02_variants_half_pipeline.log); E0's two barrier tests issued by the unit in front of it: no change
+  //  (r02_variants_e0_pretest.log); three conv1 accumulators + one conv0 accumulator in TMEM: 5 % slower
+  //  (r02_variants_three_acc1_buffers.log).)
   // (Tried and dropped: moving the block in four 16 x 16 pieces through a ring of register sets with the loads
   // running two pieces ahead ACROSS units -- parity-green but 6 % slower on cfg3 and 19 % on cfg1,
   // profiles/r02_variants_piece_pipeline.log: the extra loads / waits cost more issue slots than the hidden latency
@@ -1808,7 +1814,8 @@ conv_fused_kernel(const __grid_constant__ SrcMaps tmS, const __grid_constant__ C
       // ---- taps [kw0, kw1) of tap row kh of GEMM1: K-blocks x K-steps each, descriptors by addition,
       //      weights in order
       uint32_t tap_i = 0;  // taps issued so far (GEMM1 throttle, all-resident plan only: see kG1Ahead)
-      const bool throttle = g.w0_res() && g.w1_res();
+      // (the conv-only operator has no conv1 chunks that could queue behind GEMM1: no throttle there)
+      const bool throttle = g.w0_res() && g.w1_res() && !(!G::is_static && p.conv0_only != 0);
       const int n_ks = G::is_static ? 1 : p.n_ks, nkb_s = g.nkb() / n_ks;  // halo K-slices (Params::n_ks): weight K-blocks per slice
       auto gemm1_taps = [&](int kh, int kw0, int kw1, uint32_t d_tmem, uint64_t a_tile, int kslice = 0) {
         for (int kw = kw0; kw < kw1; ++kw) {

@@ -6,4 +6,5 @@ KernelFn pick_dynamic_u8(bool, bool, bool) { return KernelFn{nullptr, nullptr}; 
 KernelFn pick_dynamic_s8(bool, bool, bool) { return KernelFn{nullptr, nullptr}; }
 KernelFn pick_dynamic_s32(bool, bool, bool) { return KernelFn{nullptr, nullptr}; }
 KernelFn pick_dynamic_f32(bool, bool, bool) { return KernelFn{nullptr, nullptr}; }
+KernelFn pick_pair_dyn(int) { return KernelFn{nullptr, nullptr}; }
 }  // namespace dfconv

@@ -17,7 +17,8 @@ args = (layout.oihw_to_blocked(w0), layout.oihw_to_blocked(w1.reshape(oc1, oc, 1
         synth.bias(5, oc1, "s32"), synth.channel_scales(oc, {64: 12, 128: 13, 256: 14}[ic]), synth.channel_scales(oc1, 12))
 st = df.Stream()
 print(f"# {which}: {h}x{w} {ic}->{oc}->{oc1}, u8 out; peak = 3348 TOPS (2 x measured bf16)")
-for n in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048):
+NS = [int(x) for x in os.environ["SWEEP_NS"].split(",")] if os.environ.get("SWEEP_NS") else (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048)
+for n in NS:
     op = df.Conv(n, h, w, ic, oc, oc1, df.U8, *args, df.S32, df.S32)
     i = op.info()
     per_set = n * h * w * (ic + oc1)

@@ -11,9 +11,10 @@ TAGS = {1: "A.issue", 2: "A.landed", 3: "A.clamped", 8: "M.begin", 9: "M.start",
         40: "S.full", 41: "S.issued", 42: "S.read_done"}
 
 def run(n, h, w, ic, oc, oc1, dst="u8", cta=0, cap=512, max_lines=120, skip=0, ics=None):
-    w0 = synth.wei_s8(2, (oc, ic, 3, 3)); w1 = synth.wei_s8(3, (oc1, oc))
-    args = (layout.oihw_to_blocked(w0), layout.oihw_to_blocked(w1.reshape(oc1, oc, 1, 1)),
-            synth.bias(4, oc, "s32"), synth.bias(5, oc1, "s32"), synth.channel_scales(oc, 13), synth.channel_scales(oc1, 12), df.S32, df.S32)
+    w0 = synth.wei_s8(2, (oc, ic, 3, 3)); w1 = synth.wei_s8(3, (max(oc1, 16), oc))
+    args = (layout.oihw_to_blocked(w0), layout.oihw_to_blocked(w1.reshape(-1, oc, 1, 1)) if oc1 else None,
+            synth.bias(4, oc, "s32"), synth.bias(5, oc1, "s32") if oc1 else None, synth.channel_scales(oc, 13),
+            synth.channel_scales(oc1, 12) if oc1 else (1.0,), df.S32, df.S32 if oc1 else df.UNDEF)
     if ics:  # concat fused into the halo load
         op = df.ConcatConv(n, h, w, ics, True, oc, oc1, df.DT_OF[dst], *args)
         src = [df.DeviceBuffer.from_numpy(synth.src_u8(1 + k, (n, h, w, c))) for k, c in enumerate(ics)]
@@ -21,7 +22,7 @@ def run(n, h, w, ic, oc, oc1, dst="u8", cta=0, cap=512, max_lines=120, skip=0, i
         op = df.Conv(n, h, w, ic, oc, oc1, df.DT_OF[dst], *args)
         src = df.DeviceBuffer.from_numpy(synth.src_u8(1, (n, h, w, ic)))
     i = op.info()
-    out = df.DeviceBuffer(n * h * w * oc1 * (4 if dst in ("s32", "f32") else 1))
+    out = df.DeviceBuffer(n * h * w * (oc1 or oc) * (4 if dst in ("s32", "f32") else 1))
     for _ in range(3): op.run(src, out)
     df.sync()
     tb = df.DeviceBuffer(i.grid * 4 * cap * 8); tb.fill(0)
@@ -61,5 +62,6 @@ if __name__ == "__main__":
     if which == "cfg1": run(nb, 56, 56, 64, 64, 256)
     elif which == "cfg3": run(nb, 28, 28, 128, 128, 512, skip=skip)
     elif which == "cfg4": run(256, 14, 14, 256, 256, 1024)
+    elif which == "vgg2": run(nb, 112, 112, 64, 128, 0, skip=skip, max_lines=200)   # conv-only, 64-byte K-blocks, one chunk per tile
     elif which == "catf": run(nb, 28, 28, 256, 128, 512, skip=skip, max_lines=260, ics=(64, 128, 32, 32))
     elif which == "cat": run(nb, 28, 28, 256, 128, 512, skip=skip, max_lines=260)  # the conv behind BASELINE configs[1]'s concat (run-time geometry)
