@@ -23,6 +23,7 @@ for n in NS:
     i = op.info()
     per_set = n * h * w * (ic + oc1)
     n_sets = max(2, min(64, -(-2 * 126 * 2 ** 20 // per_set)))
+    if os.environ.get("SWEEP_SETS"): n_sets = int(os.environ["SWEEP_SETS"])  # development: 1 = the same buffers every launch (L2-resident when they fit)
     base = synth.src_u8(1, (n, h, w, ic))
     sets = [(df.DeviceBuffer.from_numpy(base), df.DeviceBuffer(n * h * w * oc1)) for _ in range(n_sets)]
     iters = 200 if n <= 256 else 40
