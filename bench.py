@@ -288,6 +288,7 @@ def time_shape(df, st, wl, steps, peaks, rank=0):
     g.launch()
     st.sync()
     e0, e1 = df.Event(), df.Event()
+    g.launch()  # untimed, keeps the stream busy while the host queues the timed replay (see the main conv leg)
     e0.record(st.ptr)
     g.launch()
     e1.record(st.ptr)
@@ -335,6 +336,7 @@ def time_concat_conv(df, st, steps, rank=0, batch=None):
         g.launch()
         st.sync()
         e0, e1 = df.Event(), df.Event()
+        g.launch()  # untimed, keeps the stream busy while the host queues the timed replay
         e0.record(st.ptr)
         g.launch()
         e1.record(st.ptr)
@@ -393,23 +395,32 @@ def run_ours(args, rank, world, local_rank):
     st = df.Stream()
     for i in range(args.warmup):
         op.run(*sets[i % n_sets], stream=st.ptr)
+    # The two timing events are nodes of the SAME graph, around exactly the K timed steps, with `lead` untimed steps in
+    # front of them: a graph replay starts ~18 us after the work before it has drained (measured: 15.0 us per step at
+    # K = 20 against 14.06 at K = 400 with the events outside the graph), which is the graph machinery's latency and not
+    # the step's; inside the graph the K steps follow the lead-in steps the way steps follow each other in a long run.
     graph = None
+    lead = max(3, args.warmup)
+    e0, e1 = df.Event(), df.Event()
     if not args.no_graph:
         with df.Graph(st) as graph:
+            for i in range(lead):
+                op.run(*sets[i % n_sets], stream=st.ptr)
+            e0.record_node(st.ptr)
             for i in range(args.steps):
-                op.run(*sets[(args.warmup + i) % n_sets], stream=st.ptr)
+                op.run(*sets[(lead + i) % n_sets], stream=st.ptr)
+            e1.record_node(st.ptr)
         graph.launch()  # untimed replay: graph upload, instruction caches
     st.sync()
     barrier(dist)
-    e0, e1 = df.Event(), df.Event()
     t_start = time.time()
-    e0.record(st.ptr)
     if graph is not None:
         graph.launch()
     else:
+        e0.record(st.ptr)
         for i in range(args.steps):
             op.run(*sets[(args.warmup + i) % n_sets], stream=st.ptr)
-    e1.record(st.ptr)
+        e1.record(st.ptr)
     st.sync()
     ms_total = e0.elapsed_ms(e1)
     t_end = time.time()
@@ -441,6 +452,8 @@ def run_ours(args, rank, world, local_rank):
         cgraph.launch()
     st.sync()
     ce0, ce1 = df.Event(), df.Event()
+    if cgraph is not None:
+        cgraph.launch()  # keeps the stream busy while the host queues the timed replay (see the conv leg)
     ce0.record(st.ptr)
     if cgraph is not None:
         cgraph.launch()
@@ -489,10 +502,10 @@ def run_ours(args, rank, world, local_rank):
         s1.record(st.ptr)
         st.sync()
         t_s1 = time.time()
-        s_ms = s0.elapsed_ms(s1) / (reps * args.steps)
+        s_ms = s0.elapsed_ms(s1) / (reps * (args.steps + lead))  # every replay runs the lead-in steps too
         s_tops = n * ops_per_image(p) / (s_ms * 1e-3) / 1e12
         peak_s = 2.0 * (peaks["bf16_sustained"] or peaks["bf16_tflops"])
-        sustained = {"seconds": s0.elapsed_ms(s1) / 1e3, "launches": reps * args.steps, "us_per_launch": s_ms * 1e3, "tops": s_tops,
+        sustained = {"seconds": s0.elapsed_ms(s1) / 1e3, "launches": reps * (args.steps + lead), "us_per_launch": s_ms * 1e3, "tops": s_tops,
                      "peak": peak_s, "frac": s_tops / peak_s, "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json",
                      "clocks": sampler.summary(t_s0, t_s1)}
 
@@ -558,7 +571,7 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "u8", "data": "synthetic", "images_per_s": total_images / (ms_step * 1e-3),
         "config": shared_config(args.workload, n, world),
         "run": {"cache": f"rotating {n_sets} src/dst buffer sets ({n_sets * (src_bytes + dst_bytes) >> 20} MiB > 2x L2) so no step finds its data in L2",
-                "launch": "plain loop of df_conv_run calls" if args.no_graph else f"{args.steps} steps captured in one CUDA graph, replayed once inside the timed region",
+                "launch": "plain loop of df_conv_run calls" if args.no_graph else f"one CUDA graph = {lead} untimed lead-in steps, event, the {args.steps} timed steps, event; replayed once between the two synchronisations (the events are graph nodes around exactly the timed steps, so the ~18 us a graph replay takes to start is not inside them)",
                 "tiles": info.tiles_per_launch, "grid": info.grid, "smem_bytes": info.smem_bytes,
                 "weights_resident": [info.w0_resident, info.w1_resident], "mma_row_efficiency": round(info.mma_efficiency, 4)},
         "roofline": {"bound": "tensor", "achieved": kernel_tops_this_rank, "peak": tensor_peak, "unit": "TOPS",

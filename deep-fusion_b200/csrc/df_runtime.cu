@@ -95,6 +95,12 @@ int df_event_record(void* e, void* s) {
   DF_CUDA(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s));
   return 0;
 }
+int df_event_record_node(void* e, void* s) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  DF_CUDA(cudaStreamIsCapturing((cudaStream_t)s, &cs));
+  DF_CUDA(cudaEventRecordWithFlags((cudaEvent_t)e, (cudaStream_t)s, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+  return 0;
+}
 int df_stream_wait_event(void* s, void* e) {
   DF_CUDA(cudaStreamWaitEvent((cudaStream_t)s, (cudaEvent_t)e, 0));
   return 0;

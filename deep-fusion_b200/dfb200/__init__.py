@@ -25,7 +25,7 @@ NP_OF = {F32: np.float32, S32: np.int32, S8: np.int8, U8: np.uint8}
 ABI_SYMBOLS = [
     "df_last_error", "df_version", "df_device_count", "df_set_device", "df_get_device", "df_device_sm_count", "df_malloc",
     "df_free", "df_memset", "df_host_register", "df_host_unregister", "df_h2d", "df_d2h", "df_stream_create",
-    "df_stream_sync", "df_stream_destroy", "df_event_create", "df_event_record", "df_stream_wait_event", "df_event_elapsed_ms",
+    "df_stream_sync", "df_stream_destroy", "df_event_create", "df_event_record", "df_event_record_node", "df_stream_wait_event", "df_event_elapsed_ms",
     "df_event_destroy", "df_concat_check", "df_concat_run", "df_conv_create", "df_conv_run", "df_conv_query", "df_conv_create_concat", "df_conv_run_concat", "df_conv_create_sum", "df_conv_run_sum", "df_pool_check", "df_pool_run",
     "df_conv_destroy", "df_conv_debug_trace", "df_graph_begin", "df_graph_end", "df_graph_launch", "df_graph_destroy",
     "df_wei_blocked_offset", "df_repack_oihw_to_blocked", "df_repack_blocked_to_oihw", "df_repack_goihw_to_blocked",
@@ -84,6 +84,7 @@ def lib():
         l.df_stream_destroy.argtypes = [C.c_void_p]
         l.df_event_create.argtypes = [C.POINTER(C.c_void_p)]
         l.df_event_record.argtypes = [C.c_void_p, C.c_void_p]
+        l.df_event_record_node.argtypes = [C.c_void_p, C.c_void_p]
         l.df_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         l.df_event_destroy.argtypes = [C.c_void_p]
         l.df_stream_wait_event.argtypes = [C.c_void_p, C.c_void_p]
@@ -189,6 +190,10 @@ class Event:
 
     def record(self, stream=None):
         check(lib().df_event_record(self.ptr, stream))
+
+    def record_node(self, stream):
+        """Inside a Graph capture: the event becomes a node of the graph, time-stamped by every replay."""
+        check(lib().df_event_record_node(self.ptr, stream))
 
     def elapsed_ms(self, later: "Event") -> float:
         ms = C.c_float(0)

@@ -54,6 +54,9 @@ int df_stream_sync(void *stream);
 int df_stream_destroy(void *stream);
 int df_event_create(void **event);
 int df_event_record(void *event, void *stream);
+/* inside a df_graph_begin / df_graph_end capture: records the event as a node of the graph (cudaEventRecordExternal), so that
+ * every replay time-stamps it and df_event_elapsed_ms works on it; outside a capture the same as df_event_record */
+int df_event_record_node(void *event, void *stream);
 int df_stream_wait_event(void *stream, void *event);
 int df_event_elapsed_ms(void *start, void *stop, float *ms); /* synchronises on `stop` */
 int df_event_destroy(void *event);
