@@ -136,8 +136,11 @@ def dist_setup(world):
         return None
     import torch
     import torch.distributed as dist
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    dist.init_process_group("nccl")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import atexit
+    atexit.register(lambda: dist.is_initialized() and dist.destroy_process_group())
     return dist
 
 
