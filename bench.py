@@ -398,21 +398,33 @@ def run_ours(args, rank, world, local_rank):
     st = df.Stream()
     for i in range(args.warmup):
         op.run(*sets[i % n_sets], stream=st.ptr)
-    # The two timing events are nodes of the SAME graph, around exactly the K timed steps, with `lead` untimed steps in
-    # front of them: a graph replay starts ~18 us after the work before it has drained (measured: 15.0 us per step at
-    # K = 20 against 14.06 at K = 400 with the events outside the graph), which is the graph machinery's latency and not
-    # the step's; inside the graph the K steps follow the lead-in steps the way steps follow each other in a long run.
+    # The K timed steps are nodes of one CUDA graph together with `lead` untimed steps in front of them and one behind,
+    # and the two timing events are nodes of the same graph on a forked stream: e0 fires when the last lead-in step
+    # completes, e1 when the last timed step completes -- exactly K step periods of a stream of launches that overlap the way
+    # back-to-back df_conv_run calls do (programmatic dependent launch: step k+1's prologue and weight loads run under step
+    # k's tail).  Events outside the graph, or events as nodes IN the chain of launches, put the graph's start-up latency
+    # (~18 us) or one non-overlapped fill + drain (~16 us) inside a 20-step region: 15.0 / 14.85 us per step at K = 20
+    # against 14.03 at K = 200 (measured); on the forked stream K = 20 and K = 200 agree.
     graph = None
     lead = max(3, args.warmup)
     e0, e1 = df.Event(), df.Event()
     if not args.no_graph:
+        side = df.Stream()
+        fork0, fork1, join = df.Event(), df.Event(), df.Event()  # capture-internal ordering markers
         with df.Graph(st) as graph:
             for i in range(lead):
                 op.run(*sets[i % n_sets], stream=st.ptr)
-            e0.record_node(st.ptr)
+            fork0.record(st.ptr)
+            df.check(df.lib().df_stream_wait_event(side.ptr, fork0.ptr))
+            e0.record_node(side.ptr)
             for i in range(args.steps):
                 op.run(*sets[(lead + i) % n_sets], stream=st.ptr)
-            e1.record_node(st.ptr)
+            fork1.record(st.ptr)
+            df.check(df.lib().df_stream_wait_event(side.ptr, fork1.ptr))
+            e1.record_node(side.ptr)
+            op.run(*sets[(lead + args.steps) % n_sets], stream=st.ptr)  # untimed: the last timed step ends the way the others do
+            join.record(side.ptr)
+            df.check(df.lib().df_stream_wait_event(st.ptr, join.ptr))
         graph.launch()  # untimed replay: graph upload, instruction caches
     st.sync()
     barrier(dist)
@@ -505,10 +517,10 @@ def run_ours(args, rank, world, local_rank):
         s1.record(st.ptr)
         st.sync()
         t_s1 = time.time()
-        s_ms = s0.elapsed_ms(s1) / (reps * (args.steps + lead))  # every replay runs the lead-in steps too
+        s_ms = s0.elapsed_ms(s1) / (reps * (args.steps + lead + 1))  # every replay runs the lead-in and the trailing step too
         s_tops = n * ops_per_image(p) / (s_ms * 1e-3) / 1e12
         peak_s = 2.0 * (peaks["bf16_sustained"] or peaks["bf16_tflops"])
-        sustained = {"seconds": s0.elapsed_ms(s1) / 1e3, "launches": reps * (args.steps + lead), "us_per_launch": s_ms * 1e3, "tops": s_tops,
+        sustained = {"seconds": s0.elapsed_ms(s1) / 1e3, "launches": reps * (args.steps + lead + 1), "us_per_launch": s_ms * 1e3, "tops": s_tops,
                      "peak": peak_s, "frac": s_tops / peak_s, "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json",
                      "clocks": sampler.summary(t_s0, t_s1)}
 
@@ -574,7 +586,7 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "u8", "data": "synthetic", "images_per_s": total_images / (ms_step * 1e-3),
         "config": shared_config(args.workload, n, world),
         "run": {"cache": f"rotating {n_sets} src/dst buffer sets ({n_sets * (src_bytes + dst_bytes) >> 20} MiB > 2x L2) so no step finds its data in L2",
-                "launch": "plain loop of df_conv_run calls" if args.no_graph else f"one CUDA graph = {lead} untimed lead-in steps, event, the {args.steps} timed steps, event; replayed once between the two synchronisations (the events are graph nodes around exactly the timed steps, so the ~18 us a graph replay takes to start is not inside them)",
+                "launch": "plain loop of df_conv_run calls" if args.no_graph else f"one CUDA graph = {lead} untimed lead-in steps, the {args.steps} timed steps, one untimed trailing step; the two timing events are nodes of the same graph on a forked stream (first fires when the last lead-in step completes, second when the last timed step completes = exactly {args.steps} step periods of back-to-back launches); replayed once between the two synchronisations",
                 "tiles": info.tiles_per_launch, "grid": info.grid, "smem_bytes": info.smem_bytes,
                 "weights_resident": [info.w0_resident, info.w1_resident], "mma_row_efficiency": round(info.mma_efficiency, 4)},
         "roofline": {"bound": "tensor", "achieved": kernel_tops_this_rank, "peak": tensor_peak, "unit": "TOPS",
