@@ -83,7 +83,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // (measured: 3-5x on both MMA issue and epilogue math, profiles/r01_trace_*.log).
 // kBackoffNs > 0 adds a sleep between polls: a poller shares its scheduler with working warps (ncu: the
 // 16 pollers of the first accumulator wait alone executed 10 % of the kernel's instructions).
-template <int kBackoffNs = 32>
+// (A/B in round 2, cfg3 through the static epilogue: 0 / 8 / 32 / 128 ns -> 13.94 / 14.10 / 14.08 / 14.28 us at batch 64,
+// identical from batch 256 up: with the early barrier tests only ONE lane per warp ever polls, and the sleep's
+// granularity costs more than the polls' issue slots; profiles/r02_variants_poll_backoff.log)
+#ifndef DF_EPI_BACKOFF_NS
+#define DF_EPI_BACKOFF_NS 0
+#endif
+template <int kBackoffNs = DF_EPI_BACKOFF_NS>
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   if (__all_sync(0xffffffffu, mbar_test_wait(bar, parity))) return;
   if ((threadIdx.x & 31) == 0) {
