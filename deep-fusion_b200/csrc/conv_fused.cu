@@ -336,6 +336,8 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   p.OC = d->oc;
   p.OC1 = conv0_only ? d->oc : d->oc1;  // destination channels
   p.conv0_only = conv0_only ? 1 : 0;
+  p.w1_pack = 1;
+  p.g_interleave = 0;
 #if DF_DIAG
   p.dbg_no_mma = getenv("DF_DEBUG_NO_MMA") ? atoi(getenv("DF_DEBUG_NO_MMA")) : 0;  // bit 0: no MMA, 1: no TMA stores, 2: no staging writes
 #else
@@ -692,10 +694,12 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
       q.b_stage_bytes = 0;
       op->pair_smem = q.off_b + 1024;
     } else {
-      q.SA = 2;
+      q.SA = getenv("DF_PAIR_SA") ? atoi(getenv("DF_PAIR_SA")) : 2;  // (development knob)
       q.off_b = q.off_a + q.SA * q.a_stage_bytes;
       const uint32_t half0 = q.w0_block_bytes / 2, half1 = q.w1_block_bytes / 2;
       q.b_stage_bytes = align_up(half0 > half1 ? half0 : half1, 1024);
+      q.g_interleave = (!conv0_only && !getenv("DF_NO_INTERLEAVE")) ? 1 : 0;
+      q.w1_pack = (!conv0_only && half1 % 1024 == 0 && 2 * half1 <= q.b_stage_bytes && q.nkb1 % 2 == 0 && !getenv("DF_NO_W1_PACK")) ? 2 : 1;
       const int sb = q.off_b < avail ? (int)((avail - q.off_b) / q.b_stage_bytes) : 0;
       ok = sb >= 2;
       q.SB = sb > kMaxBStages ? kMaxBStages : sb;

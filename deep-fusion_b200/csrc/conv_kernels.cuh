@@ -99,6 +99,8 @@ struct Params {
   uint32_t off_mid, mid_bytes, mid_kb_stride;
   uint32_t off_w0, w0_block_bytes, off_w1, w1_block_bytes;
   uint32_t off_b, b_stage_bytes;
+  int g_interleave;  // streamed CTA-pair kernel: GEMM2(it - 1)'s chunks and GEMM1(it)'s taps alternate in the ring's order
+  int w1_pack;  // streamed CTA-pair kernel: conv1 K-blocks (weight halves) per ring stage (1, or 2 when two fit and nkb1 is even)
   int relu1, round0, round1, nan_safe;
   int dbg_no_mma;      // diagnostic (DF_DEBUG_NO_MMA=1): skip every tcgen05.mma, keep the hand-offs; results are garbage
   int conv0_only;      // conv() without the 1x1 stage (include/deepfusion.h:121-129): the 3x3 accumulator goes
@@ -2197,11 +2199,38 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_load_2d_pair(sbase + p.off_b + s * p.b_stage_bytes, tm, leader_full, 0, row);
         if (++s == (uint32_t)p.SB) { s = 0; ph ^= 1; }
       };
-      for (int it = 0; it <= n_local; ++it) {  // same order as the MMA thread below
-        if (it < n_local)
-          for (int b = 0; b < kNW0; ++b) load_half(&tmW0, kW0Half, b * g.OC() + (int)rank * kHalfRows0);
-        if (it >= 1)
-          for (int b = 0; b < kNW1; ++b) load_half(&tmW1, kW1Half, b * g.nc1() + (int)rank * kHalfRows1);
+      auto load_w0_tap = [&](int t) __attribute__((always_inline)) {
+        for (int kb = 0; kb < g.nkb(); ++kb) load_half(&tmW0, kW0Half, (t * g.nkb() + kb) * g.OC() + (int)rank * kHalfRows0);
+      };
+      // conv1 half-blocks are smaller than a stage (half as big for the BASELINE shapes): w1_pack of them share one, so
+      // that a stage feeds as many MMA cycles in GEMM2 as in GEMM1 and the ring's refill latency is covered there too
+      auto load_w1_chunk = [&](int j) __attribute__((always_inline)) {
+        const int pack = p.w1_pack;
+        for (int b = j * g.nkb1(); b < (j + 1) * g.nkb1(); b += pack) {
+          mbar_wait(smem_u32(&bar->b_empty[s]), ph);
+          const uint32_t leader_full = mapa_u32(smem_u32(&bar->b_full[s]), 0);
+          mbar_expect_tx_cluster(leader_full, (uint32_t)pack * kW1Half);
+          for (int q = 0; q < pack; ++q)
+            tma_load_2d_pair(sbase + p.off_b + s * p.b_stage_bytes + q * kW1Half, &tmW1, leader_full, 0, (b + q) * g.nc1() + (int)rank * kHalfRows1);
+          if (++s == (uint32_t)p.SB) { s = 0; ph ^= 1; }
+        }
+      };
+      const int n_taps = g.KH() * g.KW(), n_ch = c0_only ? 0 : g.n_chunks();
+      for (int it = 0; it <= n_local; ++it) {  // same order as the MMA thread below (see there)
+        const bool has_g1 = it < n_local, has_g2 = it >= 1 && n_ch > 0;
+        if (p.g_interleave && has_g1 && has_g2) {
+          load_w0_tap(0);
+          int t = 1;
+          for (int j = 0; j < n_ch; ++j) {
+            load_w1_chunk(j);
+            for (const int upto = 1 + ((j + 1) * (n_taps - 1)) / n_ch; t < upto; ++t) load_w0_tap(t);
+          }
+        } else {
+          if (has_g1)
+            for (int t = 0; t < n_taps; ++t) load_w0_tap(t);
+          if (has_g2)
+            for (int j = 0; j < n_ch; ++j) load_w1_chunk(j);
+        }
       }
     }
    } else {
@@ -2281,71 +2310,125 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       Tracer tr(p, 1);
       tr.ev(9);
       uint32_t sa = 0, a_par = 0, bs = 0, bph = 0, c1count = 0;
-      for (int it = 0; it <= n_local; ++it) {
-        if (it < n_local) {
-          const int ab = it % g.n_acc0();
-          mbar_wait(smem_u32(&bar->acc0_empty[ab]), ((it / g.n_acc0()) & 1) ^ 1);
-          mbar_wait(smem_u32(&bar->a_full[sa]), a_par);
+      // GEMM1 of tile it: begin (accumulator + halo ready), one tap at a time, end (halo stage and accumulator handed on)
+      int g1_ab = 0;
+      uint32_t g1_d0 = 0;
+      uint64_t g1_a_tile = 0;
+      auto g1_begin = [&](int it) __attribute__((always_inline)) {
+        g1_ab = it % g.n_acc0();
+        mbar_wait(smem_u32(&bar->acc0_empty[g1_ab]), ((it / g.n_acc0()) & 1) ^ 1);
+        mbar_wait(smem_u32(&bar->a_full[sa]), a_par);
+        tc_fence_after_sync();
+        tr.ev(10);
+        g1_d0 = tmem + g1_ab * g.OC();
+        g1_a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_origin) >> 4);
+      };
+      auto g1_tap = [&](int kh, int kw) __attribute__((always_inline)) {
+#pragma unroll
+        for (int kb = 0; kb < g.nkb(); ++kb) {
+          const int blk = (kh * g.KW() + kw) * g.nkb() + kb;
+          mbar_wait(smem_u32(&bar->b_full[bs]), bph);
           tc_fence_after_sync();
-          tr.ev(10);
-          const uint32_t d0 = tmem + ab * g.OC();
-          const uint64_t a_tile = desc0_hi | ((sbase + p.off_a + sa * p.a_stage_bytes + a_origin) >> 4);
+          const uint64_t b_desc = bst0_desc + (uint64_t)(bs * b_stage_step);
+          const uint64_t a_desc = g1_a_tile + kh * a_step_kh + kw * a_step_kw + kb * a_step_kb;
+          const int nks_full = g.swb() >> 5;
+          const int nks = (kb == g.nkb() - 1) ? g.ks_last() : nks_full;
 #pragma unroll
-          for (int kh = 0; kh < g.KH(); ++kh) {
-#pragma unroll
-            for (int kw = 0; kw < g.KW(); ++kw) {
-#pragma unroll
-              for (int kb = 0; kb < g.nkb(); ++kb) {
-                const int blk = (kh * g.KW() + kw) * g.nkb() + kb;
-                mbar_wait(smem_u32(&bar->b_full[bs]), bph);
-                tc_fence_after_sync();
-                const uint64_t b_desc = bst0_desc + (uint64_t)(bs * b_stage_step);
-                const uint64_t a_desc = a_tile + kh * a_step_kh + kw * a_step_kw + kb * a_step_kb;
-                const int nks_full = g.swb() >> 5;
-                const int nks = (kb == g.nkb() - 1) ? g.ks_last() : nks_full;
-#pragma unroll
-                for (int ks = 0; ks < nks; ++ks)
-                  if (!dbg_flag(p, 1)) umma_i8_pair(d0, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
-                umma_commit_pair(smem_u32(&bar->b_empty[bs]));
-                if (++bs == (uint32_t)p.SB) { bs = 0; bph ^= 1; }
-              }
-            }
-          }
-          umma_commit_pair(smem_u32(&bar->a_empty[sa]));
-          umma_commit_pair(smem_u32(&bar->acc0_full[ab]));
-          tr.ev(11);
-          if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
+          for (int ks = 0; ks < nks; ++ks)
+            if (!dbg_flag(p, 1)) umma_i8_pair(g1_d0, a_desc + 2 * ks, b_desc + 2 * ks, idesc0, (blk | ks) != 0);
+          umma_commit_pair(smem_u32(&bar->b_empty[bs]));
+          if (++bs == (uint32_t)p.SB) { bs = 0; bph ^= 1; }
         }
-        if (it >= 1 && !c0_only) {
-          const int jt = it - 1, mb = jt % p.NM;
-          mbar_wait(smem_u32(&bar->mid_full[mb]), (jt / p.NM) & 1);
-          tc_fence_after_sync();
-          tr.ev(12);
-          const uint64_t mid_it = mid_desc + (uint64_t)((mb * p.mid_bytes) >> 4);
-          for (int j = 0; j < g.n_chunks(); ++j, ++c1count) {
-            const uint32_t cb = c1count & 1;
-            mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ (epilogue_seeds<G>() ? 0 : 1));
+      };
+      auto g1_end = [&]() __attribute__((always_inline)) {
+        umma_commit_pair(smem_u32(&bar->a_empty[sa]));
+        umma_commit_pair(smem_u32(&bar->acc0_full[g1_ab]));
+        tr.ev(11);
+        if (++sa == (uint32_t)p.SA) { sa = 0; a_par ^= 1; }
+      };
+      // GEMM2 of tile jt: begin (intermediate tile ready), one chunk at a time, end (intermediate tile handed back)
+      int g2_mb = 0;
+      uint64_t g2_mid = 0;
+      auto g2_begin = [&](int jt) __attribute__((always_inline)) {
+        g2_mb = jt % p.NM;
+        mbar_wait(smem_u32(&bar->mid_full[g2_mb]), (jt / p.NM) & 1);
+        tc_fence_after_sync();
+        tr.ev(12);
+        g2_mid = mid_desc + (uint64_t)((g2_mb * p.mid_bytes) >> 4);
+      };
+      auto g2_chunk = [&]() __attribute__((always_inline)) {
+        const uint32_t cb = c1count & 1;
+        mbar_wait(smem_u32(&bar->acc1_empty[cb]), ((c1count >> 1) & 1) ^ (epilogue_seeds<G>() ? 0 : 1));
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
+        if constexpr (seed_by_cp<G>()) seed_chunk_cp<true>(d_tmem, make_smem_desc(sbase + p.off_k1, 16, 128, kLayoutNone));
+        const int pack = p.w1_pack;
+#pragma unroll
+        for (int kb = 0; kb < g.nkb1(); ++kb) {
+          const int q = kb & (pack - 1);  // position inside the ring stage (pack is 1 or 2, see the loader)
+          if (q == 0) {
+            mbar_wait(smem_u32(&bar->b_full[bs]), bph);
             tc_fence_after_sync();
-            const uint32_t d_tmem = tmem + kAcc1Col + cb * kAcc1Stride;
-            if constexpr (seed_by_cp<G>()) seed_chunk_cp<true>(d_tmem, make_smem_desc(sbase + p.off_k1, 16, 128, kLayoutNone));
-#pragma unroll
-            for (int kb = 0; kb < g.nkb1(); ++kb) {
-              mbar_wait(smem_u32(&bar->b_full[bs]), bph);
-              tc_fence_after_sync();
-              const uint64_t b_desc = bst1_desc + (uint64_t)(bs * b_stage_step);
-              const uint64_t a_desc = mid_it + kb * ((kTileM * g.swb1()) >> 4);
-              const int nks_full = g.swb1() >> 5;
-              const int nks = (kb == g.nkb1() - 1) ? g.ks1_last() : nks_full;
-#pragma unroll
-              for (int ks = 0; ks < nks; ++ks)
-                if (!dbg_flag(p, 1)) umma_i8_pair(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, seeded_acc1<G>() || (kb | ks) != 0);
-              umma_commit_pair(smem_u32(&bar->b_empty[bs]));
-              if (++bs == (uint32_t)p.SB) { bs = 0; bph ^= 1; }
-            }
-            umma_commit_pair(smem_u32(&bar->acc1_full[cb]));
-            tr.ev(13);
           }
-          umma_commit_pair(smem_u32(&bar->mid_empty[mb]));
+          const uint64_t b_desc = bst1_desc + (uint64_t)(bs * b_stage_step) + (uint64_t)((q * kW1Half) >> 4);
+          const uint64_t a_desc = g2_mid + kb * ((kTileM * g.swb1()) >> 4);
+          const int nks_full = g.swb1() >> 5;
+          const int nks = (kb == g.nkb1() - 1) ? g.ks1_last() : nks_full;
+#pragma unroll
+          for (int ks = 0; ks < nks; ++ks)
+            if (!dbg_flag(p, 1)) umma_i8_pair(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc1, seeded_acc1<G>() || (kb | ks) != 0);
+          if (q == pack - 1) {
+            umma_commit_pair(smem_u32(&bar->b_empty[bs]));
+            if (++bs == (uint32_t)p.SB) { bs = 0; bph ^= 1; }
+          }
+        }
+        umma_commit_pair(smem_u32(&bar->acc1_full[cb]));
+        tr.ev(13);
+        ++c1count;
+      };
+      auto g2_end = [&]() __attribute__((always_inline)) { umma_commit_pair(smem_u32(&bar->mid_empty[g2_mb])); };
+      // Order of issue = order of the ring.  GEMM1(it) as a block followed by GEMM2(it - 1) as a block serialises the two
+      // pipelines: during GEMM1 the epilogue has nothing but E0 to do, during GEMM2 the tensor pipe waits for the
+      // epilogue chunk by chunk (two conv1 accumulators) -- a cfg4 pair-tile took 22 k cycles for 13.3 k of MMA and ~11 k
+      // of epilogue.  Interleaved (g_interleave), chunk j of GEMM2(it - 1) is followed by the next ~taps / chunks taps of
+      // GEMM1(it): while the epilogue works on a chunk the tensor pipe runs a tap.  Dependencies are unchanged: the first
+      // tap needs E0(it - 1) to have read the conv0 accumulator (it has: chunk 0 needed its result), E0(it) needs the
+      // last tap, which follows the last chunk, which needs C_{n-3}(it - 1) -- all earlier in the epilogue's unit stream.
+      const int n_taps = g.KH() * g.KW(), n_ch = c0_only ? 0 : g.n_chunks();
+      for (int it = 0; it <= n_local; ++it) {
+        const bool has_g1 = it < n_local, has_g2 = it >= 1 && n_ch > 0;
+        if (p.g_interleave && has_g1 && has_g2) {
+          int t = 0, kh = 0, kw = 0;
+          auto taps_upto = [&](int upto) __attribute__((always_inline)) {
+            for (; t < upto; ++t) {
+              g1_tap(kh, kw);
+              if (++kw == g.KW()) { kw = 0; ++kh; }
+            }
+          };
+          g1_begin(it);  // the first tap goes ahead of chunk 0: it only needs E0(it - 1) to have READ the accumulator
+          taps_upto(1);
+          g2_begin(it - 1);
+          for (int j = 0; j < n_ch; ++j) {
+            g2_chunk();
+            taps_upto(1 + ((j + 1) * (n_taps - 1)) / n_ch);
+          }
+          g2_end();
+          g1_end();
+        } else {
+          if (has_g1) {
+            g1_begin(it);
+#pragma unroll
+            for (int kh = 0; kh < g.KH(); ++kh) {
+#pragma unroll
+              for (int kw = 0; kw < g.KW(); ++kw) g1_tap(kh, kw);
+            }
+            g1_end();
+          }
+          if (has_g2) {
+            g2_begin(it - 1);
+            for (int j = 0; j < n_ch; ++j) g2_chunk();
+            g2_end();
+          }
         }
       }
     }
