@@ -600,6 +600,10 @@ PAIR_DYN = [
     (2, 20, 20, 128, 64, 144, 7, 2, 3, "u8"),      # 7x7 stride 2
     (7, 7, 7, 256, 208, 528, 3, 1, 1, "f32"),      # odd tile count (one tile of the last pair is empty), oc not a multiple of 32
     (1, 9, 40, 192, 96, 0, 3, 1, 1, "u8"),
+    # the interleaved issue / ring order (GEMM2 chunks and GEMM1 taps alternate) at its edges:
+    (40, 14, 14, 256, 256, 1024, 1, 1, 0, "u8"),   # ONE tap, eight chunks: nothing to interleave after the leading tap; many tiles per pair
+    (9, 13, 13, 256, 256, 1024, 2, 1, 0, "s32"),   # four taps over eight chunks (2x2 window)
+    (33, 14, 14, 256, 256, 128, 3, 1, 1, "u8"),    # nine taps behind ONE chunk
 ]
 
 
