@@ -391,7 +391,9 @@ static int conv_create_impl(const df_conv_desc* d, int n_src, const int* src_ic,
   p.dst_ch0 = 0;
   p.nc1 = p.OC1 < 128 ? p.OC1 : 128;
   p.n_chunks = (p.OC1 + p.nc1 - 1) / p.nc1;
-  p.n_acc0 = d->oc <= 128 ? 2 : 1;
+  // two conv0 accumulators when both fit: always for oc <= 128; the conv-only operator has no conv1 accumulators in the
+  // other half of the TMEM, so there also for oc <= 256 (GEMM1 of the next tile then runs under this tile's epilogue)
+  p.n_acc0 = (d->oc <= 128 || (conv0_only && d->oc <= 256 && !getenv("DF_NO_C0_DOUBLE"))) ? 2 : 1;
   p.relu1 = conv0_only ? d->relu0 : d->relu1;
   p.round0 = d->round0;
   p.round1 = conv0_only ? d->round0 : d->round1;
