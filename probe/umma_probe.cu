@@ -562,6 +562,7 @@ int main(int argc, char** argv) {
     for (int sh : {1, 4, 8, 9, 30, 59}) run_bench_one<128>(prop.multiProcessorCount, sh, 128);
     for (int sh : {0, 1, 2, 9, 58}) run_bench_one<64>(prop.multiProcessorCount, sh, 64);
     for (int sh : {1, 9}) run_bench_one<256>(prop.multiProcessorCount, sh, 128);
+    for (int sh : {0, 1, 58}) run_bench_one<128>(prop.multiProcessorCount, sh, 64);  // 64-byte K-blocks at N = 128 (ic = 64 -> oc = 128 shapes)
   }
   printf("probe done, failing groups: %d\n", fails);
   return 0;
